@@ -1,0 +1,219 @@
+"""Generate tests/golden/*.npz by EXECUTING the unmodified reference classes.
+
+Run in the build container (where /root/reference is mounted):
+    python oracle/make_golden.py
+The reference has no tests, fixtures or golden vectors of its own, so
+these files -- reference inputs and the reference's own outputs -- are what pins the oracle
+and, through it, the CUDA path on machines where /root/reference does not exist.
+
+TEST INFRASTRUCTURE ONLY.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+
+_spec = importlib.util.spec_from_file_location(
+    "_b2s_synth",
+    os.path.join(ROOT, "a-2d-lidar-based-slam-system-for-wheeled-mobile-robots_b200", "synth.py"))
+synth = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(synth)
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _counting_icp(params):
+    cls = ref_loader.load_icp_class(params)
+    obj = cls()
+    calls = {"n": 0}
+    inner = obj.findNearest
+
+    def counted(src, tar):
+        calls["n"] += 1
+        return inner(src, tar)
+
+    obj.findNearest = counted
+    return obj, calls
+
+
+def icp_pairs_golden():
+    """(i) whole-pipeline ICP.process on seeded pairs, both parameter sets."""
+    cases = []
+    # (seed, beams, pairs, max_iter, tolerance)
+    plan = [
+        (7101, 120, 6, 30, 0.001),   # real simulator beam count, node defaults
+        (7102, 120, 3, 10, 0.0),     # W7 launch parameters: never breaks early
+        (7001, 360, 1, 10, 0.0),     # cfg 1 as launched by W7 icp.launch
+        (7001, 360, 1, 30, 0.001),   # cfg 1 with the defaults W8/W9/W12 silently use
+        (7103, 360, 1, 30, 0.001),
+    ]
+    for seed, beams, pairs, max_iter, tol in plan:
+        tar, src, truth = synth.icp_pairs(seed, pairs, beams)
+        for p in range(pairs):
+            icp, calls = _counting_icp({"/icp/tolerance": tol, "/icp/max_iter": max_iter})
+            assert icp.max_iter == max_iter
+            T = icp.process(synth.homogeneous(tar[p].astype(np.float64)),
+                            synth.homogeneous(src[p].astype(np.float64)))
+            cases.append(dict(tar=tar[p], src=src[p], T=np.asarray(T, dtype=np.float64),
+                              iters=calls["n"], max_iter=max_iter, tol=tol, seed=seed,
+                              truth=truth[p]))
+            print("icp seed=%d beams=%d pair=%d iters=%d" % (seed, beams, p, calls["n"]))
+    # unequal cloud sizes (N != M): the virtual-scan ICP of W9 localization.py:152-157
+    tar, src, _ = synth.icp_pairs(7104, 1, 150)
+    icp, calls = _counting_icp({})
+    T = icp.process(synth.homogeneous(tar[0].astype(np.float64)),
+                    synth.homogeneous(src[0][:, :97].astype(np.float64)))
+    cases.append(dict(tar=tar[0], src=src[0][:, :97], T=np.asarray(T), iters=calls["n"],
+                      max_iter=30, tol=0.001, seed=7104, truth=np.zeros(3)))
+    blob = {"count": len(cases)}
+    for i, c in enumerate(cases):
+        for k, v in c.items():
+            blob["%d_%s" % (i, k)] = v
+    np.savez_compressed(os.path.join(OUT, "icp_pairs.npz"), **blob)
+
+
+def nearest_and_fit_golden():
+    """(ii) findNearest incl. exact ties, (iii) getTransform incl. reflection-branch inputs."""
+    rng = np.random.Generator(np.random.PCG64(8101))
+    icp = ref_loader.load_icp_class({})()
+    blob = {}
+    # ties: duplicated targets and symmetric layouts (lowest index must win)
+    tar = rng.uniform(-5, 5, size=(40, 2)).astype(np.float32).astype(np.float64)
+    tar[17] = tar[3]
+    tar[30] = tar[3]
+    tar[25] = tar[9]
+    src = rng.uniform(-5, 5, size=(60, 2)).astype(np.float32).astype(np.float64)
+    src[0] = tar[3]                       # zero distance onto a triplicated target
+    src[1] = (tar[9] + np.array([0.25, 0.0]))
+    sym_t = np.array([[1.0, 0.0], [-1.0, 0.0], [0.0, 1.0], [0.0, -1.0], [1.0, 0.0]])
+    sym_s = np.array([[0.0, 0.0], [0.5, 0.5], [-0.5, 0.5], [0.0, 2.0]])
+    d, i = icp.findNearest(src, tar)
+    blob.update(tie_src=src, tie_tar=tar, tie_dist=d, tie_idx=np.asarray(i, dtype=np.int64))
+    d, i = icp.findNearest(sym_s, sym_t)
+    blob.update(sym_src=sym_s, sym_tar=sym_t, sym_dist=d, sym_idx=np.asarray(i, dtype=np.int64))
+    # fits: random rigid motions, pure reflections of the cloud (forces det(U Vt) < 0), noise
+    fs, ft, fT = [], [], []
+    for k in range(24):
+        n = 50
+        a = rng.normal(0, 2.0, size=(n, 2))
+        th = rng.uniform(-np.pi, np.pi)
+        c, s = np.cos(th), np.sin(th)
+        b = a @ np.array([[c, s], [-s, c]]) + rng.uniform(-1, 1, size=2)
+        if k % 3 == 1:
+            b = b * np.array([1.0, -1.0])          # mirrored target -> reflection branch
+        if k % 3 == 2:
+            b = b + rng.normal(0, 0.3, size=b.shape)
+        fs.append(a)
+        ft.append(b)
+        fT.append(np.asarray(icp.getTransform(a, b)))
+    blob.update(fit_src=np.array(fs), fit_tar=np.array(ft), fit_T=np.array(fT))
+    np.savez_compressed(os.path.join(OUT, "icp_pieces.npz"), **blob)
+
+
+def bresenham_golden():
+    """(iv) rasteriser: every (dx,dy) with |dx|,|dy| <= 24 in all octants, a dx<=96 sweep of the
+    first octant (where float64 != integer Bresenham shows up), long random segments."""
+    _, bres = ref_loader.load_mapping_classes()
+    segs = []
+    for dx in range(-24, 25):
+        for dy in range(-24, 25):
+            segs.append((100, 100, 100 + dx, 100 + dy))
+    for dx in range(25, 97):
+        for dy in range(0, dx + 1):
+            segs.append((7, -3, 7 + dx, -3 + dy))
+    rng = np.random.Generator(np.random.PCG64(8201))
+    for _ in range(400):
+        x0, y0 = rng.integers(-50, 700, size=2)
+        x1, y1 = rng.integers(-50, 700, size=2)
+        segs.append((int(x0), int(y0), int(x1), int(y1)))
+    segs = np.array(segs, dtype=np.int32)
+    offs = [0]
+    cells = []
+    for x0, y0, x1, y1 in segs:
+        path = bres([int(x0), int(y0)], [int(x1), int(y1)]).path
+        cells.extend(path)
+        offs.append(len(cells))
+    np.savez_compressed(os.path.join(OUT, "bresenham.npz"), segs=segs,
+                        offsets=np.array(offs, dtype=np.int64),
+                        cells=np.array(cells, dtype=np.int32).reshape(-1, 2))
+    print("bresenham segments=%d cells=%d" % (len(segs), len(cells)))
+
+
+def _edge_beams(rng, n, cx, cy):
+    """Endpoints that exercise every branch of Mapping.update around a sensor at (cx, cy)."""
+    ang = np.linspace(-np.pi, np.pi, n)
+    r = rng.uniform(0.3, 9.0, size=n)
+    ox = cx + r * np.cos(ang)
+    oy = cy + r * np.sin(ang)
+    ox[0], oy[0] = cx + 0.004, cy + 0.003          # same cell as the sensor: no update at all
+    ox[1], oy[1] = cx + 30.0, cy + 0.5             # endpoint far outside: ray clipped, no hit
+    ox[2], oy[2] = -10.05, cy                      # x in (-10.1,-10): truncation toward zero -> cell 0
+    ox[3], oy[3] = cx, -10.07
+    ox[4], oy[4] = np.inf, cy                      # skipped ([MAP]:30)
+    ox[5], oy[5] = -np.inf, cy                     # skipped as well (isinf)
+    ox[6], oy[6] = 9.999, 9.999                    # last in-map cell
+    ox[7], oy[7] = 10.0, 10.0                      # first out-of-map cell (index 200)
+    ox[8], oy[8] = -25.0, -25.0                    # negative cells
+    ox[9], oy[9] = cx + 0.1, cy                    # one-cell step
+    return ox.astype(np.float32), oy.astype(np.float32)
+
+
+def mapping_golden():
+    """(v) Mapping.update on the reference's own 200x200 / 0.1 m map, (vi) +4 variant."""
+    rng = np.random.Generator(np.random.PCG64(8301))
+    blob = {}
+    for tag, loader in (("w20", ref_loader.load_mapping_classes),
+                        ("w4", ref_loader.load_mapping_online_classes)):
+        Mapping, _ = loader()
+        m = Mapping(200, 200, 0.1)
+        centers = [(0.0, 0.0), (3.0, 3.0), (-9.96, 9.93), (2.7, 2.7), (-10.04, -10.02),
+                   (0.05, 0.0), (0.05, 0.0), (0.05, 0.0)]
+        oxs, oys = [], []
+        for (cx, cy) in centers:
+            ox, oy = _edge_beams(rng, 120, cx, cy)
+            oxs.append(ox)
+            oys.append(oy)
+            pm = m.update(ox.astype(np.float64), oy.astype(np.float64),
+                          float(np.float32(cx)), float(np.float32(cy)))
+        blob[tag + "_ox"] = np.array(oxs)
+        blob[tag + "_oy"] = np.array(oys)
+        blob[tag + "_cx"] = np.array([c[0] for c in centers], dtype=np.float32)
+        blob[tag + "_cy"] = np.array([c[1] for c in centers], dtype=np.float32)
+        blob[tag + "_datamap"] = np.array(m.datamap)
+        blob[tag + "_pmap"] = np.array(pm).astype(np.int8)
+        print(tag, "occupied", int((np.array(pm) == 100).sum()), "free", int((np.array(pm) == 0).sum()))
+    # (vi) threshold crossings of the +0.01 stream: 1000 traversals stay free, 1001 flip
+    Mapping, _ = ref_loader.load_mapping_classes()
+    m = Mapping(200, 200, 0.1)
+    ox = np.array([1.05], dtype=np.float32)
+    oy = np.array([0.05], dtype=np.float32)
+    snaps = {}
+    for k in range(1, 1003):
+        pm = m.update(ox.astype(np.float64), oy.astype(np.float64), 0.05, 0.05)
+        if k in (1000, 1001, 1002):
+            snaps[k] = (float(m.datamap[105][100]), int(pm[105][100]))
+    blob["miss_stream_counts"] = np.array(sorted(snaps), dtype=np.int64)
+    blob["miss_stream_score"] = np.array([snaps[k][0] for k in sorted(snaps)])
+    blob["miss_stream_pmap"] = np.array([snaps[k][1] for k in sorted(snaps)], dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "mapping.npz"), **blob)
+
+
+def main():
+    if not ref_loader.available():
+        raise SystemExit("reference tree not found at %s" % ref_loader.REF_ROOT)
+    os.makedirs(OUT, exist_ok=True)
+    bresenham_golden()
+    nearest_and_fit_golden()
+    mapping_golden()
+    icp_pairs_golden()
+
+
+if __name__ == "__main__":
+    main()
