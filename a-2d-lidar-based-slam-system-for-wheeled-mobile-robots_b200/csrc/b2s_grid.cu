@@ -1,0 +1,355 @@
+// Occupancy-grid kernels: Bresenham ray-cast into int32 hit/miss planes, finalize, ROS packing.
+//
+// Replaces Mapping.update ([MAP]:22-51) with bresenham ([BRES]:2-58) inlined.  Cell indices are
+// bit-exact against the reference: the world->cell transform and the Bresenham error term are
+// evaluated in float64 with the reference's operation order, one sequential recurrence per beam.
+//
+// Layout in HBM: hit, miss int32 [xw][yw] x-major (reference datamap[x][y]); endpoints ox, oy
+// float32 [scans][beams] (SoA, as the reference passes two arrays); sensor positions cx, cy
+// float32 [scans].  One lane per beam, so a warp reads 32 consecutive endpoints (coalesced) and
+// its 32 rays fan out from the same sensor cell.
+#include "b2s_common.cuh"
+
+namespace b2s {
+
+int g_grid_variant = 2;  // 1: one RED per visit; 2: warp-aggregated runs (default)
+
+// ------------------------------------------------------------------------------------------
+// Per-beam setup shared by all variants.
+
+struct Beam {
+    int major0;   // canonical start, major axis (ascending trace direction, [BRES]:19-29)
+    int minor0;   // canonical start, minor axis
+    int span;     // major-axis steps; the path has span+1 cells
+    int inc;      // minor step direction ([BRES]:40-43)
+    int hit_k;    // canonical index of the obstacle cell: span, or 0 when the trace was flipped
+    int steep;    // major axis is y ([BRES]:14-17)
+    double slope; // dy / float(dx) in float64 ([BRES]:35)
+};
+
+enum BeamStatus { BEAM_OK = 0, BEAM_NOOP = 1, BEAM_NONFINITE = 2, BEAM_TOO_LONG = 3, BEAM_INF_SKIP = 4 };
+
+// [MAP]:33-36  int(S * (v + H)): float64 add, then multiply, then truncate toward zero.
+__device__ __forceinline__ double cell_coord(float v, double cells_per_m, double off)
+{
+    return __dmul_rn(cells_per_m, __dadd_rn((double)v, off));
+}
+
+__device__ __forceinline__ int beam_setup(float fox, float foy, float fcx, float fcy, int xw, int yw,
+                                          double cells_per_m, double off_x, double off_y, Beam &b)
+{
+    if (isinf(fox)) return BEAM_INF_SKIP;  // [MAP]:30 tests ox only
+    if (isnan(fox) || !isfinite(foy) || !isfinite(fcx) || !isfinite(fcy)) return BEAM_NONFINITE;
+    const double dxo = cell_coord(fox, cells_per_m, off_x), dyo = cell_coord(foy, cells_per_m, off_y);
+    const double dxc = cell_coord(fcx, cells_per_m, off_x), dyc = cell_coord(fcy, cells_per_m, off_y);
+    const double lim = 1073741824.0;  // 2^30: keeps every difference inside int32
+    if (!(fabs(dxo) < lim && fabs(dyo) < lim && fabs(dxc) < lim && fabs(dyc) < lim)) return BEAM_TOO_LONG;
+    int x0 = __double2int_rz(dxc), y0 = __double2int_rz(dyc);  // sensor cell
+    int x1 = __double2int_rz(dxo), y1 = __double2int_rz(dyo);  // obstacle cell
+    if (x0 == x1 && y0 == y1) return BEAM_NOOP;                // [BRES]:10-11 empty path
+    // no cell of the segment's bounding box inside the grid -> nothing to update
+    if (max(x0, x1) < 0 || min(x0, x1) >= xw || max(y0, y1) < 0 || min(y0, y1) >= yw) return BEAM_NOOP;
+    const int steep = abs(y1 - y0) > abs(x1 - x0);
+    if (steep) {
+        int t = x0; x0 = y0; y0 = t;
+        t = x1; x1 = y1; y1 = t;
+    }
+    const int flipped = x0 > x1;
+    if (flipped) {
+        int t = x0; x0 = x1; x1 = t;
+        t = y0; y0 = y1; y1 = t;
+    }
+    b.span = x1 - x0;
+    if (b.span > B2S_MAX_PATH_CELLS) return BEAM_TOO_LONG;
+    b.major0 = x0;
+    b.minor0 = y0;
+    b.inc = (y0 < y1) ? 1 : -1;
+    b.hit_k = flipped ? 0 : b.span;
+    b.steep = steep;
+    b.slope = __ddiv_rn((double)abs(y1 - y0), (double)b.span);
+    return BEAM_OK;
+}
+
+__device__ __forceinline__ void count_status(int st, int32_t *counters)
+{
+    if (counters == nullptr) return;
+    if (st == BEAM_NONFINITE) atomicAdd(&counters[B2S_CNT_NONFINITE], 1);
+    if (st == BEAM_TOO_LONG) atomicAdd(&counters[B2S_CNT_TOO_LONG], 1);
+    if (st == BEAM_INF_SKIP) atomicAdd(&counters[B2S_CNT_SKIPPED_INF], 1);
+}
+
+// One step of [BRES]:51-55.
+__device__ __forceinline__ void bres_step(double &acc, int &minor, double slope, int inc)
+{
+    acc = __dadd_rn(acc, slope);
+    if (acc >= 0.5) {
+        minor += inc;
+        acc = __dadd_rn(acc, -1.0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Variant 1: one beam per thread, one RED.ADD per in-grid cell.
+
+__global__ void __launch_bounds__(256)
+grid_raycast_v1(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int xw, int yw,
+                double cells_per_m, double off_x, double off_y, const float *__restrict__ ox,
+                const float *__restrict__ oy, const float *__restrict__ cx,
+                const float *__restrict__ cy, long long total, int beams, int32_t *counters)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int s = (int)(i / beams);
+    Beam b;
+    const int st = beam_setup(__ldg(ox + i), __ldg(oy + i), __ldg(cx + s), __ldg(cy + s), xw, yw,
+                              cells_per_m, off_x, off_y, b);
+    if (st != BEAM_OK) {
+        count_status(st, counters);
+        return;
+    }
+    const int wmaj = b.steep ? yw : xw, wmin = b.steep ? xw : yw;
+    const int smaj = b.steep ? 1 : yw, smin = b.steep ? yw : 1;
+    // in-grid window of the major axis; the recurrence is still replayed from k = 0
+    const int k_lo = max(0, -b.major0);
+    const int k_hi = min(b.span, wmaj - 1 - b.major0);
+    double acc = 0.0;
+    int minor = b.minor0;
+    int k = 0;
+    for (; k < k_lo; ++k) bres_step(acc, minor, b.slope, b.inc);
+    for (; k <= k_hi; ++k) {
+        if ((unsigned)minor < (unsigned)wmin) {
+            const int cell = (b.major0 + k) * smaj + minor * smin;
+            if (k == b.hit_k) atomicAdd(hit + cell, 1); else atomicAdd(miss + cell, 1);
+        }
+        bres_step(acc, minor, b.slope, b.inc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Variant 2: warp-synchronous march with run aggregation.
+//
+// The 32 lanes of a warp hold 32 angularly adjacent beams of one scan.  All lanes advance one
+// major-axis cell per iteration, lined up by distance from the sensor cell (a flipped trace
+// starts at the obstacle, so it is delayed until it is `t` cells away from the sensor like its
+// neighbours).  Adjacent beams share cells for the first ~1/(beam spacing) steps, and because
+// they are sorted by angle, equal cells sit in adjacent lanes: one shuffle + ballot finds the
+// runs and only the head lane of each run issues RED.ADD with the run length.
+
+__global__ void __launch_bounds__(256)
+grid_raycast_v2(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int xw, int yw,
+                double cells_per_m, double off_x, double off_y, const float *__restrict__ ox,
+                const float *__restrict__ oy, const float *__restrict__ cx,
+                const float *__restrict__ cy, long long total, int beams, int32_t *counters)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    Beam b;
+    int st = BEAM_NOOP;
+    if (i < total) {
+        const int s = (int)(i / beams);
+        st = beam_setup(__ldg(ox + i), __ldg(oy + i), __ldg(cx + s), __ldg(cy + s), xw, yw,
+                        cells_per_m, off_x, off_y, b);
+        if (st != BEAM_OK) count_status(st, counters);
+    }
+    const bool live = (st == BEAM_OK);
+    int span = live ? b.span : -1;
+    int tmax = span;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    if (tmax < 0) return;
+
+    const int wmaj = b.steep ? yw : xw, wmin = b.steep ? xw : yw;
+    const int smaj = b.steep ? 1 : yw, smin = b.steep ? yw : 1;
+    // canonical index k = t - delay; a flipped trace ends at the sensor cell when t == tmax
+    const int delay = (live && b.hit_k == 0) ? (tmax - span) : 0;
+    double acc = 0.0;
+    int minor = live ? b.minor0 : 0;
+    const int dead_key = -1 - lane;  // unique per lane: never equal to a neighbour's cell
+
+    for (int t = 0; t <= tmax; ++t) {
+        const int k = t - delay;
+        const bool on = live && k >= 0 && k <= span;
+        int key = dead_key;
+        if (on) {
+            const int major = b.major0 + k;
+            if ((unsigned)major < (unsigned)wmaj && (unsigned)minor < (unsigned)wmin) {
+                const int cell = major * smaj + minor * smin;
+                if (k == b.hit_k) atomicAdd(hit + cell, 1);  // once per beam
+                else key = cell;
+            }
+            bres_step(acc, minor, b.slope, b.inc);
+        }
+        const int left = __shfl_up_sync(0xffffffffu, key, 1);
+        const bool head = (lane == 0) || (key != left);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        if (head && key >= 0) {
+            const unsigned rest = (lane == 31) ? 0u : (heads >> (lane + 1));
+            const int run = rest ? __ffs(rest) : (32 - lane);
+            atomicAdd(miss + key, run);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// counts -> evidence score + occupancy.  Pure streaming.
+
+__global__ void __launch_bounds__(256)
+grid_finalize_kernel(const int32_t *__restrict__ hit, const int32_t *__restrict__ miss,
+                     long long cells, double w_hit, double w_miss, double thresh,
+                     float *__restrict__ datamap, int8_t *__restrict__ pmap)
+{
+    const long long quads = cells >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += stride) {
+        const int4 h = __ldg(reinterpret_cast<const int4 *>(hit) + q);
+        const int4 m = __ldg(reinterpret_cast<const int4 *>(miss) + q);
+        const int hh[4] = {h.x, h.y, h.z, h.w};
+        const int mm[4] = {m.x, m.y, m.z, m.w};
+        float sc[4];
+        char pm[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double v = __dadd_rn(__dmul_rn(w_miss, (double)mm[j]), __dmul_rn(w_hit, (double)hh[j]));
+            sc[j] = (float)v;
+            pm[j] = (hh[j] == 0 && mm[j] == 0) ? 50 : (v > thresh ? 100 : 0);
+        }
+        if (datamap) reinterpret_cast<float4 *>(datamap)[q] = make_float4(sc[0], sc[1], sc[2], sc[3]);
+        if (pmap) reinterpret_cast<char4 *>(pmap)[q] = make_char4(pm[0], pm[1], pm[2], pm[3]);
+    }
+    // tail (cells % 4)
+    const long long tail0 = quads << 2;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < cells - tail0) {
+        const long long c = tail0 + g;
+        const int hv = hit[c], mv = miss[c];
+        const double v = __dadd_rn(__dmul_rn(w_miss, (double)mv), __dmul_rn(w_hit, (double)hv));
+        if (datamap) datamap[c] = (float)v;
+        if (pmap) pmap[c] = (hv == 0 && mv == 0) ? 50 : (v > thresh ? 100 : 0);
+    }
+}
+
+// [SLAM]:270-271  data = pmap.T.reshape(-1): data[y * xw + x] = pmap[x][y].  32x32 smem transpose.
+__global__ void __launch_bounds__(256)
+grid_pack_ros_kernel(const int8_t *__restrict__ pmap, int xw, int yw, int8_t *__restrict__ data)
+{
+    __shared__ int8_t tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;  // bx over x, by over y
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int x = bx + r, y = by + threadIdx.x;
+        if (x < xw && y < yw) tile[r][threadIdx.x] = pmap[(size_t)x * yw + y];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int y = by + r, x = bx + threadIdx.x;
+        if (x < xw && y < yw) data[(size_t)y * xw + x] = tile[threadIdx.x][r];
+    }
+}
+
+// [BRES]:2-58 for a batch of segments: one thread per segment writes its whole path in the
+// reference's order (first cell = start, last cell = end).
+__global__ void __launch_bounds__(128)
+bresenham_paths_kernel(const int32_t *__restrict__ segs, int count, const int64_t *__restrict__ offsets,
+                       int32_t *__restrict__ cells_xy)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    int x0 = segs[4 * i], y0 = segs[4 * i + 1], x1 = segs[4 * i + 2], y1 = segs[4 * i + 3];
+    if (x0 == x1 && y0 == y1) return;
+    const int steep = abs(y1 - y0) > abs(x1 - x0);
+    if (steep) {
+        int t = x0; x0 = y0; y0 = t;
+        t = x1; x1 = y1; y1 = t;
+    }
+    const int flipped = x0 > x1;
+    if (flipped) {
+        int t = x0; x0 = x1; x1 = t;
+        t = y0; y0 = y1; y1 = t;
+    }
+    const int span = x1 - x0;
+    const double slope = __ddiv_rn((double)abs(y1 - y0), (double)span);
+    const int inc = (y0 < y1) ? 1 : -1;
+    int32_t *out = cells_xy + 2 * offsets[i];
+    double acc = 0.0;
+    int minor = y0;
+    for (int k = 0; k <= span; ++k) {
+        const int major = x0 + k;
+        const int slot = flipped ? (span - k) : k;
+        out[2 * slot] = steep ? minor : major;
+        out[2 * slot + 1] = steep ? major : minor;
+        bres_step(acc, minor, slope, inc);
+    }
+}
+
+}  // namespace b2s
+
+// ============================================================================== C ABI
+
+using namespace b2s;
+
+extern "C" int b2s_grid_raycast(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m,
+                                double off_x, double off_y, const float *ox, const float *oy,
+                                const float *cx, const float *cy, int scans, int beams,
+                                int32_t *counters, void *stream)
+{
+    B2S_REQUIRE(hit && miss && ox && oy && cx && cy, "b2s_grid_raycast: null pointer");
+    B2S_REQUIRE(xw > 0 && yw > 0 && (long long)xw * yw < (1ll << 31), "b2s_grid_raycast: grid size");
+    B2S_REQUIRE(scans >= 0 && beams >= 0, "b2s_grid_raycast: negative count");
+    B2S_REQUIRE(cells_per_m == cells_per_m && off_x == off_x && off_y == off_y, "b2s_grid_raycast: NaN scale");
+    const long long total = (long long)scans * beams;
+    if (total == 0) return B2S_OK;
+    const int threads = 256;
+    const long long blocks = (total + threads - 1) / threads;
+    B2S_REQUIRE(blocks < (1ll << 31), "b2s_grid_raycast: too many beams for one launch");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (g_grid_variant == 1)
+        grid_raycast_v1<<<(unsigned)blocks, threads, 0, st>>>(hit, miss, xw, yw, cells_per_m, off_x, off_y,
+                                                              ox, oy, cx, cy, total, beams, counters);
+    else
+        grid_raycast_v2<<<(unsigned)blocks, threads, 0, st>>>(hit, miss, xw, yw, cells_per_m, off_x, off_y,
+                                                              ox, oy, cx, cy, total, beams, counters);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+
+extern "C" int b2s_grid_finalize(const int32_t *hit, const int32_t *miss, int xw, int yw, double w_hit,
+                                 double w_miss, double thresh, float *datamap, int8_t *pmap,
+                                 void *stream)
+{
+    B2S_REQUIRE(hit && miss, "b2s_grid_finalize: null plane");
+    B2S_REQUIRE(xw > 0 && yw > 0, "b2s_grid_finalize: grid size");
+    if (!datamap && !pmap) return B2S_OK;
+    const long long cells = (long long)xw * yw;
+    B2S_REQUIRE(((uintptr_t)hit % 16 == 0) && ((uintptr_t)miss % 16 == 0) &&
+                    (!datamap || (uintptr_t)datamap % 16 == 0) && (!pmap || (uintptr_t)pmap % 4 == 0),
+                "b2s_grid_finalize: planes must be 16-byte aligned");
+    const int threads = 256;
+    long long want = ((cells >> 2) + threads - 1) / threads;
+    const long long cap = (long long)sm_count() * 16;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    grid_finalize_kernel<<<(unsigned)want, threads, 0, (cudaStream_t)stream>>>(hit, miss, cells, w_hit, w_miss,
+                                                                              thresh, datamap, pmap);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+
+extern "C" int b2s_grid_pack_ros(const int8_t *pmap, int xw, int yw, int8_t *data, void *stream)
+{
+    B2S_REQUIRE(pmap && data, "b2s_grid_pack_ros: null pointer");
+    B2S_REQUIRE(xw > 0 && yw > 0, "b2s_grid_pack_ros: grid size");
+    dim3 grid((xw + 31) / 32, (yw + 31) / 32), block(32, 8);
+    grid_pack_ros_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(pmap, xw, yw, data);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+
+extern "C" int b2s_bresenham_paths(const int32_t *segs, int count, const int64_t *offsets,
+                                   int32_t *cells_xy, void *stream)
+{
+    B2S_REQUIRE(count >= 0, "b2s_bresenham_paths: negative count");
+    if (count == 0) return B2S_OK;
+    B2S_REQUIRE(segs && offsets && cells_xy, "b2s_bresenham_paths: null pointer");
+    bresenham_paths_kernel<<<(count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(segs, count, offsets, cells_xy);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}

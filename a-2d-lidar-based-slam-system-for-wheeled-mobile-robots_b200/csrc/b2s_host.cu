@@ -1,0 +1,566 @@
+// Layer 2 of the C ABI: host-buffer entry points (the calls the Python ICP / Mapping classes
+// make), error reporting, and NCCL plumbing for the count-delta all-reduce.
+#include "b2s_common.cuh"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+
+namespace b2s {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count()
+{
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+extern int g_grid_variant;
+
+// Growable device / pinned-host staging buffer.
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return B2S_OK;
+        release();
+        size_t want = bytes + bytes / 4;
+        cudaError_t e = pinned ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            cap = 0;
+            set_error("allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+            return e == cudaErrorMemoryAllocation ? B2S_ERR_NOMEM : B2S_ERR_CUDA;
+        }
+        cap = want;
+        return B2S_OK;
+    }
+    void release()
+    {
+        if (p) {
+            if (pinned) cudaFreeHost(p); else cudaFree(p);
+        }
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (dev >= 0 && dev != prev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace b2s
+
+using namespace b2s;
+
+struct b2s_icp {
+    int device;
+    cudaStream_t stream;
+    Buf d_tar, d_src, d_T, d_iters, d_aux;
+};
+
+struct b2s_mapping {
+    int device;
+    int xw, yw;
+    double xyreso, cells_per_m, off_x, off_y;
+    double w_hit, w_miss, thresh;
+    cudaStream_t stream;
+    int32_t *hit, *miss;
+    int32_t *counters;
+    Buf d_in, d_datamap, d_pmap;
+};
+
+extern "C" int b2s_version(void) { return 100; }
+
+extern "C" const char *b2s_status_string(int status)
+{
+    switch (status) {
+    case B2S_OK: return "ok";
+    case B2S_ERR_INVALID_ARG: return "invalid argument";
+    case B2S_ERR_NONFINITE: return "non-finite coordinate";
+    case B2S_ERR_CUDA: return "CUDA error";
+    case B2S_ERR_TOO_LONG: return "beam longer than B2S_MAX_PATH_CELLS";
+    case B2S_ERR_NCCL: return "NCCL error";
+    case B2S_ERR_NOMEM: return "out of memory";
+    default: return "unknown status";
+    }
+}
+
+extern "C" const char *b2s_last_error(void) { return g_err; }
+
+extern "C" int b2s_device_count(int *count)
+{
+    B2S_REQUIRE(count, "b2s_device_count: null pointer");
+    *count = 0;
+    B2S_CUDA(cudaGetDeviceCount(count));
+    return B2S_OK;
+}
+
+// Tuning hook used by bench.py to compare kernel variants; not part of the reference surface.
+extern "C" int b2s_tune(const char *key, int value)
+{
+    B2S_REQUIRE(key, "b2s_tune: null key");
+    if (strcmp(key, "grid_variant") == 0) {
+        B2S_REQUIRE(value >= 1 && value <= 2, "b2s_tune: grid_variant must be 1 or 2");
+        g_grid_variant = value;
+        return B2S_OK;
+    }
+    set_error("b2s_tune: unknown key %s", key);
+    return B2S_ERR_INVALID_ARG;
+}
+
+// ------------------------------------------------------------------------------ ICP object
+
+extern "C" int b2s_icp_create(b2s_icp **out, int device)
+{
+    B2S_REQUIRE(out, "b2s_icp_create: null pointer");
+    *out = nullptr;
+    int ndev = 0;
+    B2S_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) {
+        set_error("no CUDA device");
+        return B2S_ERR_CUDA;
+    }
+    if (device < 0) B2S_CUDA(cudaGetDevice(&device));
+    B2S_REQUIRE(device < ndev, "b2s_icp_create: device index out of range");
+    DeviceGuard g(device);
+    b2s_icp *c = new (std::nothrow) b2s_icp();
+    if (!c) return B2S_ERR_NOMEM;
+    c->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete c;
+        return cuda_fail(e, "cudaStreamCreate");
+    }
+    *out = c;
+    return B2S_OK;
+}
+
+extern "C" int b2s_icp_destroy(b2s_icp *c)
+{
+    if (!c) return B2S_OK;
+    DeviceGuard g(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->d_tar.release(); c->d_src.release(); c->d_T.release(); c->d_iters.release(); c->d_aux.release();
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return B2S_OK;
+}
+
+extern "C" int b2s_icp_process(b2s_icp *c, const void *tar_xy, const void *src_xy, int is_f64,
+                               int pairs, int n_src, int n_tar, int max_iter, double tol,
+                               double *T_out, int32_t *iters_out)
+{
+    B2S_REQUIRE(c, "b2s_icp_process: null handle");
+    B2S_REQUIRE(pairs >= 0 && n_src > 0 && n_tar > 0 && max_iter >= 0, "b2s_icp_process: bad sizes");
+    if (pairs == 0) return B2S_OK;
+    B2S_REQUIRE(tar_xy && src_xy && T_out, "b2s_icp_process: null pointer");
+    DeviceGuard g(c->device);
+    const size_t el = is_f64 ? 8 : 4;
+    const size_t tb = (size_t)pairs * 2 * n_tar * el, sb = (size_t)pairs * 2 * n_src * el;
+    int rc;
+    if ((rc = c->d_tar.reserve(tb))) return rc;
+    if ((rc = c->d_src.reserve(sb))) return rc;
+    if ((rc = c->d_T.reserve((size_t)pairs * 9 * sizeof(double)))) return rc;
+    if ((rc = c->d_iters.reserve((size_t)pairs * sizeof(int32_t)))) return rc;
+    B2S_CUDA(cudaMemcpyAsync(c->d_tar.p, tar_xy, tb, cudaMemcpyHostToDevice, c->stream));
+    B2S_CUDA(cudaMemcpyAsync(c->d_src.p, src_xy, sb, cudaMemcpyHostToDevice, c->stream));
+    if (is_f64)
+        rc = b2s_icp_batch_f64((const double *)c->d_tar.p, (const double *)c->d_src.p, pairs, n_src, n_tar,
+                               max_iter, tol, (double *)c->d_T.p, (int32_t *)c->d_iters.p, c->stream);
+    else
+        rc = b2s_icp_batch_f32((const float *)c->d_tar.p, (const float *)c->d_src.p, pairs, n_src, n_tar,
+                               max_iter, tol, (double *)c->d_T.p, (int32_t *)c->d_iters.p, c->stream);
+    if (rc) return rc;
+    B2S_CUDA(cudaMemcpyAsync(T_out, c->d_T.p, (size_t)pairs * 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (iters_out)
+        B2S_CUDA(cudaMemcpyAsync(iters_out, c->d_iters.p, (size_t)pairs * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                 c->stream));
+    B2S_CUDA(cudaStreamSynchronize(c->stream));
+    return B2S_OK;
+}
+
+extern "C" int b2s_icp_find_nearest(b2s_icp *c, const double *src_xy, int n, const double *tar_xy,
+                                    int m, double *dist_out, int64_t *idx_out)
+{
+    B2S_REQUIRE(c, "b2s_icp_find_nearest: null handle");
+    B2S_REQUIRE(n >= 0 && m >= 0, "b2s_icp_find_nearest: negative size");
+    if (n == 0) return B2S_OK;
+    B2S_REQUIRE(src_xy && dist_out && idx_out && (tar_xy || m == 0), "b2s_icp_find_nearest: null pointer");
+    DeviceGuard g(c->device);
+    int rc;
+    if ((rc = c->d_src.reserve((size_t)n * 16))) return rc;
+    if ((rc = c->d_tar.reserve((size_t)(m > 0 ? m : 1) * 16))) return rc;
+    if ((rc = c->d_T.reserve((size_t)n * 8))) return rc;
+    if ((rc = c->d_aux.reserve((size_t)n * 8))) return rc;
+    B2S_CUDA(cudaMemcpyAsync(c->d_src.p, src_xy, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    if (m > 0) B2S_CUDA(cudaMemcpyAsync(c->d_tar.p, tar_xy, (size_t)m * 16, cudaMemcpyHostToDevice, c->stream));
+    rc = b2s_nearest_f64((const double *)c->d_src.p, n, (const double *)c->d_tar.p, m, (double *)c->d_T.p,
+                         (int64_t *)c->d_aux.p, c->stream);
+    if (rc) return rc;
+    B2S_CUDA(cudaMemcpyAsync(dist_out, c->d_T.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    B2S_CUDA(cudaMemcpyAsync(idx_out, c->d_aux.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    B2S_CUDA(cudaStreamSynchronize(c->stream));
+    return B2S_OK;
+}
+
+extern "C" int b2s_icp_get_transform(b2s_icp *c, const double *src_xy, const double *tar_xy, int n,
+                                     double *T_out)
+{
+    B2S_REQUIRE(c, "b2s_icp_get_transform: null handle");
+    B2S_REQUIRE(n > 0 && src_xy && tar_xy && T_out, "b2s_icp_get_transform: bad arguments");
+    DeviceGuard g(c->device);
+    int rc;
+    if ((rc = c->d_src.reserve((size_t)n * 16))) return rc;
+    if ((rc = c->d_tar.reserve((size_t)n * 16))) return rc;
+    if ((rc = c->d_T.reserve(9 * 8))) return rc;
+    B2S_CUDA(cudaMemcpyAsync(c->d_src.p, src_xy, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    B2S_CUDA(cudaMemcpyAsync(c->d_tar.p, tar_xy, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    rc = b2s_rigid_fit_f64((const double *)c->d_src.p, (const double *)c->d_tar.p, n, (double *)c->d_T.p, c->stream);
+    if (rc) return rc;
+    B2S_CUDA(cudaMemcpyAsync(T_out, c->d_T.p, 9 * 8, cudaMemcpyDeviceToHost, c->stream));
+    B2S_CUDA(cudaStreamSynchronize(c->stream));
+    return B2S_OK;
+}
+
+// ------------------------------------------------------------------------------ Mapping object
+
+extern "C" int b2s_mapping_create(b2s_mapping **out, int xw, int yw, double xyreso, double w_hit,
+                                  double w_miss, double thresh, int device)
+{
+    B2S_REQUIRE(out, "b2s_mapping_create: null pointer");
+    *out = nullptr;
+    B2S_REQUIRE(xw > 0 && yw > 0 && (long long)xw * yw < (1ll << 31), "b2s_mapping_create: grid size");
+    B2S_REQUIRE(xyreso > 0.0 && isfinite(xyreso), "b2s_mapping_create: xyreso must be positive");
+    int ndev = 0;
+    B2S_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) {
+        set_error("no CUDA device");
+        return B2S_ERR_CUDA;
+    }
+    if (device < 0) B2S_CUDA(cudaGetDevice(&device));
+    B2S_REQUIRE(device < ndev, "b2s_mapping_create: device index out of range");
+    DeviceGuard g(device);
+    b2s_mapping *m = new (std::nothrow) b2s_mapping();
+    if (!m) return B2S_ERR_NOMEM;
+    m->device = device;
+    m->xw = xw;
+    m->yw = yw;
+    m->xyreso = xyreso;
+    // generalisation of the literals of [MAP]:33-36; exactly 10.0 / 10.0 at (200, 200, 0.1)
+    m->cells_per_m = 1.0 / xyreso;
+    m->off_x = (double)xw * xyreso / 2.0;
+    m->off_y = (double)yw * xyreso / 2.0;
+    m->w_hit = w_hit;
+    m->w_miss = w_miss;
+    m->thresh = thresh;
+    m->hit = m->miss = m->counters = nullptr;
+    const size_t plane = (size_t)xw * yw * sizeof(int32_t);
+    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&m->hit, plane);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&m->miss, plane);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&m->counters, B2S_CNT_WORDS * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->hit, 0, plane, m->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->miss, 0, plane, m->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->counters, 0, B2S_CNT_WORDS * sizeof(int32_t), m->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    if (e != cudaSuccess) {
+        int rc = cuda_fail(e, "b2s_mapping_create");
+        b2s_mapping_destroy(m);
+        return e == cudaErrorMemoryAllocation ? B2S_ERR_NOMEM : rc;
+    }
+    *out = m;
+    return B2S_OK;
+}
+
+extern "C" int b2s_mapping_destroy(b2s_mapping *m)
+{
+    if (!m) return B2S_OK;
+    DeviceGuard g(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->hit) cudaFree(m->hit);
+    if (m->miss) cudaFree(m->miss);
+    if (m->counters) cudaFree(m->counters);
+    m->d_in.release(); m->d_datamap.release(); m->d_pmap.release();
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+    return B2S_OK;
+}
+
+extern "C" int b2s_mapping_reset(b2s_mapping *m)
+{
+    B2S_REQUIRE(m, "b2s_mapping_reset: null handle");
+    DeviceGuard g(m->device);
+    const size_t plane = (size_t)m->xw * m->yw * sizeof(int32_t);
+    B2S_CUDA(cudaMemsetAsync(m->hit, 0, plane, m->stream));
+    B2S_CUDA(cudaMemsetAsync(m->miss, 0, plane, m->stream));
+    B2S_CUDA(cudaStreamSynchronize(m->stream));
+    return B2S_OK;
+}
+
+// What int() in [MAP]:33-36 raises on: NaN -> ValueError, inf -> OverflowError.  ox == +-inf is
+// the one tolerated value ([MAP]:30).  Checked on the host before anything is applied.
+static int validate_scan(const float *ox, const float *oy, const float *cx, const float *cy, int scans, int beams)
+{
+    for (int s = 0; s < scans; ++s)
+        if (!isfinite(cx[s]) || !isfinite(cy[s])) {
+            set_error("non-finite sensor position in scan %d", s);
+            return B2S_ERR_NONFINITE;
+        }
+    const size_t total = (size_t)scans * beams;
+    for (size_t i = 0; i < total; ++i) {
+        const float x = ox[i];
+        if (isinf(x)) continue;
+        if (isnan(x) || !isfinite(oy[i])) {
+            set_error("non-finite endpoint at beam %zu", i);
+            return B2S_ERR_NONFINITE;
+        }
+    }
+    return B2S_OK;
+}
+
+extern "C" int b2s_mapping_update(b2s_mapping *m, const float *ox, const float *oy, const float *cx,
+                                  const float *cy, int scans, int beams, int8_t *pmap_out)
+{
+    B2S_REQUIRE(m, "b2s_mapping_update: null handle");
+    B2S_REQUIRE(scans >= 0 && beams >= 0, "b2s_mapping_update: negative count");
+    DeviceGuard g(m->device);
+    const size_t total = (size_t)scans * beams;
+    int rc;
+    if (total > 0) {
+        B2S_REQUIRE(ox && oy && cx && cy, "b2s_mapping_update: null pointer");
+        if ((rc = validate_scan(ox, oy, cx, cy, scans, beams))) return rc;
+        const size_t pts = total * sizeof(float), ctr = (size_t)scans * sizeof(float);
+        // one device block: [ox | oy | cx | cy], each section 16-byte aligned
+        const size_t a_pts = (pts + 15) & ~(size_t)15, a_ctr = (ctr + 15) & ~(size_t)15;
+        if ((rc = m->d_in.reserve(2 * a_pts + 2 * a_ctr))) return rc;
+        char *base = (char *)m->d_in.p;
+        float *d_ox = (float *)base, *d_oy = (float *)(base + a_pts);
+        float *d_cx = (float *)(base + 2 * a_pts), *d_cy = (float *)(base + 2 * a_pts + a_ctr);
+        B2S_CUDA(cudaMemcpyAsync(d_ox, ox, pts, cudaMemcpyHostToDevice, m->stream));
+        B2S_CUDA(cudaMemcpyAsync(d_oy, oy, pts, cudaMemcpyHostToDevice, m->stream));
+        B2S_CUDA(cudaMemcpyAsync(d_cx, cx, ctr, cudaMemcpyHostToDevice, m->stream));
+        B2S_CUDA(cudaMemcpyAsync(d_cy, cy, ctr, cudaMemcpyHostToDevice, m->stream));
+        B2S_CUDA(cudaMemsetAsync(m->counters, 0, B2S_CNT_WORDS * sizeof(int32_t), m->stream));
+        rc = b2s_grid_raycast(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y, d_ox, d_oy,
+                              d_cx, d_cy, scans, beams, m->counters, m->stream);
+        if (rc) return rc;
+    }
+    if (pmap_out) {
+        const size_t cells = (size_t)m->xw * m->yw;
+        if ((rc = m->d_pmap.reserve(cells))) return rc;
+        rc = b2s_grid_finalize(m->hit, m->miss, m->xw, m->yw, m->w_hit, m->w_miss, m->thresh, nullptr,
+                               (int8_t *)m->d_pmap.p, m->stream);
+        if (rc) return rc;
+        B2S_CUDA(cudaMemcpyAsync(pmap_out, m->d_pmap.p, cells, cudaMemcpyDeviceToHost, m->stream));
+    }
+    int32_t cnt[B2S_CNT_WORDS] = {0, 0, 0, 0};
+    if (total > 0)
+        B2S_CUDA(cudaMemcpyAsync(cnt, m->counters, sizeof(cnt), cudaMemcpyDeviceToHost, m->stream));
+    B2S_CUDA(cudaStreamSynchronize(m->stream));
+    if (cnt[B2S_CNT_TOO_LONG] > 0) {
+        set_error("%d beam(s) longer than %d cells were dropped", cnt[B2S_CNT_TOO_LONG], B2S_MAX_PATH_CELLS);
+        return B2S_ERR_TOO_LONG;
+    }
+    return B2S_OK;
+}
+
+extern "C" int b2s_mapping_read(b2s_mapping *m, int32_t *hit, int32_t *miss, float *datamap, int8_t *pmap)
+{
+    B2S_REQUIRE(m, "b2s_mapping_read: null handle");
+    DeviceGuard g(m->device);
+    const size_t cells = (size_t)m->xw * m->yw;
+    int rc;
+    if (datamap || pmap) {
+        if (datamap && (rc = m->d_datamap.reserve(cells * sizeof(float)))) return rc;
+        if (pmap && (rc = m->d_pmap.reserve(cells))) return rc;
+        rc = b2s_grid_finalize(m->hit, m->miss, m->xw, m->yw, m->w_hit, m->w_miss, m->thresh,
+                               datamap ? (float *)m->d_datamap.p : nullptr,
+                               pmap ? (int8_t *)m->d_pmap.p : nullptr, m->stream);
+        if (rc) return rc;
+        if (datamap)
+            B2S_CUDA(cudaMemcpyAsync(datamap, m->d_datamap.p, cells * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+        if (pmap) B2S_CUDA(cudaMemcpyAsync(pmap, m->d_pmap.p, cells, cudaMemcpyDeviceToHost, m->stream));
+    }
+    if (hit) B2S_CUDA(cudaMemcpyAsync(hit, m->hit, cells * sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+    if (miss) B2S_CUDA(cudaMemcpyAsync(miss, m->miss, cells * sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+    B2S_CUDA(cudaStreamSynchronize(m->stream));
+    return B2S_OK;
+}
+
+extern "C" int b2s_mapping_planes(b2s_mapping *m, int32_t **hit, int32_t **miss, void **stream)
+{
+    B2S_REQUIRE(m, "b2s_mapping_planes: null handle");
+    if (hit) *hit = m->hit;
+    if (miss) *miss = m->miss;
+    if (stream) *stream = (void *)m->stream;
+    return B2S_OK;
+}
+
+extern "C" int b2s_bresenham_host(const int32_t *segs, int count, const int64_t *offsets, int32_t *cells_xy)
+{
+    B2S_REQUIRE(count >= 0, "b2s_bresenham_host: negative count");
+    if (count == 0) return B2S_OK;
+    B2S_REQUIRE(segs && offsets, "b2s_bresenham_host: null pointer");
+    const int64_t total = offsets[count];
+    B2S_REQUIRE(total >= 0 && (total == 0 || cells_xy), "b2s_bresenham_host: bad offsets");
+    int32_t *d_segs = nullptr, *d_cells = nullptr;
+    int64_t *d_off = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_segs, (size_t)count * 16);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_off, (size_t)(count + 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_cells, (size_t)(total > 0 ? total : 1) * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(d_segs, segs, (size_t)count * 16, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_off, offsets, (size_t)(count + 1) * 8, cudaMemcpyHostToDevice);
+    int rc = B2S_OK;
+    if (e == cudaSuccess) rc = b2s_bresenham_paths(d_segs, count, d_off, d_cells, nullptr);
+    if (e == cudaSuccess && rc == B2S_OK) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && rc == B2S_OK && total > 0)
+        e = cudaMemcpy(cells_xy, d_cells, (size_t)total * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_segs);
+    cudaFree(d_off);
+    cudaFree(d_cells);
+    if (e != cudaSuccess) return cuda_fail(e, "b2s_bresenham_host");
+    return rc;
+}
+
+// ------------------------------------------------------------------------------ NCCL (dlopen)
+//
+// The library is not linked against NCCL: in a torch process libnccl.so.2 is already loaded
+// (torch bundles it) and dlopen returns that copy, so both sides share one NCCL runtime.
+
+namespace {
+typedef struct { char internal[128]; } nccl_uid;
+typedef int (*fn_get_uid)(nccl_uid *);
+typedef int (*fn_init_rank)(void **, int, nccl_uid, int);
+typedef int (*fn_destroy)(void *);
+typedef int (*fn_allreduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*fn_group)(void);
+typedef const char *(*fn_errstr)(int);
+
+struct NcclApi {
+    void *handle = nullptr;
+    fn_get_uid get_uid = nullptr;
+    fn_init_rank init_rank = nullptr;
+    fn_destroy destroy = nullptr;
+    fn_allreduce allreduce = nullptr;
+    fn_group group_start = nullptr, group_end = nullptr;
+    fn_errstr errstr = nullptr;
+    bool tried = false;
+};
+NcclApi g_nccl;
+
+int nccl_load()
+{
+    if (g_nccl.allreduce) return B2S_OK;
+    if (!g_nccl.tried) {
+        g_nccl.tried = true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            g_nccl.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (g_nccl.handle) break;
+        }
+        if (g_nccl.handle) {
+            g_nccl.get_uid = (fn_get_uid)dlsym(g_nccl.handle, "ncclGetUniqueId");
+            g_nccl.init_rank = (fn_init_rank)dlsym(g_nccl.handle, "ncclCommInitRank");
+            g_nccl.destroy = (fn_destroy)dlsym(g_nccl.handle, "ncclCommDestroy");
+            g_nccl.allreduce = (fn_allreduce)dlsym(g_nccl.handle, "ncclAllReduce");
+            g_nccl.group_start = (fn_group)dlsym(g_nccl.handle, "ncclGroupStart");
+            g_nccl.group_end = (fn_group)dlsym(g_nccl.handle, "ncclGroupEnd");
+            g_nccl.errstr = (fn_errstr)dlsym(g_nccl.handle, "ncclGetErrorString");
+        }
+    }
+    if (!g_nccl.allreduce || !g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.destroy || !g_nccl.group_start ||
+        !g_nccl.group_end) {
+        set_error("NCCL not available: %s", g_nccl.handle ? "missing symbols" : "libnccl.so.2 not found");
+        return B2S_ERR_NCCL;
+    }
+    return B2S_OK;
+}
+
+int nccl_fail(int code, const char *what)
+{
+    set_error("%s: %s", what, g_nccl.errstr ? g_nccl.errstr(code) : "nccl error");
+    return B2S_ERR_NCCL;
+}
+}  // namespace
+
+extern "C" int b2s_nccl_unique_id(void *id128)
+{
+    B2S_REQUIRE(id128, "b2s_nccl_unique_id: null pointer");
+    int rc = nccl_load();
+    if (rc) return rc;
+    nccl_uid uid;
+    int e = g_nccl.get_uid(&uid);
+    if (e) return nccl_fail(e, "ncclGetUniqueId");
+    memcpy(id128, &uid, sizeof(uid));
+    return B2S_OK;
+}
+
+extern "C" int b2s_nccl_comm_init(void **comm_out, int nranks, int rank, const void *id128)
+{
+    B2S_REQUIRE(comm_out && id128 && nranks > 0 && rank >= 0 && rank < nranks, "b2s_nccl_comm_init: bad arguments");
+    int rc = nccl_load();
+    if (rc) return rc;
+    nccl_uid uid;
+    memcpy(&uid, id128, sizeof(uid));
+    int e = g_nccl.init_rank(comm_out, nranks, uid, rank);
+    if (e) return nccl_fail(e, "ncclCommInitRank");
+    return B2S_OK;
+}
+
+extern "C" int b2s_nccl_comm_destroy(void *comm)
+{
+    if (!comm) return B2S_OK;
+    int rc = nccl_load();
+    if (rc) return rc;
+    int e = g_nccl.destroy(comm);
+    if (e) return nccl_fail(e, "ncclCommDestroy");
+    return B2S_OK;
+}
+
+extern "C" int b2s_grid_allreduce(int32_t *hit, int32_t *miss, size_t cells, void *nccl_comm, void *stream)
+{
+    B2S_REQUIRE(hit && miss && nccl_comm, "b2s_grid_allreduce: null pointer");
+    int rc = nccl_load();
+    if (rc) return rc;
+    const int nccl_int32 = 2, nccl_sum = 0;  // ncclInt32, ncclSum
+    int e = g_nccl.group_start();
+    if (e) return nccl_fail(e, "ncclGroupStart");
+    e = g_nccl.allreduce(hit, hit, cells, nccl_int32, nccl_sum, nccl_comm, (cudaStream_t)stream);
+    if (!e) e = g_nccl.allreduce(miss, miss, cells, nccl_int32, nccl_sum, nccl_comm, (cudaStream_t)stream);
+    int e2 = g_nccl.group_end();
+    if (e) return nccl_fail(e, "ncclAllReduce");
+    if (e2) return nccl_fail(e2, "ncclGroupEnd");
+    return B2S_OK;
+}

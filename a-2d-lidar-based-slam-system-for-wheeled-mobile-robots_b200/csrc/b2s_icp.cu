@@ -1,0 +1,339 @@
+// Batched 2-D point-to-point ICP: one CTA per scan pair, whole iteration loop on chip.
+//
+// Replaces ICP.process ([ICP]:38-88), findNearest ([ICP]:90-114), getTransform ([ICP]:149-179).
+//
+// Per pair the kernel reads 2*(N+M) coordinates once (target rows staged into shared memory
+// with a 1-D bulk async copy + mbarrier), then runs up to max_iter iterations of
+//   brute-force nearest neighbour  (N*M distance evaluations, strict '<', ascending j so the
+//                                   lowest index wins ties exactly like the reference loop)
+//   centroid + 2x2 cross-covariance (two-pass, as the reference centres before multiplying)
+//   closed-form proper rotation     (theta = atan2(W10-W01, W00+W11) == U.Vt with the W9 fix)
+//   src <- T.src, mean-error stop rule
+// and the final re-fit of the original source onto the moved source ([ICP]:81).
+//
+// Numerics: everything is float64, like the reference.  B200 (sm_100a) issues FP64 at half the
+// FP32 rate, and an FP32 search would need a second-best tracker plus a float64 re-check of
+// near ties to keep correspondences identical, which costs about the same issue slots; see
+// DESIGN.md "ICP numerics".  Source points live in registers (SRC_PER_THREAD per thread) for
+// the whole solve; targets live in shared memory as double2 and are read as warp broadcasts.
+#include "b2s_common.cuh"
+
+#include <math.h>
+
+namespace b2s {
+
+constexpr int SRC_PER_THREAD = 4;
+
+// Closed-form Kabsch for row-matched sets given centred sums; returns T (row-major 2x3 part).
+__device__ __forceinline__ void rotation_from_w(double w00, double w01, double w10, double w11,
+                                                double cax, double cay, double cbx, double cby,
+                                                double (&T)[6])
+{
+    const double cc = w00 + w11, ss = w10 - w01;
+    const double h = hypot(cc, ss);
+    double c = 1.0, s = 0.0;
+    if (h > 0.0) {
+        c = cc / h;
+        s = ss / h;
+    }
+    T[0] = c;
+    T[1] = -s;
+    T[2] = cbx - (c * cax - s * cay);
+    T[3] = s;
+    T[4] = c;
+    T[5] = cby - (s * cax + c * cay);
+}
+
+// Fit of per-thread registers a[r] -> b[r] over the CTA (getTransform, [ICP]:149-179).
+// valid[r] marks the slots that hold a point.  Four __syncthreads() inside.
+__device__ __forceinline__ void cta_rigid_fit(const double (&ax)[SRC_PER_THREAD],
+                                              const double (&ay)[SRC_PER_THREAD],
+                                              const double (&bx)[SRC_PER_THREAD],
+                                              const double (&by)[SRC_PER_THREAD], int count, int n,
+                                              double *scratch, double (&T)[6])
+{
+    double s4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int r = 0; r < SRC_PER_THREAD; ++r)
+        if (r < count) {
+            s4[0] += ax[r];
+            s4[1] += ay[r];
+            s4[2] += bx[r];
+            s4[3] += by[r];
+        }
+    block_sum<4>(s4, scratch);
+    const double inv = 1.0 / (double)n;
+    const double cax = s4[0] * inv, cay = s4[1] * inv, cbx = s4[2] * inv, cby = s4[3] * inv;
+    double w4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int r = 0; r < SRC_PER_THREAD; ++r)
+        if (r < count) {
+            const double px = ax[r] - cax, py = ay[r] - cay;
+            const double qx = bx[r] - cbx, qy = by[r] - cby;
+            w4[0] = fma(qx, px, w4[0]);  // W = BB^T . AA  ([ICP]:160)
+            w4[1] = fma(qx, py, w4[1]);
+            w4[2] = fma(qy, px, w4[2]);
+            w4[3] = fma(qy, py, w4[3]);
+        }
+    block_sum<4>(w4, scratch);
+    rotation_from_w(w4[0], w4[1], w4[2], w4[3], cax, cay, cbx, cby, T);
+}
+
+template <typename TIn>
+__global__ void icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__restrict__ src_xy, int n,
+                                 int m, int max_iter, double tol, double *__restrict__ T_out,
+                                 int32_t *__restrict__ iters_out, int use_bulk)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: [mbarrier 16 B][scratch 4*32 doubles][tar double2 * m][staging TIn * 2m]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    double *scratch = reinterpret_cast<double *>(smem_raw + 16);
+    double2 *tar = reinterpret_cast<double2 *>(smem_raw + 16 + 4 * 32 * sizeof(double));
+    TIn *stage = reinterpret_cast<TIn *>(tar + m);
+
+    const int pair = blockIdx.x;
+    const int tid = threadIdx.x;
+    const TIn *tar_g = tar_xy + (size_t)pair * 2 * m;
+    const TIn *src_g = src_xy + (size_t)pair * 2 * n;
+
+    // ---- stage the target scan: global -> shared via the bulk-copy engine when alignment allows
+    if (use_bulk) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytes = 2u * (uint32_t)m * (uint32_t)sizeof(TIn);
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(stage, tar_g, bytes, bar);
+        }
+    } else {
+        for (int j = tid; j < 2 * m; j += blockDim.x) stage[j] = tar_g[j];
+    }
+
+    // ---- this thread's source points (registers for the whole solve); overlaps the copy
+    double ox_[SRC_PER_THREAD], oy_[SRC_PER_THREAD];  // original
+    double sx[SRC_PER_THREAD], sy[SRC_PER_THREAD];    // moved
+    int count = 0;
+#pragma unroll
+    for (int r = 0; r < SRC_PER_THREAD; ++r) {
+        const int i = tid + r * blockDim.x;
+        ox_[r] = oy_[r] = 0.0;
+        if (i < n) {
+            ox_[r] = (double)src_g[i];
+            oy_[r] = (double)src_g[n + i];
+            count = r + 1;
+        }
+        sx[r] = ox_[r];
+        sy[r] = oy_[r];
+    }
+
+    if (use_bulk) mbar_wait(bar, 0);
+    else __syncthreads();
+    for (int j = tid; j < m; j += blockDim.x) tar[j] = make_double2((double)stage[j], (double)stage[m + j]);
+    __syncthreads();
+
+    double prev_err = 0.0;
+    int iters = 0;
+    for (int it = 0; it < max_iter; ++it) {
+        // ---- nearest neighbour ([ICP]:99-106)
+        double best[SRC_PER_THREAD];
+        int arg[SRC_PER_THREAD];
+#pragma unroll
+        for (int r = 0; r < SRC_PER_THREAD; ++r) {
+            best[r] = INFINITY;
+            arg[r] = 0;
+        }
+#pragma unroll 4
+        for (int j = 0; j < m; ++j) {
+            const double2 t = tar[j];
+#pragma unroll
+            for (int r = 0; r < SRC_PER_THREAD; ++r) {
+                const double dx = sx[r] - t.x, dy = sy[r] - t.y;
+                const double d2 = fma(dy, dy, dx * dx);
+                if (d2 < best[r]) {
+                    best[r] = d2;
+                    arg[r] = j;
+                }
+            }
+        }
+        // ---- matched targets, distances ([ICP]:69,75)
+        double bx[SRC_PER_THREAD], by[SRC_PER_THREAD];
+        double dsum[1] = {0.0};
+#pragma unroll
+        for (int r = 0; r < SRC_PER_THREAD; ++r) {
+            const double2 t = tar[arg[r]];
+            bx[r] = t.x;
+            by[r] = t.y;
+            if (r < count) dsum[0] += (best[r] == INFINITY) ? 0.0 : sqrt(best[r]);
+        }
+        double T[6];
+        cta_rigid_fit(sx, sy, bx, by, count, n, scratch, T);
+        block_sum<1>(dsum, scratch);
+        // ---- src <- T . src ([ICP]:71)
+#pragma unroll
+        for (int r = 0; r < SRC_PER_THREAD; ++r) {
+            const double x = sx[r], y = sy[r];
+            sx[r] = T[0] * x + T[1] * y + T[2];
+            sy[r] = T[3] * x + T[4] * y + T[5];
+        }
+        ++iters;
+        const double err = dsum[0] / (double)n;
+        if (fabs(prev_err - err) < tol) break;  // [ICP]:76, uniform across the CTA
+        prev_err = err;
+    }
+
+    double T[6];
+    cta_rigid_fit(ox_, oy_, sx, sy, count, n, scratch, T);  // [ICP]:81
+    if (tid == 0) {
+        double *o = T_out + (size_t)pair * 9;
+        o[0] = T[0]; o[1] = T[1]; o[2] = T[2];
+        o[3] = T[3]; o[4] = T[4]; o[5] = T[5];
+        o[6] = 0.0;  o[7] = 0.0;  o[8] = 1.0;
+        if (iters_out) iters_out[pair] = iters;
+    }
+}
+
+// ICP.findNearest as a standalone op: src [n][2], tar [m][2] (point rows).  Targets are tiled
+// through shared memory; each thread owns one source point.
+constexpr int NN_TILE = 1024;
+
+__global__ void __launch_bounds__(128)
+nearest_kernel(const double *__restrict__ src_xy, int n, const double *__restrict__ tar_xy, int m,
+               double *__restrict__ dist_out, int64_t *__restrict__ idx_out)
+{
+    __shared__ double2 tile[NN_TILE];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double sx = 0.0, sy = 0.0;
+    if (i < n) {
+        sx = src_xy[2 * i];
+        sy = src_xy[2 * i + 1];
+    }
+    double best = INFINITY;
+    long long arg = 0;
+    for (int base = 0; base < m; base += NN_TILE) {
+        const int cnt = min(NN_TILE, m - base);
+        __syncthreads();
+        for (int j = threadIdx.x; j < cnt; j += blockDim.x)
+            tile[j] = make_double2(tar_xy[2 * (size_t)(base + j)], tar_xy[2 * (size_t)(base + j) + 1]);
+        __syncthreads();
+        for (int j = 0; j < cnt; ++j) {
+            const double dx = sx - tile[j].x, dy = sy - tile[j].y;
+            const double d2 = fma(dy, dy, dx * dx);
+            if (d2 < best) {
+                best = d2;
+                arg = base + j;
+            }
+        }
+    }
+    if (i < n) {
+        dist_out[i] = (best == INFINITY) ? 0.0 : sqrt(best);
+        idx_out[i] = arg;
+    }
+}
+
+// ICP.getTransform as a standalone op: one CTA, grid-stride over n row-matched points.
+__global__ void __launch_bounds__(256)
+rigid_fit_kernel(const double *__restrict__ src_xy, const double *__restrict__ tar_xy, int n,
+                 double *__restrict__ T_out)
+{
+    __shared__ double scratch[4 * 32];
+    double s4[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        s4[0] += src_xy[2 * i];
+        s4[1] += src_xy[2 * i + 1];
+        s4[2] += tar_xy[2 * i];
+        s4[3] += tar_xy[2 * i + 1];
+    }
+    block_sum<4>(s4, scratch);
+    const double inv = 1.0 / (double)n;
+    const double cax = s4[0] * inv, cay = s4[1] * inv, cbx = s4[2] * inv, cby = s4[3] * inv;
+    double w4[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double px = src_xy[2 * i] - cax, py = src_xy[2 * i + 1] - cay;
+        const double qx = tar_xy[2 * i] - cbx, qy = tar_xy[2 * i + 1] - cby;
+        w4[0] = fma(qx, px, w4[0]);
+        w4[1] = fma(qx, py, w4[1]);
+        w4[2] = fma(qy, px, w4[2]);
+        w4[3] = fma(qy, py, w4[3]);
+    }
+    block_sum<4>(w4, scratch);
+    if (threadIdx.x == 0) {
+        double T[6];
+        rotation_from_w(w4[0], w4[1], w4[2], w4[3], cax, cay, cbx, cby, T);
+        T_out[0] = T[0]; T_out[1] = T[1]; T_out[2] = T[2];
+        T_out[3] = T[3]; T_out[4] = T[4]; T_out[5] = T[5];
+        T_out[6] = 0.0;  T_out[7] = 0.0;  T_out[8] = 1.0;
+    }
+}
+
+template <typename TIn>
+static int launch_icp(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_src, int n_tar,
+                      int max_iter, double tol, double *T_out, int32_t *iters_out, void *stream)
+{
+    B2S_REQUIRE(pairs >= 0 && n_src > 0 && n_tar > 0 && max_iter >= 0, "b2s_icp_batch: bad sizes");
+    if (pairs == 0) return B2S_OK;
+    B2S_REQUIRE(tar_xy && src_xy && T_out, "b2s_icp_batch: null pointer");
+    B2S_REQUIRE(tol == tol, "b2s_icp_batch: NaN tolerance");
+    int threads = (n_src + SRC_PER_THREAD - 1) / SRC_PER_THREAD;
+    threads = ((threads + 31) / 32) * 32;
+    if (threads < 64) threads = 64;
+    B2S_REQUIRE(threads <= 1024, "b2s_icp_batch: n_src above 4096 points per scan is not supported");
+    const size_t smem = 16 + 4 * 32 * sizeof(double) + (size_t)n_tar * sizeof(double2) +
+                        (size_t)n_tar * 2 * sizeof(TIn);
+    B2S_REQUIRE(smem <= 227 * 1024, "b2s_icp_batch: n_tar too large for shared memory");
+    static size_t configured[2] = {0, 0};
+    const int slot = sizeof(TIn) == 8;
+    if (smem > 48 * 1024 && smem > configured[slot]) {
+        B2S_CUDA(cudaFuncSetAttribute(icp_batch_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        configured[slot] = smem;
+    }
+    // bulk copy needs 16-byte aligned source and size: every pair's target block must qualify
+    const size_t pair_bytes = (size_t)2 * n_tar * sizeof(TIn);
+    const int use_bulk = ((uintptr_t)tar_xy % 16 == 0) && (pair_bytes % 16 == 0);
+    icp_batch_kernel<TIn><<<pairs, threads, smem, (cudaStream_t)stream>>>(
+        tar_xy, src_xy, n_src, n_tar, max_iter, tol, T_out, iters_out, use_bulk);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+
+}  // namespace b2s
+
+using namespace b2s;
+
+extern "C" int b2s_icp_batch_f32(const float *tar_xy, const float *src_xy, int pairs, int n_src,
+                                 int n_tar, int max_iter, double tol, double *T_out,
+                                 int32_t *iters_out, void *stream)
+{
+    return launch_icp<float>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream);
+}
+
+extern "C" int b2s_icp_batch_f64(const double *tar_xy, const double *src_xy, int pairs, int n_src,
+                                 int n_tar, int max_iter, double tol, double *T_out,
+                                 int32_t *iters_out, void *stream)
+{
+    return launch_icp<double>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream);
+}
+
+extern "C" int b2s_nearest_f64(const double *src_xy, int n, const double *tar_xy, int m,
+                               double *dist_out, int64_t *idx_out, void *stream)
+{
+    B2S_REQUIRE(n >= 0 && m >= 0, "b2s_nearest: negative size");
+    if (n == 0) return B2S_OK;
+    B2S_REQUIRE(src_xy && dist_out && idx_out && (tar_xy || m == 0), "b2s_nearest: null pointer");
+    nearest_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(src_xy, n, tar_xy, m, dist_out, idx_out);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+
+extern "C" int b2s_rigid_fit_f64(const double *src_xy, const double *tar_xy, int n, double *T_out,
+                                 void *stream)
+{
+    B2S_REQUIRE(n > 0, "b2s_rigid_fit: need at least one point");
+    B2S_REQUIRE(src_xy && tar_xy && T_out, "b2s_rigid_fit: null pointer");
+    rigid_fit_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(src_xy, tar_xy, n, T_out);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}

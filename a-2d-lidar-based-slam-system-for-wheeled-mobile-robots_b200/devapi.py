@@ -1,0 +1,77 @@
+"""Layer-1 C ABI on torch CUDA tensors: device pointers in, asynchronous on torch's current stream.
+
+torch is plumbing here (device memory, streams, torch.distributed); every kernel is in
+libb2slam.so.  Used by bench.py, the multi-GPU path (dist.py) and the parity tests.
+"""
+import torch
+
+from b2slam import _lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise ValueError("%s must be a contiguous CUDA tensor of dtype %s" % (name, dtype))
+    return t.data_ptr()
+
+
+def grid_scale(xw, yw, xyreso):
+    """(cells_per_m, off_x, off_y) exactly as b2s_mapping_create derives them."""
+    return 1.0 / xyreso, xw * xyreso / 2.0, yw * xyreso / 2.0
+
+
+def new_planes(xw, yw, device=None):
+    hit = torch.zeros((xw, yw), dtype=torch.int32, device=device or "cuda")
+    miss = torch.zeros_like(hit)
+    return hit, miss
+
+
+def grid_raycast(hit, miss, cells_per_m, off_x, off_y, ox, oy, cx, cy, counters=None):
+    """b2s_grid_raycast: hit/miss int32 (xw,yw); ox, oy float32 (K,N); cx, cy float32 (K,)."""
+    xw, yw = hit.shape
+    K, N = ox.shape
+    rc = _lib.lib().b2s_grid_raycast(
+        _chk(hit, torch.int32, "hit"), _chk(miss, torch.int32, "miss"), xw, yw,
+        float(cells_per_m), float(off_x), float(off_y),
+        _chk(ox, torch.float32, "ox"), _chk(oy, torch.float32, "oy"),
+        _chk(cx, torch.float32, "cx"), _chk(cy, torch.float32, "cy"), K, N,
+        None if counters is None else _chk(counters, torch.int32, "counters"), _stream())
+    _lib.check(rc)
+
+
+def grid_finalize(hit, miss, w_hit=20.0, w_miss=0.01, thresh=10.0, datamap=None, pmap=None):
+    xw, yw = hit.shape
+    rc = _lib.lib().b2s_grid_finalize(
+        _chk(hit, torch.int32, "hit"), _chk(miss, torch.int32, "miss"), xw, yw, float(w_hit),
+        float(w_miss), float(thresh),
+        None if datamap is None else _chk(datamap, torch.float32, "datamap"),
+        None if pmap is None else _chk(pmap, torch.int8, "pmap"), _stream())
+    _lib.check(rc)
+
+
+def grid_pack_ros(pmap, out=None):
+    xw, yw = pmap.shape
+    if out is None:
+        out = torch.empty(xw * yw, dtype=torch.int8, device=pmap.device)
+    _lib.check(_lib.lib().b2s_grid_pack_ros(_chk(pmap, torch.int8, "pmap"), xw, yw,
+                                            _chk(out, torch.int8, "out"), _stream()))
+    return out
+
+
+def icp_batch(tar, src, max_iter=30, tol=1e-3, T_out=None, iters_out=None):
+    """b2s_icp_batch_f32/f64: tar (P,2,M), src (P,2,N) float32 or float64 CUDA tensors."""
+    P, _, M = tar.shape
+    N = src.shape[2]
+    if T_out is None:
+        T_out = torch.empty((P, 3, 3), dtype=torch.float64, device=tar.device)
+    if iters_out is None:
+        iters_out = torch.empty(P, dtype=torch.int32, device=tar.device)
+    fn = _lib.lib().b2s_icp_batch_f64 if tar.dtype == torch.float64 else _lib.lib().b2s_icp_batch_f32
+    rc = fn(_chk(tar, tar.dtype, "tar"), _chk(src, tar.dtype, "src"), P, N, M, int(max_iter),
+            float(tol), _chk(T_out, torch.float64, "T_out"), _chk(iters_out, torch.int32, "iters"),
+            _stream())
+    _lib.check(rc)
+    return T_out, iters_out

@@ -1,0 +1,122 @@
+"""ICP scan matching on the GPU behind the reference's class API.
+
+Drop-in for `from icp import ICP` (W9 / W12 course_agv_slam/scripts/icp.py): same method
+names, argument order (TARGET first), shapes and float64 NumPy in/out.  All arithmetic runs
+in the CUDA library (include/b2slam.h); nothing here computes a distance or a fit.
+"""
+import ctypes
+
+import numpy as np
+
+from b2slam import _lib
+
+
+def _ros_param(name, default):
+    """rospy.get_param when a ROS master is reachable, else the reference default."""
+    try:
+        import rospy  # noqa: F401  (absent outside ROS; the class must import without it)
+        return rospy.get_param(name, default)
+    except Exception:
+        return default
+
+
+class ICP(object):
+    """[ICP]:10-36.  max_iter / dis_th / tolerance default to the reference's 30 / 5 / 0.001.
+
+    `dis_th` is read but never used by the reference either ([ICP]:23).  Pass
+    use_ros_params=True to look the values up on the ROS parameter server like the original.
+    """
+
+    def __init__(self, max_iter=30, dis_th=5, tolerance=0.001, use_ros_params=False, device=-1):
+        if use_ros_params:
+            max_iter = _ros_param('/icp/max_iter', max_iter)
+            dis_th = _ros_param('/icp/dis_th', dis_th)
+            tolerance = _ros_param('/icp/tolerance', tolerance)
+        self.max_iter = int(max_iter)
+        self.dis_th = dis_th
+        self.tolerance = float(tolerance)
+        self.isFirstScan = True
+        self.src_pc = []
+        self.tar_pc = []
+        self.last_iterations = None
+        self._L = _lib.lib()
+        _lib.require_device()
+        h = ctypes.c_void_p()
+        _lib.check(self._L.b2s_icp_create(ctypes.byref(h), int(device)))
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._L.b2s_icp_destroy(h)
+            self._h = None
+
+    # ------------------------------------------------------------------ reference methods
+
+    def process(self, tar_pc, src_pc):
+        """[ICP]:38-88.  tar_pc (3,M) / src_pc (3,N) (rows x, y, 1; only rows 0-1 are read).
+
+        Returns the 3x3 float64 transform taking the source scan into the target frame.
+        Inputs are not modified.
+        """
+        tar = np.ascontiguousarray(np.asarray(tar_pc, dtype=np.float64)[:2, :])
+        src = np.ascontiguousarray(np.asarray(src_pc, dtype=np.float64)[:2, :])
+        T, iters = self.process_batch(tar[None], src[None])
+        self.last_iterations = int(iters[0])
+        return T[0]
+
+    def findNearest(self, src, tar):
+        """[ICP]:90-114.  src (N,2), tar (M,2) -> (distances (N,), indices (N,) int)."""
+        src = np.ascontiguousarray(src, dtype=np.float64).reshape(-1, 2)
+        tar = np.ascontiguousarray(tar, dtype=np.float64).reshape(-1, 2)
+        n, m = src.shape[0], tar.shape[0]
+        dist = np.zeros(n)
+        idx = np.zeros(n, dtype=np.int64)
+        _lib.check(self._L.b2s_icp_find_nearest(self._h, _lib.ptr(src), n, _lib.ptr(tar), m,
+                                                _lib.ptr(dist), _lib.ptr(idx)))
+        return dist, idx
+
+    def getTransform(self, src, tar):
+        """[ICP]:149-179.  Row-matched src (N,2), tar (N,2) -> 3x3 T with tar ~= R src + t."""
+        src = np.ascontiguousarray(src, dtype=np.float64).reshape(-1, 2)
+        tar = np.ascontiguousarray(tar, dtype=np.float64).reshape(-1, 2)
+        if src.shape != tar.shape:
+            raise ValueError("getTransform needs row-matched clouds, got %s and %s"
+                             % (src.shape, tar.shape))
+        T = np.empty(9)
+        _lib.check(self._L.b2s_icp_get_transform(self._h, _lib.ptr(src), _lib.ptr(tar),
+                                                 src.shape[0], _lib.ptr(T)))
+        return T.reshape(3, 3)
+
+    def laserToNumpy(self, msg):
+        """[ICP]:216-229 (no inf clamp in this copy of the reference)."""
+        from b2slam import scan
+        return scan.laser_to_points(msg.ranges, msg.angle_min, msg.angle_max)
+
+    # ------------------------------------------------------------------ batched entry point
+
+    def process_batch(self, tar, src, max_iter=None, tolerance=None):
+        """ICP.process over P independent pairs in one launch.
+
+        tar (P,2,M), src (P,2,N): x row / y row per pair, float64 (the reference dtype) or
+        float32.  Returns (T (P,3,3) float64, iterations (P,) int32).
+        """
+        tar = np.asarray(tar)
+        src = np.asarray(src)
+        if tar.ndim != 3 or src.ndim != 3 or tar.shape[1] != 2 or src.shape[1] != 2 \
+                or tar.shape[0] != src.shape[0]:
+            raise ValueError("expected tar (P,2,M) and src (P,2,N), got %s and %s"
+                             % (tar.shape, src.shape))
+        f64 = not (tar.dtype == np.float32 and src.dtype == np.float32)
+        dt = np.float64 if f64 else np.float32
+        tar = np.ascontiguousarray(tar, dtype=dt)
+        src = np.ascontiguousarray(src, dtype=dt)
+        P, M, N = tar.shape[0], tar.shape[2], src.shape[2]
+        T = np.empty((P, 9))
+        iters = np.empty(P, dtype=np.int32)
+        _lib.check(self._L.b2s_icp_process(
+            self._h, _lib.ptr(tar), _lib.ptr(src), 1 if f64 else 0, P, N, M,
+            self.max_iter if max_iter is None else int(max_iter),
+            self.tolerance if tolerance is None else float(tolerance),
+            _lib.ptr(T), _lib.ptr(iters)))
+        return T.reshape(P, 3, 3), iters

@@ -1,0 +1,125 @@
+"""Occupancy-grid mapping on the GPU behind the reference's class API.
+
+Drop-in for `from mapping import Mapping` (W12 w12-mapping / w12-mapping-online
+course_agv_slam/scripts/mapping.py).  The device owns two int32 planes (endpoint hits,
+traversals) for the life of the object; `pmap` / `datamap` are materialised from them.
+"""
+import ctypes
+
+import numpy as np
+
+from b2slam import _lib
+
+
+class Mapping(object):
+    """[MAP]:7-51.  Mapping(xw, yw, xyreso) as in the reference, plus keyword weights:
+
+    hit_weight 20.0 ([MAP]:45; use 4.0 for w12-mapping-online, [MAPO]:46), miss_weight 0.01
+    ([MAP]:43), occ_threshold 10.0 ([MAP]:47).  The world->cell transform generalises the
+    reference's literals: cells_per_m = 1/xyreso, offset = extent/2 (exactly 10, 10 for the
+    reference's 200 x 200 x 0.1 m map).
+    """
+
+    def __init__(self, xw, yw, xyreso, hit_weight=20.0, miss_weight=0.01, occ_threshold=10.0,
+                 device=-1):
+        self.xw = int(xw)
+        self.yw = int(yw)
+        self.xyreso = float(xyreso)
+        self.width_x = self.xw * self.xyreso
+        self.width_y = self.yw * self.xyreso
+        self.minx = -self.width_x / 2.0
+        self.maxx = self.width_x / 2.0
+        self.miny = -self.width_y / 2.0
+        self.maxy = self.width_y / 2.0
+        self.hit_weight = float(hit_weight)
+        self.miss_weight = float(miss_weight)
+        self.occ_threshold = float(occ_threshold)
+        self._L = _lib.lib()
+        _lib.require_device()
+        h = ctypes.c_void_p()
+        _lib.check(self._L.b2s_mapping_create(ctypes.byref(h), self.xw, self.yw, self.xyreso,
+                                              self.hit_weight, self.miss_weight,
+                                              self.occ_threshold, int(device)))
+        self._h = h
+        self._pmap8 = np.full((self.xw, self.yw), 50, dtype=np.int8)
+        self.pmap = 50 * np.ones((self.xw, self.yw))  # [MAP]:14 unknown = 50
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._L.b2s_mapping_destroy(h)
+            self._h = None
+
+    # ------------------------------------------------------------------ reference methods
+
+    def update(self, ox, oy, center_x, center_y):
+        """[MAP]:22-51.  ox, oy (N,) world-frame endpoints, center_* scalar (or 1-element array,
+        as slam_ekf.py:90 passes).  Returns the (xw, yw) float64 occupancy in {0, 50, 100}.
+
+        Raises ValueError / OverflowError on NaN / inf where the reference's int() does
+        (infinite ox alone is skipped, [MAP]:30) -- but before any beam is applied.
+        """
+        ox = np.asarray(ox, dtype=np.float64).reshape(1, -1)
+        oy = np.asarray(oy, dtype=np.float64).reshape(1, -1)
+        cx = np.asarray(center_x, dtype=np.float64).reshape(-1)[:1]
+        cy = np.asarray(center_y, dtype=np.float64).reshape(-1)[:1]
+        return self.update_batch(ox, oy, cx, cy)
+
+    # ------------------------------------------------------------------ batched entry points
+
+    def update_batch(self, ox, oy, cx, cy, want_pmap=True):
+        """K scans at once: ox, oy (K,N); cx, cy (K,).  Coordinates are consumed as float32."""
+        ox = np.ascontiguousarray(ox, dtype=np.float32)
+        oy = np.ascontiguousarray(oy, dtype=np.float32)
+        cx = np.ascontiguousarray(cx, dtype=np.float32).reshape(-1)
+        cy = np.ascontiguousarray(cy, dtype=np.float32).reshape(-1)
+        if ox.ndim != 2 or ox.shape != oy.shape or cx.shape[0] != ox.shape[0] \
+                or cy.shape[0] != ox.shape[0]:
+            raise ValueError("expected ox, oy (K,N) and cx, cy (K,), got %s %s %s %s"
+                             % (ox.shape, oy.shape, cx.shape, cy.shape))
+        out = self._pmap8 if want_pmap else None
+        rc = self._L.b2s_mapping_update(self._h, _lib.ptr(ox), _lib.ptr(oy), _lib.ptr(cx),
+                                        _lib.ptr(cy), ox.shape[0], ox.shape[1], _lib.ptr(out))
+        if rc == _lib.ERR_NONFINITE:
+            bad_nan = np.isnan(ox).any() or np.isnan(oy).any() or np.isnan(cx).any() \
+                or np.isnan(cy).any()
+            if bad_nan:
+                raise ValueError("cannot convert float NaN to integer")
+            raise OverflowError("cannot convert float infinity to integer")
+        _lib.check(rc)
+        if want_pmap:
+            self.pmap = self._pmap8.astype(np.float64)
+            return self.pmap
+        return None
+
+    def counts(self):
+        """(hit, miss) int32 (xw, yw) snapshots of the device planes."""
+        hit = np.empty((self.xw, self.yw), dtype=np.int32)
+        miss = np.empty((self.xw, self.yw), dtype=np.int32)
+        _lib.check(self._L.b2s_mapping_read(self._h, _lib.ptr(hit), _lib.ptr(miss), None, None))
+        return hit, miss
+
+    @property
+    def datamap(self):
+        """Evidence score [MAP]:15 as float64, = miss_weight*miss + hit_weight*hit."""
+        d = np.empty((self.xw, self.yw), dtype=np.float32)
+        _lib.check(self._L.b2s_mapping_read(self._h, None, None, _lib.ptr(d), None))
+        return d.astype(np.float64)
+
+    def occupancy(self):
+        """int8 (xw, yw) occupancy in {0, 50, 100} straight from the device."""
+        p = np.empty((self.xw, self.yw), dtype=np.int8)
+        _lib.check(self._L.b2s_mapping_read(self._h, None, None, None, _lib.ptr(p)))
+        return p
+
+    def reset(self):
+        _lib.check(self._L.b2s_mapping_reset(self._h))
+        self._pmap8.fill(50)
+        self.pmap = 50 * np.ones((self.xw, self.yw))
+
+    def device_planes(self):
+        """(hit_ptr, miss_ptr, stream_ptr) integers for layer-1 calls and collectives."""
+        h, m, s = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(self._L.b2s_mapping_planes(self._h, ctypes.byref(h), ctypes.byref(m),
+                                              ctypes.byref(s)))
+        return h.value, m.value, s.value or 0

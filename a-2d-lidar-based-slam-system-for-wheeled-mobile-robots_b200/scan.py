@@ -1,0 +1,54 @@
+"""Host-side adjacent steps of the hot path: scan conversion, pose chain.
+
+These are the tiny sequential pieces the ROS nodes run around ICP.process / Mapping.update;
+they stay on the host in float64 exactly like the reference.
+"""
+import math
+
+import numpy as np
+
+MAX_LASER_RANGE = 30  # W12 slam_ekf.py:18
+
+
+def laser_to_points(ranges, angle_min, angle_max, clamp_inf_to=None):
+    """laserToNumpy: [ICP]:216-229 (clamp_inf_to=None) / W12 slam_ekf.py:115-123 (30 m clamp).
+
+    Returns the (3, N) float64 homogeneous cloud [r cos a; r sin a; 1].
+    """
+    r = np.array(ranges, dtype=np.float64)
+    if clamp_inf_to is not None:
+        r[r == np.inf] = clamp_inf_to
+    n = r.shape[0]
+    a = np.linspace(angle_min, angle_max, n)
+    pc = np.ones((3, n))
+    pc[0, :] = np.cos(a) * r
+    pc[1, :] = np.sin(a) * r
+    return pc
+
+
+def T2u(t):
+    """W12 slam_ekf.py:125-128: 3x3 transform -> (dx, dy, dyaw) column."""
+    return np.array([[t[0, 2], t[1, 2], math.atan2(t[1, 0], t[0, 0])]]).T
+
+
+def u2T(u):
+    """W12 slam_ekf.py:130-137: pose (x, y, yaw) -> 2x3 world transform."""
+    x, y, w = (float(np.asarray(v).reshape(-1)[0]) for v in (u[0], u[1], u[2]))
+    return np.array([[math.cos(w), -math.sin(w), x], [math.sin(w), math.cos(w), y]])
+
+
+def compose_odometry(state, transforms):
+    """Odometry chain, [ICP]:185-190 / W9 localization.py:79-83, over a (P,3,3) stack.
+
+    Returns the (P+1, 3) trajectory starting at `state`.
+    """
+    out = np.empty((len(transforms) + 1, 3))
+    x, y, th = (float(v) for v in state)
+    out[0] = (x, y, th)
+    for i, t in enumerate(transforms):
+        dyaw = math.atan2(t[1, 0], t[0, 0])
+        nx = x + math.cos(th) * t[0, 2] - math.sin(th) * t[1, 2]
+        ny = y + math.sin(th) * t[0, 2] + math.cos(th) * t[1, 2]
+        x, y, th = nx, ny, th + dyaw
+        out[i + 1] = (x, y, th)
+    return out

@@ -1,0 +1,150 @@
+/*
+ * b2slam C ABI -- the drop-in boundary of the B200-native ICP / occupancy-grid hot path.
+ *
+ * The reference (zjwzcx/A-2D-LiDAR-based-SLAM-System-for-Wheeled-Mobile-Robots) has no FFI
+ * layer: its boundary is the Python class API of course_agv_slam/scripts/{icp,mapping,
+ * bresenham}.py.  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference root):
+ *   [ICP]  W9_Fusion Localization (LiDAR Odometry)/course_agv_slam/scripts/icp.py
+ *   [MAP]  W12_LiDAR SLAM/w12-mapping/course_agv_slam/scripts/mapping.py
+ *   [MAPO] W12_LiDAR SLAM/w12-mapping-online/course_agv_slam/scripts/mapping.py
+ *   [BRES] W12_LiDAR SLAM/w12-mapping/course_agv_slam/scripts/bresenham.py
+ *   [SLAM] W12_LiDAR SLAM/w12-mapping/course_agv_slam/scripts/slam_ekf.py
+ *
+ * Two layers:
+ *   layer 1  b2s_*            device pointers, asynchronous on the given CUDA stream
+ *   layer 2  b2s_icp_* / b2s_mapping_*  host buffers in, host buffers out (the calls the
+ *            Python classes ICP / Mapping make); copies and kernels run on the object's stream
+ *
+ * All functions return 0 (B2S_OK) or a negative status; b2s_last_error() gives the detail.
+ * Plain pointers and sizes only; there is no CPU fallback -- without a CUDA device every
+ * compute entry point returns B2S_ERR_CUDA.
+ */
+#ifndef B2SLAM_H
+#define B2SLAM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_OK 0
+#define B2S_ERR_INVALID_ARG (-1) /* bad shape / null pointer / negative size */
+#define B2S_ERR_NONFINITE (-2)   /* NaN/inf coordinate the reference raises ValueError/OverflowError on */
+#define B2S_ERR_CUDA (-3)        /* CUDA runtime error or no device */
+#define B2S_ERR_TOO_LONG (-4)    /* a beam longer than B2S_MAX_PATH_CELLS cells */
+#define B2S_ERR_NCCL (-5)        /* NCCL missing or failed */
+#define B2S_ERR_NOMEM (-6)
+
+#define B2S_MAX_PATH_CELLS (1 << 22)
+
+/* index into the optional device counters of b2s_grid_raycast */
+#define B2S_CNT_NONFINITE 0 /* beams dropped: NaN anywhere, inf in oy or the sensor position */
+#define B2S_CNT_TOO_LONG 1  /* beams dropped: longer than B2S_MAX_PATH_CELLS */
+#define B2S_CNT_SKIPPED_INF 2 /* beams skipped because ox is +-inf ([MAP]:30), not an error */
+#define B2S_CNT_WORDS 4
+
+int b2s_version(void);
+const char *b2s_status_string(int status);
+const char *b2s_last_error(void); /* thread-local, valid until the next call on this thread */
+int b2s_device_count(int *count);
+/* Kernel-variant switch for benchmarking (key "grid_variant": 1 = one RED per visit, 2 = warp-
+ * aggregated runs, the default).  Not part of the reference surface. */
+int b2s_tune(const char *key, int value);
+
+/* ===================================================================== layer 1: device */
+
+/* ICP.process for a batch of independent scan pairs -- replaces [ICP]:38-88 (and through it
+ * findNearest [ICP]:90-114 and getTransform [ICP]:149-179).
+ *   tar_xy [pairs][2][n_tar], src_xy [pairs][2][n_src]: x row then y row, i.e. rows 0-1 of the
+ *   3xN homogeneous arrays the reference passes.  T_out [pairs][9] row-major 3x3 float64 mapping
+ *   the source scan into the target frame; iters_out [pairs] iterations run (may be NULL).
+ *   max_iter / tol are rospy.get_param('/icp/max_iter', 30) / ('/icp/tolerance', 0.001). */
+int b2s_icp_batch_f32(const float *tar_xy, const float *src_xy, int pairs, int n_src, int n_tar,
+                      int max_iter, double tol, double *T_out, int32_t *iters_out, void *stream);
+int b2s_icp_batch_f64(const double *tar_xy, const double *src_xy, int pairs, int n_src, int n_tar,
+                      int max_iter, double tol, double *T_out, int32_t *iters_out, void *stream);
+
+/* ICP.findNearest -- replaces [ICP]:90-114.  src_xy [n][2], tar_xy [m][2] (row = point, as the
+ * reference passes them); dist_out [n] float64, idx_out [n] int64.  Lowest index wins ties. */
+int b2s_nearest_f64(const double *src_xy, int n, const double *tar_xy, int m, double *dist_out,
+                    int64_t *idx_out, void *stream);
+
+/* ICP.getTransform -- replaces [ICP]:149-179.  src_xy, tar_xy [n][2] row-matched; T_out [9]. */
+int b2s_rigid_fit_f64(const double *src_xy, const double *tar_xy, int n, double *T_out,
+                      void *stream);
+
+/* Mapping.update in integer form -- replaces [MAP]:22-51 with bresenham [BRES]:2-58 inlined.
+ *   hit, miss [xw][yw] int32, x-major like the reference's datamap[x][y]; updated atomically.
+ *   ox, oy [scans][beams] world-frame endpoints; cx, cy [scans] sensor positions.
+ *   cell = (int)(cells_per_m * (v + off)) in float64, truncating ([MAP]:33-36: 10, 10).
+ *   counters: device int32[B2S_CNT_WORDS] accumulating dropped/skipped beams, or NULL. */
+int b2s_grid_raycast(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m,
+                     double off_x, double off_y, const float *ox, const float *oy,
+                     const float *cx, const float *cy, int scans, int beams, int32_t *counters,
+                     void *stream);
+
+/* Evidence score and occupancy from the counts -- replaces the per-visit rule of [MAP]:42-50
+ * (w_hit 20) / [MAPO]:43-51 (w_hit 4): datamap = w_miss*miss + w_hit*hit (float32 out),
+ * pmap = 50 if untouched else (100 if datamap > thresh else 0).  Either output may be NULL. */
+int b2s_grid_finalize(const int32_t *hit, const int32_t *miss, int xw, int yw, double w_hit,
+                      double w_miss, double thresh, float *datamap, int8_t *pmap, void *stream);
+
+/* OccupancyGrid payload -- replaces [SLAM]:270-271: data[y*xw + x] = (int8) pmap[x][y]. */
+int b2s_grid_pack_ros(const int8_t *pmap, int xw, int yw, int8_t *data, void *stream);
+
+/* bresenham(start, end).path for a batch of segments -- replaces [BRES]:2-58.
+ *   segs [count][4] = x0,y0,x1,y1; offsets [count+1] exclusive prefix sums of the path lengths
+ *   (max(|dx|,|dy|)+1, 0 for a same-cell segment); cells_xy [offsets[count]][2]. */
+int b2s_bresenham_paths(const int32_t *segs, int count, const int64_t *offsets, int32_t *cells_xy,
+                        void *stream);
+
+/* Sum of per-GPU count deltas (no reference counterpart: the reference is single-process).
+ * In-place ncclAllReduce(int32, sum) of both planes on an existing communicator. */
+int b2s_grid_allreduce(int32_t *hit, int32_t *miss, size_t cells, void *nccl_comm, void *stream);
+
+/* NCCL plumbing for callers that do not bring their own communicator. */
+int b2s_nccl_unique_id(void *id128);
+int b2s_nccl_comm_init(void **comm_out, int nranks, int rank, const void *id128);
+int b2s_nccl_comm_destroy(void *comm);
+
+/* ===================================================================== layer 2: host */
+
+typedef struct b2s_icp b2s_icp;
+typedef struct b2s_mapping b2s_mapping;
+
+/* ICP() -- [ICP]:11-36.  device < 0 selects the current device. */
+int b2s_icp_create(b2s_icp **out, int device);
+int b2s_icp_destroy(b2s_icp *icp);
+/* ICP.process on host arrays; is_f64 selects const double* (the reference's dtype) or const float*. */
+int b2s_icp_process(b2s_icp *icp, const void *tar_xy, const void *src_xy, int is_f64, int pairs,
+                    int n_src, int n_tar, int max_iter, double tol, double *T_out,
+                    int32_t *iters_out);
+int b2s_icp_find_nearest(b2s_icp *icp, const double *src_xy, int n, const double *tar_xy, int m,
+                         double *dist_out, int64_t *idx_out);
+int b2s_icp_get_transform(b2s_icp *icp, const double *src_xy, const double *tar_xy, int n,
+                          double *T_out);
+
+/* Mapping(xw, yw, xyreso) -- [MAP]:8-20.  Owns zeroed int32 hit/miss planes on the device. */
+int b2s_mapping_create(b2s_mapping **out, int xw, int yw, double xyreso, double w_hit,
+                       double w_miss, double thresh, int device);
+int b2s_mapping_destroy(b2s_mapping *map);
+int b2s_mapping_reset(b2s_mapping *map);
+/* Mapping.update -- [MAP]:22-51 for `scans` scans at once.  Validates like the reference
+ * (B2S_ERR_NONFINITE where int() would raise) BEFORE touching the planes; when pmap_out is
+ * not NULL it receives the refreshed occupancy [xw][yw]. */
+int b2s_mapping_update(b2s_mapping *map, const float *ox, const float *oy, const float *cx,
+                       const float *cy, int scans, int beams, int8_t *pmap_out);
+/* Snapshot to host; any pointer may be NULL. */
+int b2s_mapping_read(b2s_mapping *map, int32_t *hit, int32_t *miss, float *datamap, int8_t *pmap);
+/* The planes themselves, for layer-1 calls and collectives. */
+int b2s_mapping_planes(b2s_mapping *map, int32_t **hit, int32_t **miss, void **stream);
+/* bresenham(start,end).path on host arrays (segs [count][4], cells_xy sized by the caller). */
+int b2s_bresenham_host(const int32_t *segs, int count, const int64_t *offsets, int32_t *cells_xy);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2SLAM_H */

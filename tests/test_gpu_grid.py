@@ -1,0 +1,251 @@
+"""GPU parity: occupancy-grid path (A4-A7) through the C ABI against the CPU oracle and the
+golden vectors produced by the reference.  Integer counts and cell indices are bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def env():
+    import b2slam
+    from b2slam import _lib, devapi, synth
+    from b2slam import bresenham as bres
+    from oracle import corc, pyref
+    if _lib.device_count() <= 0:
+        pytest.fail("no CUDA device: the gpu tests must run on the B200 box")
+
+    class E:
+        pass
+    e = E()
+    e.b2slam, e.lib, e.dev, e.synth, e.bres, e.corc, e.pyref = b2slam, _lib, devapi, synth, bres, corc, pyref
+    return e
+
+
+def _variants(env):
+    for v in (1, 2):
+        assert env.lib.lib().b2s_tune(b"grid_variant", v) == 0
+        yield v
+    env.lib.lib().b2s_tune(b"grid_variant", 2)
+
+
+# ----------------------------------------------------------------------------- bresenham (A7)
+
+def test_bresenham_paths_equal_reference(env):
+    z = load_golden("bresenham.npz")
+    cells, offs = env.bres.paths(z["segs"])
+    assert np.array_equal(offs, z["offsets"])
+    assert np.array_equal(cells, z["cells"])
+
+
+def test_bresenham_class_api(env):
+    p = env.b2slam.bresenham([0, 0], [10, 3]).path
+    assert p == env.corc.bresenham([0, 0], [10, 3])
+    assert env.b2slam.bresenham([5, 5], [5, 5]).path == []
+    assert env.b2slam.bresenham([3, 9], [3, 2]).path == env.pyref.bresenham_cells([3, 9], [3, 2])
+
+
+def test_bresenham_long_random_segments_vs_oracle(env):
+    rng = np.random.Generator(np.random.PCG64(77))
+    segs = rng.integers(-3000, 3000, size=(3000, 4)).astype(np.int32)
+    cells, offs = env.bres.paths(segs)
+    for i in rng.integers(0, len(segs), size=150):
+        want = env.corc.bresenham(segs[i, :2], segs[i, 2:])
+        got = [tuple(r) for r in cells[offs[i]:offs[i + 1]].tolist()]
+        assert got == want
+
+
+# ----------------------------------------------------------------------------- Mapping (A4-A6)
+
+@pytest.mark.parametrize("tag,w_hit", [("w20", 20.0), ("w4", 4.0)])
+def test_mapping_class_reproduces_reference_maps(env, tag, w_hit):
+    z = load_golden("mapping.npz")
+    for v in _variants(env):
+        m = env.b2slam.Mapping(200, 200, 0.1, hit_weight=w_hit)
+        assert m.pmap.shape == (200, 200) and (m.pmap == 50).all()
+        for ox, oy, cx, cy in zip(z[tag + "_ox"], z[tag + "_oy"], z[tag + "_cx"], z[tag + "_cy"]):
+            pm = m.update(ox.astype(np.float64), oy.astype(np.float64), float(cx), np.array([float(cy)]))
+        hit, miss = m.counts()
+        oh = np.zeros((200, 200), dtype=np.int32)
+        om = np.zeros((200, 200), dtype=np.int32)
+        env.corc.grid_raycast(oh, om, 10.0, 10.0, 10.0, z[tag + "_ox"], z[tag + "_oy"], z[tag + "_cx"], z[tag + "_cy"])
+        assert np.array_equal(hit, oh) and np.array_equal(miss, om), "variant %d" % v
+        amb = env.pyref.boundary_ambiguous(hit, miss, w_hit)
+        assert ((pm == z[tag + "_pmap"]) | amb).all()
+        if w_hit == 20.0:
+            assert np.array_equal(pm.astype(np.int8), z[tag + "_pmap"])
+        assert pm.dtype == np.float64 and set(np.unique(pm)) <= {0.0, 50.0, 100.0}
+        np.testing.assert_allclose(m.datamap, z[tag + "_datamap"], rtol=1e-5, atol=1e-6)  # fp32 score
+        assert np.array_equal(m.occupancy(), pm.astype(np.int8))
+
+
+def test_mapping_edge_cases(env):
+    m = env.b2slam.Mapping(200, 200, 0.1)
+    pm = m.update(np.array([]), np.array([]), 0.0, 0.0)            # empty scan
+    assert (pm == 50).all()
+    pm = m.update(np.array([np.inf, -np.inf]), np.array([0.0, 1.0]), 0.0, 0.0)  # skipped beams
+    assert (pm == 50).all()
+    pm = m.update(np.array([0.004]), np.array([0.003]), 0.0, 0.0)  # same cell: no update at all
+    assert (pm == 50).all()
+    with pytest.raises(ValueError):
+        m.update(np.array([1.0, np.nan]), np.array([0.0, 0.0]), 0.0, 0.0)
+    with pytest.raises(OverflowError):
+        m.update(np.array([1.0]), np.array([np.inf]), 0.0, 0.0)
+    with pytest.raises(ValueError):
+        m.update(np.array([1.0]), np.array([1.0]), np.nan, 0.0)
+    assert (m.counts()[0] == 0).all() and (m.counts()[1] == 0).all()  # nothing applied on error
+    pm = m.update(np.array([30.0]), np.array([0.45]), 0.05, 0.05)  # endpoint outside: clipped, no hit
+    hit, miss = m.counts()
+    assert hit.sum() == 0 and miss.sum() == 100 and (pm[100:, 100] == 0).all()
+    m.reset()
+    assert (m.counts()[1] == 0).all() and (m.pmap == 50).all()
+
+
+def test_mapping_threshold_stream(env):
+    """1000 traversals stay free, the 1001st flips the cell (reference golden, [MAP]:47)."""
+    z = load_golden("mapping.npz")
+    m = env.b2slam.Mapping(200, 200, 0.1)
+    ox = np.full((1000, 1), 1.05, dtype=np.float32)
+    oy = np.full((1000, 1), 0.05, dtype=np.float32)
+    c = np.full(1000, 0.05, dtype=np.float32)
+    pm = m.update_batch(ox, oy, c, c)
+    assert pm[105, 100] == z["miss_stream_pmap"][0] == 0
+    pm = m.update_batch(ox[:1], oy[:1], c[:1], c[:1])
+    assert pm[105, 100] == z["miss_stream_pmap"][1] == 100
+
+
+def test_non_square_grid_and_generalised_scale(env):
+    S, Hx, Hy = env.dev.grid_scale(300, 180, 0.05)
+    ox, oy, cx, cy = env.synth.grid_scans(31, 12, 360, half_extent_m=3.0)
+    for v in _variants(env):
+        m = env.b2slam.Mapping(300, 180, 0.05)
+        m.update_batch(ox, oy, cx, cy)
+        hit, miss = m.counts()
+        oh = np.zeros((300, 180), dtype=np.int32)
+        om = np.zeros((300, 180), dtype=np.int32)
+        env.corc.grid_raycast(oh, om, S, Hx, Hy, ox, oy, cx, cy)
+        assert np.array_equal(hit, oh) and np.array_equal(miss, om)
+
+
+# ----------------------------------------------------------------------------- cfg 3 (4096^2, 1080 beams)
+
+def _device_scans(env, seed, K, N, half):
+    ox, oy, cx, cy = env.synth.grid_scans(seed, K, N, half_extent_m=half)
+    t = [torch.from_numpy(a).cuda() for a in (ox, oy, cx, cy)]
+    return (ox, oy, cx, cy), t
+
+
+def test_cfg3_counts_bit_exact_vs_oracle(env):
+    G, reso, K, N = 4096, 0.05, 96, 1080
+    S, Hx, Hy = env.dev.grid_scale(G, G, reso)
+    assert (S, Hx, Hy) == (20.0, 102.4, 102.4)
+    host, devt = _device_scans(env, 12001, K, N, 80.0)
+    oh = np.zeros((G, G), dtype=np.int32)
+    om = np.zeros((G, G), dtype=np.int32)
+    visits = env.corc.grid_raycast(oh, om, S, Hx, Hy, *host)
+    for v in _variants(env):
+        hit, miss = env.dev.new_planes(G, G)
+        cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
+        env.dev.grid_raycast(hit, miss, S, Hx, Hy, *devt, counters=cnt)
+        torch.cuda.synchronize()
+        assert int(hit.sum().item() + miss.sum().item()) == visits
+        assert np.array_equal(hit.cpu().numpy(), oh), "variant %d" % v
+        assert np.array_equal(miss.cpu().numpy(), om), "variant %d" % v
+        assert cnt.tolist() == [0, 0, 0, 0]
+    pmap = torch.empty((G, G), dtype=torch.int8, device="cuda")
+    score = torch.empty((G, G), dtype=torch.float32, device="cuda")
+    env.dev.grid_finalize(hit, miss, pmap=pmap, datamap=score)
+    osc, opm = env.corc.grid_finalize(oh, om)
+    assert np.array_equal(pmap.cpu().numpy(), opm)
+    np.testing.assert_allclose(score.cpu().numpy(), osc, rtol=1e-6, atol=0)
+    ros = env.dev.grid_pack_ros(pmap).cpu().numpy()
+    assert np.array_equal(ros, opm.T.reshape(-1))  # slam_ekf.py:270
+
+
+def test_cfg3_full_size_properties(env):
+    """Size-independent checks at the bench size: variants agree, sharded == single pass,
+    update(A) + update(B) == update(A u B), visits == sum of per-beam path lengths in grid."""
+    G, reso, K, N = 4096, 0.05, 4096, 1080
+    S, Hx, Hy = env.dev.grid_scale(G, G, reso)
+    _, devt = _device_scans(env, 12001, K, N, 80.0)
+    ox, oy, cx, cy = devt
+    env.lib.lib().b2s_tune(b"grid_variant", 1)
+    h1, m1 = env.dev.new_planes(G, G)
+    env.dev.grid_raycast(h1, m1, S, Hx, Hy, ox, oy, cx, cy)
+    env.lib.lib().b2s_tune(b"grid_variant", 2)
+    h2, m2 = env.dev.new_planes(G, G)
+    env.dev.grid_raycast(h2, m2, S, Hx, Hy, ox, oy, cx, cy)
+    assert torch.equal(h1, h2) and torch.equal(m1, m2)
+    # every beam of this workload ends inside the grid -> exactly one hit per non-degenerate beam
+    assert int(h2.sum().item()) <= K * N and int(h2.sum().item()) > 0.99 * K * N
+    # 4 emulated ranks: private delta planes summed == single pass (integer sums commute)
+    acc_h, acc_m = env.dev.new_planes(G, G)
+    for r in range(4):
+        lo, hi = r * K // 4, (r + 1) * K // 4
+        dh, dm = env.dev.new_planes(G, G)
+        env.dev.grid_raycast(dh, dm, S, Hx, Hy, ox[lo:hi].contiguous(), oy[lo:hi].contiguous(),
+                             cx[lo:hi].contiguous(), cy[lo:hi].contiguous())
+        acc_h += dh
+        acc_m += dm
+    assert torch.equal(acc_h, h2) and torch.equal(acc_m, m2)
+    # accumulate in two calls on the same planes
+    bh, bm = env.dev.new_planes(G, G)
+    half = K // 2
+    env.dev.grid_raycast(bh, bm, S, Hx, Hy, ox[:half].contiguous(), oy[:half].contiguous(),
+                         cx[:half].contiguous(), cy[:half].contiguous())
+    env.dev.grid_raycast(bh, bm, S, Hx, Hy, ox[half:].contiguous(), oy[half:].contiguous(),
+                         cx[half:].contiguous(), cy[half:].contiguous())
+    assert torch.equal(bh, h2) and torch.equal(bm, m2)
+
+
+def test_clipping_out_of_grid_and_counters(env):
+    """Sensor outside the grid, endpoints outside, rays crossing a corner; inf / NaN counters."""
+    G = 512
+    S, Hx, Hy = env.dev.grid_scale(G, G, 0.05)   # +-12.8 m
+    rng = np.random.Generator(np.random.PCG64(9))
+    K, N = 40, 256
+    cx = rng.uniform(-20, 20, K).astype(np.float32)
+    cy = rng.uniform(-20, 20, K).astype(np.float32)
+    ang = rng.uniform(-np.pi, np.pi, (K, N))
+    r = rng.uniform(0.0, 30.0, (K, N))
+    ox = (cx[:, None] + r * np.cos(ang)).astype(np.float32)
+    oy = (cy[:, None] + r * np.sin(ang)).astype(np.float32)
+    oh = np.zeros((G, G), dtype=np.int32)
+    om = np.zeros((G, G), dtype=np.int32)
+    env.corc.grid_raycast(oh, om, S, Hx, Hy, ox, oy, cx, cy)
+    assert om.sum() > 0
+    for v in _variants(env):
+        hit, miss = env.dev.new_planes(G, G)
+        env.dev.grid_raycast(hit, miss, S, Hx, Hy, *[torch.from_numpy(a).cuda() for a in (ox, oy, cx, cy)])
+        assert np.array_equal(hit.cpu().numpy(), oh) and np.array_equal(miss.cpu().numpy(), om)
+    ox2 = ox.copy()
+    oy2 = oy.copy()
+    ox2[0, 0] = np.inf
+    ox2[0, 1] = np.nan
+    oy2[0, 2] = np.inf
+    ox2[0, 3] = 3e30
+    hit, miss = env.dev.new_planes(G, G)
+    cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
+    env.dev.grid_raycast(hit, miss, S, Hx, Hy, *[torch.from_numpy(a).cuda() for a in (ox2, oy2, cx, cy)],
+                         counters=cnt)
+    assert cnt.tolist() == [2, 1, 1, 0]
+
+
+def test_cfg5_shape_smoke(env):
+    """16384^2 planes (1 GiB each): allocation, a few scans, finalize."""
+    G = 16384
+    S, Hx, Hy = env.dev.grid_scale(G, G, 0.05)
+    assert (Hx, Hy) == (409.6, 409.6)
+    host, devt = _device_scans(env, 5001, 8, 1080, 300.0)
+    hit, miss = env.dev.new_planes(G, G)
+    env.dev.grid_raycast(hit, miss, S, Hx, Hy, *devt)
+    oh = np.zeros((G, G), dtype=np.int32)
+    om = np.zeros((G, G), dtype=np.int32)
+    env.corc.grid_raycast(oh, om, S, Hx, Hy, *host)
+    nz = np.nonzero(oh | om)
+    assert np.array_equal(hit.cpu().numpy()[nz], oh[nz]) and np.array_equal(miss.cpu().numpy()[nz], om[nz])
+    assert int(miss.sum().item()) == int(om.sum())

@@ -1,0 +1,125 @@
+"""GPU parity: ICP path (A1-A3) through the C ABI against the reference goldens and the CPU
+oracle.  Tolerance: T within 1e-9 absolute of the float64 reference (the north star allows
+1e-5 relative); iteration counts equal."""
+import numpy as np
+import pytest
+
+from conftest import icp_cases, load_golden
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+T_ATOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def env():
+    import b2slam
+    from b2slam import _lib, devapi, synth
+    from oracle import corc
+    if _lib.device_count() <= 0:
+        pytest.fail("no CUDA device: the gpu tests must run on the B200 box")
+
+    class E:
+        pass
+    e = E()
+    e.b2slam, e.lib, e.dev, e.synth, e.corc = b2slam, _lib, devapi, synth, corc
+    e.icp = b2slam.ICP()
+    return e
+
+
+@pytest.mark.parametrize("case", icp_cases(), ids=lambda c: "seed%d_n%d_it%d" % (
+    int(c["seed"]), c["src"].shape[1], int(c["max_iter"])))
+def test_process_matches_reference_golden(env, case):
+    icp = env.b2slam.ICP(max_iter=int(case["max_iter"]), tolerance=float(case["tol"]))
+    tar = env.synth.homogeneous(case["tar"].astype(np.float64))
+    src = env.synth.homogeneous(case["src"].astype(np.float64))
+    keep_t, keep_s = tar.copy(), src.copy()
+    T = icp.process(tar, src)                      # target first, like the reference
+    assert T.shape == (3, 3) and T.dtype == np.float64
+    assert icp.last_iterations == int(case["iters"])
+    np.testing.assert_allclose(T, case["T"], rtol=0, atol=T_ATOL)
+    assert np.array_equal(T[2], [0.0, 0.0, 1.0])
+    assert np.array_equal(tar, keep_t) and np.array_equal(src, keep_s)  # inputs untouched
+
+
+def test_find_nearest_ties_and_golden(env):
+    z = load_golden("icp_pieces.npz")
+    for s, t, d, i in (("tie_src", "tie_tar", "tie_dist", "tie_idx"),
+                       ("sym_src", "sym_tar", "sym_dist", "sym_idx")):
+        dist, idx = env.icp.findNearest(z[s], z[t])
+        assert np.array_equal(idx, z[i])
+        np.testing.assert_allclose(dist, z[d], rtol=0, atol=1e-14)
+    big_s = np.random.Generator(np.random.PCG64(5)).uniform(-10, 10, (3000, 2))
+    big_t = np.random.Generator(np.random.PCG64(6)).uniform(-10, 10, (2500, 2))
+    dist, idx = env.icp.findNearest(big_s, big_t)
+    od, oi = env.corc.nearest(big_s, big_t)
+    assert np.array_equal(idx, oi) and np.allclose(dist, od, rtol=0, atol=1e-14)
+
+
+def test_get_transform_golden_including_reflections(env):
+    z = load_golden("icp_pieces.npz")
+    for a, b, T in zip(z["fit_src"], z["fit_tar"], z["fit_T"]):
+        np.testing.assert_allclose(env.icp.getTransform(a, b), T, rtol=0, atol=1e-12)
+    with pytest.raises(ValueError):
+        env.icp.getTransform(np.zeros((4, 2)), np.zeros((5, 2)))
+
+
+@pytest.mark.parametrize("beams,pairs", [(120, 96), (360, 64), (1080, 12)])
+def test_batch_vs_oracle(env, beams, pairs):
+    tar, src, _ = env.synth.icp_pairs(4001, pairs, beams)
+    want_T, want_it = env.corc.icp_batch(tar, src, 30, 1e-3)
+    T32, it32 = env.icp.process_batch(tar, src)                                   # float32 inputs
+    T64, it64 = env.icp.process_batch(tar.astype(np.float64), src.astype(np.float64))
+    bad = int((it32 != want_it).sum())
+    assert bad == 0, "%d pairs stopped at a different iteration" % bad
+    assert np.array_equal(it32, it64)
+    np.testing.assert_allclose(T32, want_T, rtol=0, atol=T_ATOL)
+    np.testing.assert_allclose(T64, T32, rtol=0, atol=1e-13)
+
+
+def test_w7_launch_parameters_run_exactly_max_iter(env):
+    tar, src, _ = env.synth.icp_pairs(7001, 1, 360)
+    T, iters = env.icp.process_batch(tar, src, max_iter=10, tolerance=0.0)
+    assert iters[0] == 10                      # strict '<': tolerance 0 never breaks
+    want_T, _ = env.corc.icp_batch(tar, src, 10, 0.0)
+    np.testing.assert_allclose(T, want_T, rtol=0, atol=T_ATOL)
+
+
+def test_unequal_sizes_odd_counts_and_zero_iterations(env):
+    tar, src, _ = env.synth.icp_pairs(91, 5, 150)
+    src = np.ascontiguousarray(src[:, :, :97])       # N=97 (odd: no bulk-copy alignment), M=150
+    want_T, want_it = env.corc.icp_batch(tar, src, 30, 1e-3)
+    T, it = env.icp.process_batch(tar, src)
+    assert np.array_equal(it, want_it)
+    np.testing.assert_allclose(T, want_T, rtol=0, atol=T_ATOL)
+    tar2 = np.ascontiguousarray(tar[:, :, :77])      # M=77: unaligned target rows
+    want_T, want_it = env.corc.icp_batch(tar2, src, 30, 1e-3)
+    T, it = env.icp.process_batch(tar2, src)
+    assert np.array_equal(it, want_it)
+    np.testing.assert_allclose(T, want_T, rtol=0, atol=T_ATOL)
+    T0, it0 = env.icp.process_batch(tar, src, max_iter=0)
+    assert (it0 == 0).all()
+    np.testing.assert_allclose(T0, np.broadcast_to(np.identity(3), T0.shape), rtol=0, atol=1e-12)
+    Te, ite = env.icp.process_batch(tar[:0], src[:0])
+    assert Te.shape == (0, 3, 3) and ite.shape == (0,)
+
+
+def test_device_pointer_abi_and_sequence_chain(env):
+    """Layer 1 on CUDA tensors; cfg-2 style consecutive pairs of a room sequence."""
+    xy, _ = env.synth.room_sequence(9001, 65, 360)
+    tar = torch.from_numpy(xy[:-1]).cuda().contiguous()
+    src = torch.from_numpy(xy[1:]).cuda().contiguous()
+    T, it = env.dev.icp_batch(tar, src, 30, 1e-3)
+    torch.cuda.synchronize()
+    want_T, want_it = env.corc.icp_batch(xy[:-1], xy[1:], 30, 1e-3)
+    assert np.array_equal(it.cpu().numpy(), want_it)
+    np.testing.assert_allclose(T.cpu().numpy(), want_T, rtol=0, atol=T_ATOL)
+    from b2slam import scan
+    from oracle import pyref
+    traj = scan.compose_odometry((0.0, 0.0, 0.0), T.cpu().numpy())
+    st = (0.0, 0.0, 0.0)
+    for t in want_T:
+        st = pyref.compose_pose(st, t)
+    assert np.allclose(traj[-1], st, rtol=0, atol=1e-7)
