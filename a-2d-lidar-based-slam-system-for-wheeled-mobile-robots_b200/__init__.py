@@ -3,6 +3,7 @@
 Drop-in replacements for the reference's hot-path classes
 (`course_agv_slam/scripts/icp.py`, `mapping.py`, `bresenham.py`); see DESIGN.md.
 Submodules are imported lazily so that `import b2slam.synth` works without the CUDA library.
+`b2slam.bresenham` is the module (the reference does `import bresenham as drawing`).
 """
 __version__ = "0.1.0"
 
@@ -14,7 +15,4 @@ def __getattr__(name):
     if name == "Mapping":
         from b2slam.mapping import Mapping
         return Mapping
-    if name == "bresenham":
-        from b2slam.bresenham import bresenham
-        return bresenham
     raise AttributeError(name)

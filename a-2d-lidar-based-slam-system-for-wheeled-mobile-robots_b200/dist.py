@@ -85,3 +85,48 @@ def max_over_ranks(value, device=None):
 def barrier():
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()
+
+
+class ShardedMapping(object):
+    """One rank's share of a global occupancy grid (cfg 5): host scans in, merged map out.
+
+    Every call ray-casts this rank's scans into zeroed int32 delta planes, sums the deltas of
+    all ranks (all-reduce), folds them into the rank's copy of the global counts and refreshes
+    the occupancy map, so after each call every rank holds the same global grid -- bit-identical
+    to one GPU processing all streams.
+    """
+
+    def __init__(self, xw, yw, xyreso, hit_weight=20.0, miss_weight=0.01, occ_threshold=10.0):
+        from b2slam import devapi
+        self._dev = devapi
+        self.xw, self.yw = int(xw), int(yw)
+        self.scale = devapi.grid_scale(self.xw, self.yw, float(xyreso))
+        self.weights = (float(hit_weight), float(miss_weight), float(occ_threshold))
+        self.hit, self.miss = devapi.new_planes(self.xw, self.yw)        # global counts
+        self.d_hit, self.d_miss = devapi.new_planes(self.xw, self.yw)    # this call's deltas
+        self.pmap_dev = torch.empty((self.xw, self.yw), dtype=torch.int8, device="cuda")
+        self.pmap_host = torch.empty((self.xw, self.yw), dtype=torch.int8).pin_memory()
+        self._in = None
+
+    def update_batch(self, ox, oy, cx, cy):
+        """ox, oy (K,N), cx, cy (K,) float32 host arrays (pinned for full copy speed)."""
+        host = [torch.from_numpy(a) if not isinstance(a, torch.Tensor) else a for a in (ox, oy, cx, cy)]
+        if self._in is None or self._in[0].shape != host[0].shape:
+            self._in = [torch.empty(h.shape, dtype=torch.float32, device="cuda") for h in host]
+        for d, h in zip(self._in, host):
+            d.copy_(h, non_blocking=True)
+        self.d_hit.zero_()
+        self.d_miss.zero_()
+        S, Hx, Hy = self.scale
+        self._dev.grid_raycast(self.d_hit, self.d_miss, S, Hx, Hy, *self._in)
+        allreduce_counts(self.d_hit, self.d_miss)
+        self.hit += self.d_hit
+        self.miss += self.d_miss
+        w_hit, w_miss, thr = self.weights
+        self._dev.grid_finalize(self.hit, self.miss, w_hit, w_miss, thr, pmap=self.pmap_dev)
+        self.pmap_host.copy_(self.pmap_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.pmap_host.numpy()
+
+    def counts(self):
+        return self.hit.cpu().numpy(), self.miss.cpu().numpy()

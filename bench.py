@@ -1,0 +1,505 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the b2slam hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--workload grid|icp] [--impl reference]
+
+One JSON line on stdout (rank 0).  The primary workload is cfg 3 of BASELINE.json, the W12
+occupancy-grid update (4096x4096 cells at 5 cm, 1080-beam scans, known poses), because it is the
+half of the metric the HBM roofline target applies to; the same line carries the cfg 2 ICP
+measurement (9 999 consecutive 360-beam pairs) under "icp".  `--workload icp` swaps the roles.
+
+A step is one pass of the hot path over one batch of synthetic scans resident in HBM:
+  grid: zero the count planes, ray-cast SCANS x 1080 beams, (N>1: all-reduce the int32 count
+        deltas over NCCL), finalize to the int8 occupancy map
+  icp : ICP.process over the whole batch of pairs (one CTA per pair)
+`e2e` is the same step through the host-buffer API (Mapping.update_batch / ICP.process_batch):
+pinned host arrays in, host arrays out, copies inside the timed region.
+
+`--impl reference` times the reference's own CPU algorithm (the literal Python/NumPy port in
+oracle/pyref.py -- the reference is pure Python, so there is nothing faster to be fair to) on
+all host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GRID_CELLS = 4096
+GRID_RESO = 0.05
+GRID_BEAMS = 1080
+ICP_BEAMS = 360
+ICP_SCANS = 10000
+FP64_PEAK_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # nominal B200 vector FP64 (no measured figure)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# =============================================================================== clocks
+
+class ClockSampler(object):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+            return
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _run(self):
+        nv = self._nvml
+        names = {}
+        for attr in dir(nv):
+            if attr.startswith("nvmlClocksEventReason") or attr.startswith("nvmlClocksThrottleReason"):
+                val = getattr(nv, attr)
+                if isinstance(val, int) and val and "All" not in attr:
+                    names[val] = attr.replace("nvmlClocksEventReason", "").replace(
+                        "nvmlClocksThrottleReason", "")
+        getter = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(
+            nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                if getter:
+                    bits = getter(self._h)
+                    for b, nm in names.items():
+                        if bits & b and nm not in ("GpuIdle", "None", "ApplicationsClocksSetting"):
+                            self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=2)
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+               "samples": len(self.samples)}
+        if self.samples:
+            out["sm_mhz"] = float(statistics.median(self.samples))
+        return out
+
+
+# =============================================================================== CPU baseline
+
+def _cpu_grid_worker(args):
+    from oracle import pyref
+    ox, oy, cx, cy = args
+    S, Hx, Hy = pyref.grid_scale(GRID_CELLS, GRID_CELLS, GRID_RESO)
+    hit = np.zeros((GRID_CELLS, GRID_CELLS), dtype=np.int32)
+    miss = np.zeros((GRID_CELLS, GRID_CELLS), dtype=np.int32)
+    visits = 0
+    for k in range(ox.shape[0]):
+        visits += pyref.grid_update_counts(hit, miss, ox[k].astype(np.float64), oy[k].astype(np.float64),
+                                           float(cx[k]), float(cy[k]), S, Hx, Hy)
+    return visits
+
+
+def _cpu_icp_worker(args):
+    from oracle import pyref
+    tar, src = args
+    iters = 0
+    for p in range(tar.shape[0]):
+        t = np.ones((3, tar.shape[2]))
+        s = np.ones((3, src.shape[2]))
+        t[:2] = tar[p]
+        s[:2] = src[p]
+        iters += pyref.icp_process(t, s, 30, 1e-3)[1]
+    return iters
+
+
+def _split(n, parts):
+    parts = max(1, min(parts, n))
+    edges = [n * i // parts for i in range(parts + 1)]
+    return [(edges[i], edges[i + 1]) for i in range(parts) if edges[i + 1] > edges[i]]
+
+
+def cpu_grid_rate(pool, cores, scans, data):
+    """beams/s of the literal Python port on `scans` scans spread over `cores` processes."""
+    ox, oy, cx, cy = data
+    jobs = [(ox[a:b], oy[a:b], cx[a:b], cy[a:b]) for a, b in _split(scans, cores)]
+    t0 = time.perf_counter()
+    visits = sum(pool.map(_cpu_grid_worker, jobs))
+    dt = time.perf_counter() - t0
+    return scans * ox.shape[1] / dt, dt, visits
+
+
+def cpu_icp_rate(pool, cores, pairs, tar, src):
+    idx = np.linspace(0, tar.shape[0] - 1, pairs).astype(np.int64)
+    jobs = [(tar[idx[a:b]], src[idx[a:b]]) for a, b in _split(pairs, cores)]
+    t0 = time.perf_counter()
+    iters = sum(pool.map(_cpu_icp_worker, jobs))
+    dt = time.perf_counter() - t0
+    return pairs / dt, dt, iters
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# =============================================================================== reference arm
+
+def run_reference(args):
+    """The reference's CPU algorithm on all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return 0
+    from b2slam import synth
+    cores = host_cores()
+    steps, warmup = args.steps, args.warmup
+    budget_s = 150.0 / max(1, steps + warmup)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        if args.workload == "grid":
+            probe_scans = max(cores, 8)
+            data = synth.grid_scans(12001, max(probe_scans, 4096), GRID_BEAMS)
+            rate, _, _ = cpu_grid_rate(pool, cores, probe_scans, data)
+            scans = int(min(4096, max(cores, rate * budget_s / GRID_BEAMS)))
+            times = []
+            for i in range(warmup + steps):
+                r, dt, _ = cpu_grid_rate(pool, cores, scans, data)
+                if i >= warmup:
+                    times.append(dt)
+            per_step = sum(times) / len(times)
+            value = scans * GRID_BEAMS / per_step
+            metric, unit = "grid_beam_updates_per_s", "beams/s"
+            sample = "%d of the cfg-3 scans x %d beams per step, literal Python port over %d processes" % (
+                scans, GRID_BEAMS, cores)
+            config = {"workload": "cfg3 W12 occupancy grid 4096x4096 @ 0.05 m, 1080-beam scans, known poses",
+                      "scans_per_step": scans, "beams": GRID_BEAMS}
+        else:
+            xy, _ = synth.room_sequence(9001, 513, ICP_BEAMS)
+            tar, src = xy[:-1], xy[1:]
+            rate, _, _ = cpu_icp_rate(pool, cores, cores, tar, src)
+            pairs = int(min(512, max(cores, rate * budget_s)))
+            times = []
+            for i in range(warmup + steps):
+                r, dt, _ = cpu_icp_rate(pool, cores, pairs, tar, src)
+                if i >= warmup:
+                    times.append(dt)
+            per_step = sum(times) / len(times)
+            value = pairs / per_step
+            metric, unit = "icp_scan_pairs_per_s", "pairs/s"
+            sample = "%d cfg-2 pairs x %d beams per step, literal Python port over %d processes" % (
+                pairs, ICP_BEAMS, cores)
+            config = {"workload": "cfg2 W9 LiDAR-odometry ICP, 360-beam consecutive scan pairs",
+                      "pairs_per_step": pairs, "beams": ICP_BEAMS}
+    line = {
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# =============================================================================== GPU arm
+
+def pinned(arr):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+    return t, t.numpy()
+
+
+def bench_grid(args, rank, world, torch, devapi, bdist, synth):
+    import b2slam
+    G, N, K = GRID_CELLS, GRID_BEAMS, args.scans
+    S, Hx, Hy = devapi.grid_scale(G, G, GRID_RESO)
+    host = synth.grid_scans(12001 + rank, K, N)
+    ox, oy, cx, cy = (torch.from_numpy(a).cuda() for a in host)
+    hit, miss = devapi.new_planes(G, G)
+    pmap = torch.empty((G, G), dtype=torch.int8, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def step(ev=None):
+        hit.zero_()
+        miss.zero_()
+        if ev:
+            ev[0].record()
+        devapi.grid_raycast(hit, miss, S, Hx, Hy, ox, oy, cx, cy)
+        if ev:
+            ev[1].record()
+        bdist.allreduce_counts(hit, miss)
+        devapi.grid_finalize(hit, miss, pmap=pmap)
+
+    for _ in range(args.warmup):
+        step()
+        flush.zero_()
+    torch.cuda.synchronize()
+    # algorithmic bytes of one ray-cast launch: endpoints + poses + 8 B per in-grid cell visit
+    hit.zero_(); miss.zero_()
+    devapi.grid_raycast(hit, miss, S, Hx, Hy, ox, oy, cx, cy)
+    visits = int(hit.sum(dtype=torch.int64).item() + miss.sum(dtype=torch.int64).item())
+    algo_bytes = 8 * K + 8 * K * N + 8 * visits
+
+    sampler = ClockSampler(torch.cuda.current_device())
+    bdist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    step_ms, ray_ms = [], []
+    for _ in range(args.steps):
+        e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_a.record()
+        step((k0, k1))
+        e_b.record()
+        flush.zero_()  # evict the planes / endpoints from L2 between timed steps (not timed)
+        e_b.synchronize()
+        step_ms.append(e_a.elapsed_time(e_b))
+        ray_ms.append(k0.elapsed_time(k1))
+    torch.cuda.synchronize()
+    bdist.barrier()
+    clocks = sampler.stop()
+    total_ms = bdist.max_over_ranks(sum(step_ms))
+    ray_avg_ms = sum(ray_ms) / len(ray_ms)
+
+    # ---- end to end through the host-buffer API (pinned host arrays in, occupancy map out)
+    e2e_steps = max(3, min(args.steps, 10))
+    keep = [pinned(a) for a in host]
+    h_ox, h_oy, h_cx, h_cy = (k[1] for k in keep)
+    if world == 1:
+        m = b2slam.Mapping(G, G, GRID_RESO)
+        out_t, out_np = pinned(np.zeros((G, G), dtype=np.int8))
+        m._pmap8 = out_np  # results land in pinned memory
+
+        def e2e_step():
+            m.reset()
+            m.update_batch(h_ox, h_oy, h_cx, h_cy, want_pmap=True)
+    else:
+        sm = bdist.ShardedMapping(G, G, GRID_RESO)
+
+        def e2e_step():
+            sm.update_batch(h_ox, h_oy, h_cx, h_cy)
+    e2e_step()
+    bdist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = bdist.max_over_ranks(time.perf_counter() - t0)
+    bdist.barrier()
+
+    peak, peak_src = measured_peaks()
+    achieved = algo_bytes / (ray_avg_ms * 1e-3) / 1e9
+    res = {
+        "metric": "grid_beam_updates_per_s", "unit": "beams/s",
+        "value": world * K * N * args.steps / (total_ms * 1e-3),
+        "ms_per_step": total_ms / args.steps,
+        "config": {"workload": "cfg3 W12 occupancy grid 4096x4096 @ 0.05 m, 1080-beam scans, known poses",
+                   "scans_per_gpu_per_step": K, "beams": N, "grid": [G, G], "xyreso": GRID_RESO,
+                   "hit_weight": 20.0, "cell_visits_per_step_per_gpu": visits,
+                   "l2": "working set %.0f MB per step > L2 and a 256 MB buffer is rewritten between timed steps"
+                         % ((2 * G * G * 4 + 8 * K * N) / 1e6),
+                   "parallelism": "scan streams sharded by rank, int32 count deltas all-reduced (NCCL)" if world > 1
+                   else "single GPU"},
+        "dtype": "int32 counts / f64 cell+error arithmetic",
+        "roofline": {"bound": "hbm", "kernel": "grid_raycast", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": ray_avg_ms,
+                     "cell_visits_per_s": visits / (ray_avg_ms * 1e-3)},
+        "e2e": {"value": world * K * N * e2e_steps / e2e_s, "unit": "beams/s",
+                "h2d_bytes_per_step": 8 * K * N + 8 * K, "d2h_bytes_per_step": G * G,
+                "api": "Mapping.update_batch (b2s_mapping_update)" if world == 1 else "dist.ShardedMapping.update_batch",
+                "ms_per_step": e2e_s / e2e_steps * 1e3},
+        "gpu_launches": 2 * args.steps,
+        "clocks": clocks,
+    }
+    return res
+
+
+def bench_icp(args, rank, world, torch, devapi, bdist, synth):
+    import b2slam
+    xy, _ = synth.room_sequence(9001 + rank, args.icp_scans, ICP_BEAMS)
+    P = xy.shape[0] - 1
+    tar = torch.from_numpy(np.ascontiguousarray(xy[:-1])).cuda()
+    src = torch.from_numpy(np.ascontiguousarray(xy[1:])).cuda()
+    T = torch.empty((P, 3, 3), dtype=torch.float64, device="cuda")
+    iters = torch.empty(P, dtype=torch.int32, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    for _ in range(args.warmup):
+        devapi.icp_batch(tar, src, 30, 1e-3, T, iters)
+        flush.zero_()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(torch.cuda.current_device())
+    bdist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    step_ms = []
+    for _ in range(args.steps):
+        e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_a.record()
+        devapi.icp_batch(tar, src, 30, 1e-3, T, iters)
+        e_b.record()
+        flush.zero_()
+        e_b.synchronize()
+        step_ms.append(e_a.elapsed_time(e_b))
+    torch.cuda.synchronize()
+    bdist.barrier()
+    clocks = sampler.stop()
+    total_ms = bdist.max_over_ranks(sum(step_ms))
+    it_total = int(iters.sum(dtype=torch.int64).item())
+    evals = it_total * ICP_BEAMS * ICP_BEAMS
+    flops = it_total * (5 * ICP_BEAMS * ICP_BEAMS + 24 * ICP_BEAMS) + P * 16 * ICP_BEAMS
+    step_s = sum(step_ms) / len(step_ms) * 1e-3
+    hbm_bytes = P * (8 * (ICP_BEAMS + ICP_BEAMS) + 72 + 4)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    icp = b2slam.ICP()
+    keep_t, h_tar = pinned(xy[:-1])
+    keep_s, h_src = pinned(xy[1:])
+    icp.process_batch(h_tar, h_src)
+    bdist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        icp.process_batch(h_tar, h_src)
+    e2e_s = bdist.max_over_ranks(time.perf_counter() - t0)
+    bdist.barrier()
+
+    peak, peak_src = measured_peaks()
+    return {
+        "metric": "icp_scan_pairs_per_s", "unit": "pairs/s",
+        "value": world * P * args.steps / (total_ms * 1e-3), "ms_per_step": total_ms / args.steps,
+        "config": {"workload": "cfg2 W9 LiDAR-odometry ICP, 10k-scan 360-beam room sequence, consecutive pairs",
+                   "pairs_per_gpu_per_step": P, "beams": ICP_BEAMS, "max_iter": 30, "tolerance": 1e-3,
+                   "mean_iterations": it_total / P,
+                   "l2": "a 256 MB buffer is rewritten between timed steps",
+                   "parallelism": "independent pairs sharded by rank, no collective" if world > 1 else "single GPU"},
+        "dtype": "f64",
+        "roofline": {"bound": "hbm", "kernel": "icp_batch_kernel", "achieved": hbm_bytes / step_s / 1e9, "peak": peak,
+                     "unit": "GB/s", "frac": hbm_bytes / step_s / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "note": "compute bound by design: HBM fraction is expected to be << 1%",
+                     "pair_evals_per_s": evals / step_s, "fp64_tflops": flops / step_s / 1e12,
+                     "fp64_peak_tflops_nominal": FP64_PEAK_TFLOPS,
+                     "fp64_frac_nominal": flops / step_s / 1e12 / FP64_PEAK_TFLOPS},
+        "e2e": {"value": world * P * e2e_steps / e2e_s, "unit": "pairs/s",
+                "h2d_bytes_per_step": int(h_tar.nbytes + h_src.nbytes), "d2h_bytes_per_step": P * 76,
+                "api": "ICP.process_batch (b2s_icp_process)", "ms_per_step": e2e_s / e2e_steps * 1e3},
+        "gpu_launches": args.steps,
+        "clocks": clocks,
+    }
+
+
+def cpu_baselines(args, synth):
+    cores = host_cores()
+    ctx = mp.get_context("fork")
+    out = {}
+    with ctx.Pool(cores) as pool:
+        scans = max(cores, min(256, 8 * cores))
+        data = synth.grid_scans(12001, scans, GRID_BEAMS)
+        rate, dt, _ = cpu_grid_rate(pool, cores, scans, data)
+        out["grid"] = {"value": rate, "unit": "beams/s", "cores": cores, "kind": "port",
+                       "sample": "first %d cfg-3 scans x %d beams, literal Python port (oracle/pyref.py) over %d "
+                                 "processes, %.1f s wall" % (scans, GRID_BEAMS, cores, dt)}
+        pairs = max(cores, min(32, 2 * cores))
+        xy, _ = synth.room_sequence(9001, 513, ICP_BEAMS)
+        rate, dt, _ = cpu_icp_rate(pool, cores, pairs, xy[:-1], xy[1:])
+        out["icp"] = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",
+                      "sample": "%d evenly spaced cfg-2 pairs x %d beams, literal Python port (oracle/pyref.py) over %d "
+                                "processes, %.1f s wall" % (pairs, ICP_BEAMS, cores, dt)}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b2slam", choices=["b2slam", "reference"])
+    ap.add_argument("--workload", default="grid", choices=["grid", "icp"])
+    ap.add_argument("--scans", type=int, default=16384, help="grid scans per GPU per step")
+    ap.add_argument("--icp-scans", type=int, default=ICP_SCANS)
+    ap.add_argument("--grid-variant", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only", default="both", choices=["both", "primary"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b2slam" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    from b2slam import _lib, devapi, synth
+    from b2slam import dist as bdist
+    if not torch.cuda.is_available() or _lib.device_count() <= 0:
+        raise SystemExit("bench.py needs a CUDA device: b2slam has no CPU fallback")
+    rank, local_rank, world = bdist.init()
+    if args.grid_variant:
+        _lib.check(_lib.lib().b2s_tune(b"grid_variant", args.grid_variant))
+
+    results = {}
+    order = ["grid", "icp"] if args.workload == "grid" else ["icp", "grid"]
+    if args.only == "primary":
+        order = order[:1]
+    for name in order:
+        fn = bench_grid if name == "grid" else bench_icp
+        results[name] = fn(args, rank, world, torch, devapi, bdist, synth)
+        torch.cuda.synchronize()
+        bdist.barrier()
+
+    cpu = {}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baselines(args, synth)
+    bdist.barrier()
+
+    if rank == 0:
+        prim = results[order[0]]
+        line = {
+            "metric": prim["metric"], "value": prim["value"], "unit": prim["unit"], "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": prim["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": prim["dtype"],
+            "data": "synthetic", "config": prim["config"], "roofline": prim["roofline"], "e2e": prim["e2e"],
+            "gpu_launches": sum(r["gpu_launches"] for r in results.values()), "clocks": prim["clocks"],
+            "cpu_baseline": cpu.get(order[0]),
+        }
+        if len(order) > 1:
+            sec = results[order[1]]
+            sec["cpu_baseline"] = cpu.get(order[1])
+            line[order[1]] = sec
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

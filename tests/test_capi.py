@@ -69,7 +69,8 @@ def test_no_cpu_fallback_without_device():
     with pytest.raises(_lib.B2SlamError):
         b2slam.Mapping(200, 200, 0.1)
     with pytest.raises(_lib.B2SlamError):
-        b2slam.bresenham([0, 0], [3, 1])
+        from b2slam import bresenham as drawing
+        drawing.bresenham([0, 0], [3, 1])
     h = ctypes.c_void_p()
     assert _lib.lib().b2s_mapping_create(ctypes.byref(h), 8, 8, 0.1, 20.0, 0.01, 10.0, -1) == _lib.ERR_CUDA
 

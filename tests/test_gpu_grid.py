@@ -43,10 +43,11 @@ def test_bresenham_paths_equal_reference(env):
 
 
 def test_bresenham_class_api(env):
-    p = env.b2slam.bresenham([0, 0], [10, 3]).path
+    drawing = env.bres                         # mapping.py: `import bresenham as drawing`
+    p = drawing.bresenham([0, 0], [10, 3]).path
     assert p == env.corc.bresenham([0, 0], [10, 3])
-    assert env.b2slam.bresenham([5, 5], [5, 5]).path == []
-    assert env.b2slam.bresenham([3, 9], [3, 2]).path == env.pyref.bresenham_cells([3, 9], [3, 2])
+    assert drawing.bresenham([5, 5], [5, 5]).path == []
+    assert drawing.bresenham([3, 9], [3, 2]).path == env.pyref.bresenham_cells([3, 9], [3, 2])
 
 
 def test_bresenham_long_random_segments_vs_oracle(env):
