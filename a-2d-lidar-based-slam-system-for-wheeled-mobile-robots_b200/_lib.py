@@ -35,6 +35,7 @@ SIGNATURES = {
     "b2s_rigid_fit_f64": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "b2s_grid_raycast": (_i32, [_vp, _vp, _i32, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp,
                                 _i32, _i32, _vp, _vp]),
+    "b2s_grid_validate": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "b2s_grid_finalize": (_i32, [_vp, _vp, _i32, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
     "b2s_grid_pack_ros": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "b2s_bresenham_paths": (_i32, [_vp, _i32, _vp, _vp, _vp]),
@@ -42,6 +43,8 @@ SIGNATURES = {
     "b2s_nccl_unique_id": (_i32, [_vp]),
     "b2s_nccl_comm_init": (_i32, [_pp, _i32, _i32, _vp]),
     "b2s_nccl_comm_destroy": (_i32, [_vp]),
+    "b2s_host_alloc": (_i32, [_pp, _sz]),
+    "b2s_host_free": (_i32, [_vp]),
     "b2s_icp_create": (_i32, [_pp, _i32]),
     "b2s_icp_destroy": (_i32, [_vp]),
     "b2s_icp_process": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _dbl, _vp, _vp]),
@@ -114,3 +117,24 @@ def device_count():
 def require_device():
     if device_count() <= 0:
         raise B2SlamError(ERR_CUDA, "no CUDA device visible: b2slam has no CPU fallback")
+
+
+def _free_pinned(address):
+    try:
+        lib().b2s_host_free(ctypes.c_void_p(address))
+    except Exception:
+        pass
+
+
+def pinned_empty(shape, dtype):
+    """NumPy array in page-locked memory (b2s_host_alloc); freed when the last view dies."""
+    import weakref
+
+    import numpy as np
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    p = ctypes.c_void_p()
+    check(lib().b2s_host_alloc(ctypes.byref(p), max(1, count * dtype.itemsize)))
+    raw = (ctypes.c_char * max(1, count * dtype.itemsize)).from_address(p.value)
+    weakref.finalize(raw, _free_pinned, p.value)
+    return np.frombuffer(raw, dtype=dtype, count=count).reshape(shape)

@@ -191,6 +191,32 @@ grid_raycast_v2(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int xw, i
 }
 
 // ------------------------------------------------------------------------------------------
+// Input screening for the host-buffer API: flags[0] |= NaN anywhere, flags[1] |= inf in oy or in a
+// sensor position -- the values int() raises on in [MAP]:33-36 (inf in ox alone is legal, [MAP]:30).
+
+__global__ void __launch_bounds__(256)
+grid_validate_kernel(const float *__restrict__ ox, const float *__restrict__ oy, long long total,
+                     const float *__restrict__ cx, const float *__restrict__ cy, int scans,
+                     int32_t *__restrict__ flags)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    bool has_nan = false, has_inf = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const float x = __ldg(ox + i), y = __ldg(oy + i);
+        if (isinf(x)) continue;  // the beam is skipped before oy is looked at
+        has_nan |= isnan(x) || isnan(y);
+        has_inf |= isinf(y);
+    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < scans; i += stride) {
+        const float x = __ldg(cx + i), y = __ldg(cy + i);
+        has_nan |= isnan(x) || isnan(y);
+        has_inf |= isinf(x) || isinf(y);
+    }
+    if (__any_sync(0xffffffffu, has_nan) && (threadIdx.x & 31) == 0) atomicOr(&flags[0], 1);
+    if (__any_sync(0xffffffffu, has_inf) && (threadIdx.x & 31) == 0) atomicOr(&flags[1], 1);
+}
+
+// ------------------------------------------------------------------------------------------
 // counts -> evidence score + occupancy.  Pure streaming.
 
 __global__ void __launch_bounds__(256)
@@ -307,6 +333,23 @@ extern "C" int b2s_grid_raycast(int32_t *hit, int32_t *miss, int xw, int yw, dou
     else
         grid_raycast_v2<<<(unsigned)blocks, threads, 0, st>>>(hit, miss, xw, yw, cells_per_m, off_x, off_y,
                                                               ox, oy, cx, cy, total, beams, counters);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+
+extern "C" int b2s_grid_validate(const float *ox, const float *oy, const float *cx, const float *cy,
+                                 int scans, int beams, int32_t *flags, void *stream)
+{
+    B2S_REQUIRE(scans >= 0 && beams >= 0, "b2s_grid_validate: negative count");
+    B2S_REQUIRE(flags, "b2s_grid_validate: null flags");
+    if (scans == 0) return B2S_OK;
+    B2S_REQUIRE(cx && cy && (beams == 0 || (ox && oy)), "b2s_grid_validate: null pointer");
+    const long long total = (long long)scans * beams;
+    long long blocks = (total + 256 * 8 - 1) / (256 * 8);
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    grid_validate_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ox, oy, total, cx, cy, scans, flags);
     B2S_CUDA(cudaGetLastError());
     return B2S_OK;
 }

@@ -140,6 +140,26 @@ extern "C" int b2s_tune(const char *key, int value)
     return B2S_ERR_INVALID_ARG;
 }
 
+// Page-locked host memory for callers without their own allocator (Mapping's result buffer).
+extern "C" int b2s_host_alloc(void **out, size_t bytes)
+{
+    B2S_REQUIRE(out, "b2s_host_alloc: null pointer");
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        *out = nullptr;
+        cuda_fail(e, "cudaMallocHost");
+        return e == cudaErrorMemoryAllocation ? B2S_ERR_NOMEM : B2S_ERR_CUDA;
+    }
+    return B2S_OK;
+}
+
+extern "C" int b2s_host_free(void *p)
+{
+    if (p) B2S_CUDA(cudaFreeHost(p));
+    return B2S_OK;
+}
+
 // ------------------------------------------------------------------------------ ICP object
 
 extern "C" int b2s_icp_create(b2s_icp **out, int device)
@@ -329,27 +349,6 @@ extern "C" int b2s_mapping_reset(b2s_mapping *m)
     return B2S_OK;
 }
 
-// What int() in [MAP]:33-36 raises on: NaN -> ValueError, inf -> OverflowError.  ox == +-inf is
-// the one tolerated value ([MAP]:30).  Checked on the host before anything is applied.
-static int validate_scan(const float *ox, const float *oy, const float *cx, const float *cy, int scans, int beams)
-{
-    for (int s = 0; s < scans; ++s)
-        if (!isfinite(cx[s]) || !isfinite(cy[s])) {
-            set_error("non-finite sensor position in scan %d", s);
-            return B2S_ERR_NONFINITE;
-        }
-    const size_t total = (size_t)scans * beams;
-    for (size_t i = 0; i < total; ++i) {
-        const float x = ox[i];
-        if (isinf(x)) continue;
-        if (isnan(x) || !isfinite(oy[i])) {
-            set_error("non-finite endpoint at beam %zu", i);
-            return B2S_ERR_NONFINITE;
-        }
-    }
-    return B2S_OK;
-}
-
 extern "C" int b2s_mapping_update(b2s_mapping *m, const float *ox, const float *oy, const float *cx,
                                   const float *cy, int scans, int beams, int8_t *pmap_out)
 {
@@ -360,7 +359,6 @@ extern "C" int b2s_mapping_update(b2s_mapping *m, const float *ox, const float *
     int rc;
     if (total > 0) {
         B2S_REQUIRE(ox && oy && cx && cy, "b2s_mapping_update: null pointer");
-        if ((rc = validate_scan(ox, oy, cx, cy, scans, beams))) return rc;
         const size_t pts = total * sizeof(float), ctr = (size_t)scans * sizeof(float);
         // one device block: [ox | oy | cx | cy], each section 16-byte aligned
         const size_t a_pts = (pts + 15) & ~(size_t)15, a_ctr = (ctr + 15) & ~(size_t)15;
@@ -368,10 +366,21 @@ extern "C" int b2s_mapping_update(b2s_mapping *m, const float *ox, const float *
         char *base = (char *)m->d_in.p;
         float *d_ox = (float *)base, *d_oy = (float *)(base + a_pts);
         float *d_cx = (float *)(base + 2 * a_pts), *d_cy = (float *)(base + 2 * a_pts + a_ctr);
+        B2S_CUDA(cudaMemsetAsync(m->counters, 0, B2S_CNT_WORDS * sizeof(int32_t), m->stream));
         B2S_CUDA(cudaMemcpyAsync(d_ox, ox, pts, cudaMemcpyHostToDevice, m->stream));
         B2S_CUDA(cudaMemcpyAsync(d_oy, oy, pts, cudaMemcpyHostToDevice, m->stream));
         B2S_CUDA(cudaMemcpyAsync(d_cx, cx, ctr, cudaMemcpyHostToDevice, m->stream));
         B2S_CUDA(cudaMemcpyAsync(d_cy, cy, ctr, cudaMemcpyHostToDevice, m->stream));
+        // screen the whole batch on the device BEFORE any beam is applied: the reference raises
+        // (ValueError on NaN, OverflowError on inf) where int() meets such a value, [MAP]:33-36
+        int32_t flags[2] = {0, 0};
+        if ((rc = b2s_grid_validate(d_ox, d_oy, d_cx, d_cy, scans, beams, m->counters + 2, m->stream))) return rc;
+        B2S_CUDA(cudaMemcpyAsync(flags, m->counters + 2, sizeof(flags), cudaMemcpyDeviceToHost, m->stream));
+        B2S_CUDA(cudaStreamSynchronize(m->stream));
+        if (flags[0] || flags[1]) {
+            set_error(flags[0] ? "cannot convert float NaN to integer" : "cannot convert float infinity to integer");
+            return B2S_ERR_NONFINITE;
+        }
         B2S_CUDA(cudaMemsetAsync(m->counters, 0, B2S_CNT_WORDS * sizeof(int32_t), m->stream));
         rc = b2s_grid_raycast(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y, d_ox, d_oy,
                               d_cx, d_cy, scans, beams, m->counters, m->stream);

@@ -41,14 +41,20 @@ class Mapping(object):
                                               self.hit_weight, self.miss_weight,
                                               self.occ_threshold, int(device)))
         self._h = h
-        self._pmap8 = np.full((self.xw, self.yw), 50, dtype=np.int8)
-        self.pmap = 50 * np.ones((self.xw, self.yw))  # [MAP]:14 unknown = 50
+        self._pmap8 = _lib.pinned_empty((self.xw, self.yw), np.int8)  # page-locked result buffer
+        self._pmap8.fill(50)  # [MAP]:14 unknown = 50
 
     def __del__(self):
         h = getattr(self, "_h", None)
         if h is not None and h.value:
             self._L.b2s_mapping_destroy(h)
             self._h = None
+
+    @property
+    def pmap(self):
+        """[MAP]:14 occupancy as the reference's float64 (xw, yw) array in {0, 50, 100}; a snapshot
+        of the last update (the reference hands out its live array)."""
+        return self._pmap8.astype(np.float64)
 
     # ------------------------------------------------------------------ reference methods
 
@@ -63,12 +69,16 @@ class Mapping(object):
         oy = np.asarray(oy, dtype=np.float64).reshape(1, -1)
         cx = np.asarray(center_x, dtype=np.float64).reshape(-1)[:1]
         cy = np.asarray(center_y, dtype=np.float64).reshape(-1)[:1]
-        return self.update_batch(ox, oy, cx, cy)
+        self.update_batch(ox, oy, cx, cy)
+        return self.pmap
 
     # ------------------------------------------------------------------ batched entry points
 
     def update_batch(self, ox, oy, cx, cy, want_pmap=True):
-        """K scans at once: ox, oy (K,N); cx, cy (K,).  Coordinates are consumed as float32."""
+        """K scans at once: ox, oy (K,N); cx, cy (K,).  Coordinates are consumed as float32.
+
+        Returns the refreshed occupancy as int8 (xw, yw) in {0, 50, 100} (a view of the object's
+        host buffer, overwritten by the next call), or None with want_pmap=False."""
         ox = np.ascontiguousarray(ox, dtype=np.float32)
         oy = np.ascontiguousarray(oy, dtype=np.float32)
         cx = np.ascontiguousarray(cx, dtype=np.float32).reshape(-1)
@@ -87,10 +97,7 @@ class Mapping(object):
                 raise ValueError("cannot convert float NaN to integer")
             raise OverflowError("cannot convert float infinity to integer")
         _lib.check(rc)
-        if want_pmap:
-            self.pmap = self._pmap8.astype(np.float64)
-            return self.pmap
-        return None
+        return self._pmap8 if want_pmap else None
 
     def counts(self):
         """(hit, miss) int32 (xw, yw) snapshots of the device planes."""
@@ -115,7 +122,6 @@ class Mapping(object):
     def reset(self):
         _lib.check(self._L.b2s_mapping_reset(self._h))
         self._pmap8.fill(50)
-        self.pmap = 50 * np.ones((self.xw, self.yw))
 
     def device_planes(self):
         """(hit_ptr, miss_ptr, stream_ptr) integers for layer-1 calls and collectives."""

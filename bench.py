@@ -297,8 +297,6 @@ def bench_grid(args, rank, world, torch, devapi, bdist, synth):
     h_ox, h_oy, h_cx, h_cy = (k[1] for k in keep)
     if world == 1:
         m = b2slam.Mapping(G, G, GRID_RESO)
-        out_t, out_np = pinned(np.zeros((G, G), dtype=np.int8))
-        m._pmap8 = out_np  # results land in pinned memory
 
         def e2e_step():
             m.reset()
@@ -423,7 +421,7 @@ def cpu_baselines(args, synth):
     ctx = mp.get_context("fork")
     out = {}
     with ctx.Pool(cores) as pool:
-        scans = max(cores, min(256, 8 * cores))
+        scans = 32 * cores
         data = synth.grid_scans(12001, scans, GRID_BEAMS)
         rate, dt, _ = cpu_grid_rate(pool, cores, scans, data)
         out["grid"] = {"value": rate, "unit": "beams/s", "cores": cores, "kind": "port",

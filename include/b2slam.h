@@ -86,6 +86,12 @@ int b2s_grid_raycast(int32_t *hit, int32_t *miss, int xw, int yw, double cells_p
                      const float *cx, const float *cy, int scans, int beams, int32_t *counters,
                      void *stream);
 
+/* Screening of a batch before it is applied: flags[0] |= 1 if a NaN is present, flags[1] |= 1 if
+ * oy or a sensor position holds an inf -- the values int() raises on in [MAP]:33-36 (ValueError /
+ * OverflowError); ox = +-inf alone is legal ([MAP]:30).  flags: device int32[2], caller-zeroed. */
+int b2s_grid_validate(const float *ox, const float *oy, const float *cx, const float *cy, int scans,
+                      int beams, int32_t *flags, void *stream);
+
 /* Evidence score and occupancy from the counts -- replaces the per-visit rule of [MAP]:42-50
  * (w_hit 20) / [MAPO]:43-51 (w_hit 4): datamap = w_miss*miss + w_hit*hit (float32 out),
  * pmap = 50 if untouched else (100 if datamap > thresh else 0).  Either output may be NULL. */
@@ -111,6 +117,10 @@ int b2s_nccl_comm_init(void **comm_out, int nranks, int rank, const void *id128)
 int b2s_nccl_comm_destroy(void *comm);
 
 /* ===================================================================== layer 2: host */
+
+/* Page-locked host buffers (full-speed, truly asynchronous copies). */
+int b2s_host_alloc(void **out, size_t bytes);
+int b2s_host_free(void *p);
 
 typedef struct b2s_icp b2s_icp;
 typedef struct b2s_mapping b2s_mapping;
