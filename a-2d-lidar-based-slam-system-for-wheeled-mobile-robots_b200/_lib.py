@@ -35,6 +35,10 @@ SIGNATURES = {
     "b2s_rigid_fit_f64": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "b2s_grid_raycast": (_i32, [_vp, _vp, _i32, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp,
                                 _i32, _i32, _vp, _vp]),
+    "b2s_grid_workspace_bytes": (_sz, [_i32, _i32]),
+    "b2s_grid_workspace_init": (_i32, [_vp, _i32, _i32, _vp]),
+    "b2s_grid_raycast_ws": (_i32, [_vp, _vp, _i32, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp,
+                                   _i32, _i32, _vp, _vp, _vp]),
     "b2s_grid_validate": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "b2s_grid_finalize": (_i32, [_vp, _vp, _i32, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
     "b2s_grid_pack_ros": (_i32, [_vp, _i32, _i32, _vp, _vp]),

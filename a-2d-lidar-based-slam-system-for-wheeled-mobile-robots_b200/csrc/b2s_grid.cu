@@ -12,7 +12,9 @@
 
 namespace b2s {
 
-int g_grid_variant = 2;  // 1: one RED per visit; 2: warp-aggregated runs (default)
+// 1: one RED per visit; 2: warp-aggregated runs; 3: same, lean inner loop;
+// 4 (default): 3 + transposed scratch plane for y-major beams when a workspace is supplied, else 3
+int g_grid_variant = 4;
 
 // ------------------------------------------------------------------------------------------
 // Per-beam setup shared by all variants.
@@ -25,6 +27,8 @@ struct Beam {
     int hit_k;    // canonical index of the obstacle cell: span, or 0 when the trace was flipped
     int steep;    // major axis is y ([BRES]:14-17)
     double slope; // dy / float(dx) in float64 ([BRES]:35)
+    int hx, hy;   // obstacle cell (the path's last element, [MAP]:44-45)
+    int sx, sy;   // sensor cell (the path's first element)
 };
 
 enum BeamStatus { BEAM_OK = 0, BEAM_NOOP = 1, BEAM_NONFINITE = 2, BEAM_TOO_LONG = 3, BEAM_INF_SKIP = 4 };
@@ -49,6 +53,10 @@ __device__ __forceinline__ int beam_setup(float fox, float foy, float fcx, float
     if (x0 == x1 && y0 == y1) return BEAM_NOOP;                // [BRES]:10-11 empty path
     // no cell of the segment's bounding box inside the grid -> nothing to update
     if (max(x0, x1) < 0 || min(x0, x1) >= xw || max(y0, y1) < 0 || min(y0, y1) >= yw) return BEAM_NOOP;
+    b.hx = x1;
+    b.hy = y1;
+    b.sx = x0;
+    b.sy = y0;
     const int steep = abs(y1 - y0) > abs(x1 - x0);
     if (steep) {
         int t = x0; x0 = y0; y0 = t;
@@ -187,6 +195,271 @@ grid_raycast_v2(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int xw, i
             const int run = rest ? __ffs(rest) : (32 - lane);
             atomicAdd(miss + key, run);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Variant 3: the march of variant 2 with a lean inner loop (the kernel is issue-bound: ncu shows
+// 77% issue-slot utilisation and <10% FP64 pipe for v2, so every instruction per step counts).
+//   * the endpoint hit is one RED per beam taken straight from the obstacle cell, outside the loop
+//   * per-lane emission window [t_em, t_em + em_len] in warp time replaces the per-step bounds tests
+//     on the major axis; the minor axis is tested on the pre-multiplied cell offset
+//   * cell offsets advance incrementally (no multiplies in the loop)
+//   * flipped traces need a "not started yet" guard only while some lane is still waiting
+//     (phase A); once every lane has started the guard disappears (phase B)
+//   * run length = clz of the reversed head mask, RED predicated instead of branched
+
+template <bool GUARD_START, int NORED>
+__device__ __forceinline__ void march_step(int t, int delay, double slope, double &acc, unsigned &cmaj, int &minor,
+                                           unsigned smaj, int smin, int inc, unsigned wmin, int t_em,
+                                           unsigned em_len, int dead_key, unsigned lane, unsigned lane_bit,
+                                           int32_t *__restrict__ miss)
+{
+    const bool started = !GUARD_START || (t >= delay);
+    const bool emit = ((unsigned)(t - t_em) <= em_len) && ((unsigned)minor < wmin);
+    // inside the window the true offset is in [0, xw*yw): modular arithmetic on cmaj is exact there
+    const int key = emit ? (int)(cmaj + (unsigned)(minor * smin)) : dead_key;
+    if (started) {
+        acc = __dadd_rn(acc, slope);  // [BRES]:51
+        if (acc >= 0.5) {             // [BRES]:53
+            minor += inc;             // [BRES]:54
+            acc = __dadd_rn(acc, -1.0);  // [BRES]:55
+        }
+        cmaj += smaj;
+    }
+    const int left = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = (lane == 0) || (key != left);
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    // lanes after this one up to the next head carry the same cell: run = distance to that head
+    const unsigned ahead = ((__brev(heads) << lane) << 1) | lane_bit;
+    const int run = __clz(ahead) + 1;
+    if (head && emit && (NORED == 0 || run == 77)) atomicAdd(miss + key, run);
+}
+
+template <int NORED>
+__global__ void __launch_bounds__(256)
+grid_raycast_v3(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int xw, int yw,
+                double cells_per_m, double off_x, double off_y, const float *__restrict__ ox,
+                const float *__restrict__ oy, const float *__restrict__ cx,
+                const float *__restrict__ cy, long long total, int beams, int32_t *counters)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
+    Beam b;
+    b.major0 = b.minor0 = b.span = b.inc = b.hit_k = b.steep = b.hx = b.hy = b.sx = b.sy = 0;
+    b.slope = 0.0;
+    int st = BEAM_NOOP;
+    if (i < total) {
+        const int s = (int)(i / beams);
+        st = beam_setup(__ldg(ox + i), __ldg(oy + i), __ldg(cx + s), __ldg(cy + s), xw, yw,
+                        cells_per_m, off_x, off_y, b);
+        if (st != BEAM_OK) count_status(st, counters);
+    }
+    const bool live = (st == BEAM_OK);
+    const int span = live ? b.span : -1;
+    int tmax = span;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    if (tmax < 0) return;
+
+    // endpoint: the obstacle cell is the last path element whenever the path is not empty
+    if (live && (unsigned)b.hx < (unsigned)xw && (unsigned)b.hy < (unsigned)yw)
+        atomicAdd(hit + (b.hx * yw + b.hy), 1);
+
+    const int wmaj = b.steep ? yw : xw;
+    const unsigned wmin = (unsigned)(b.steep ? xw : yw);
+    const unsigned smaj = b.steep ? 1u : (unsigned)yw;
+    const int smin = b.steep ? yw : 1;
+    // canonical index k = t - delay; a flipped trace reaches the sensor cell at t == tmax
+    const int delay = (live && b.hit_k == 0) ? (tmax - span) : 0;
+    int dmax = delay;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    // emission window in canonical k: inside the grid on the major axis, obstacle cell excluded
+    int k_lo = max(0, -b.major0), k_hi = min(span, wmaj - 1 - b.major0);
+    if (b.hit_k == 0) k_lo = max(k_lo, 1); else k_hi = min(k_hi, span - 1);
+    const bool any = live && k_hi >= k_lo;
+    const int t_em = any ? delay + k_lo : 0x3fffffff;
+    const unsigned em_len = any ? (unsigned)(k_hi - k_lo) : 0u;
+
+    double acc = 0.0;
+    unsigned cmaj = (unsigned)b.major0 * smaj;  // major part of the cell offset at k = 0 (mod 2^32)
+    int minor = b.minor0;
+    const int inc = b.inc;
+    const int dead_key = -1 - (int)lane;  // unique per lane: never equal to a neighbour's cell
+    const unsigned lane_bit = 1u << lane;
+    const double slope = b.slope;
+
+    int t = 0;
+    for (; t < dmax; ++t)
+        march_step<true, NORED>(t, delay, slope, acc, cmaj, minor, smaj, smin, inc, wmin, t_em, em_len, dead_key, lane,
+                         lane_bit, miss);
+#pragma unroll 4
+    for (; t <= tmax; ++t)
+        march_step<false, NORED>(t, delay, slope, acc, cmaj, minor, smaj, smin, inc, wmin, t_em, em_len, dead_key, lane,
+                          lane_bit, miss);
+}
+
+// ------------------------------------------------------------------------------------------
+// Variant 4: variant 3 plus a transposed scratch plane for the steep (y-major) beams.
+//
+// Measured on B200 (profiles/microbench): RED.ADD costs ~1.5 SM-cycles per distinct 32-byte sector a
+// warp instruction touches, not per lane -- 32 lanes on consecutive words retire in ~7 cycles, 32
+// scattered lanes in ~50.  In the [x][y] planes the run heads of a warp of x-major beams sit on
+// consecutive y (a few sectors per step), but those of y-major beams are a whole row apart (one
+// sector each), and they dominate the RED time of variants 2/3.  Here y-major beams accumulate
+// into a scratch plane stored [y][x], where THEIR heads are consecutive too; a tiled transpose-add
+// then folds the touched bounding box of the scratch plane into `miss` and re-zeroes it.
+// Integer adds commute, so the result is bit-identical.
+
+struct GridWorkspace {      // lives at the front of the caller-provided workspace
+    int bbox[4];            // atomicMax of (-xmin, xmax, -ymin, ymax) over y-major beams; reset to very negative
+    int pad[12];
+};
+
+template <bool GUARD_START>
+__device__ __forceinline__ void march_step4(int t, int delay, double slope, double &acc, unsigned &cmaj, int &minor,
+                                            unsigned pitch, int inc, unsigned wmin, int t_em, unsigned em_len,
+                                            unsigned steep_bit, unsigned dead_key, unsigned lane, unsigned lane_bit,
+                                            int32_t *__restrict__ plane)
+{
+    const bool started = !GUARD_START || (t >= delay);
+    const bool emit = ((unsigned)(t - t_em) <= em_len) && ((unsigned)minor < wmin);
+    const unsigned cell = cmaj + (unsigned)minor;  // exact inside the window (mod 2^32 outside)
+    const unsigned key = emit ? ((cell << 1) | steep_bit) : dead_key;
+    if (started) {
+        acc = __dadd_rn(acc, slope);  // [BRES]:51
+        if (acc >= 0.5) {             // [BRES]:53
+            minor += inc;             // [BRES]:54
+            acc = __dadd_rn(acc, -1.0);  // [BRES]:55
+        }
+        cmaj += pitch;
+    }
+    const unsigned left = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = (lane == 0) || (key != left);
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    const unsigned ahead = ((__brev(heads) << lane) << 1) | lane_bit;
+    const int run = __clz(ahead) + 1;
+    if (head && emit) atomicAdd(plane + cell, run);
+}
+
+__global__ void __launch_bounds__(256)
+grid_raycast_v4(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int32_t *__restrict__ scratch_t,
+                GridWorkspace *__restrict__ ws, int xw, int yw, double cells_per_m, double off_x, double off_y,
+                const float *__restrict__ ox, const float *__restrict__ oy, const float *__restrict__ cx,
+                const float *__restrict__ cy, long long total, int beams, int32_t *counters)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
+    Beam b;
+    b.major0 = b.minor0 = b.span = b.inc = b.hit_k = b.steep = b.hx = b.hy = b.sx = b.sy = 0;
+    b.slope = 0.0;
+    int st = BEAM_NOOP;
+    if (i < total) {
+        const int s = (int)(i / beams);
+        st = beam_setup(__ldg(ox + i), __ldg(oy + i), __ldg(cx + s), __ldg(cy + s), xw, yw,
+                        cells_per_m, off_x, off_y, b);
+        if (st != BEAM_OK) count_status(st, counters);
+    }
+    const bool live = (st == BEAM_OK);
+    const int span = live ? b.span : -1;
+    int tmax = span;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    if (tmax < 0) return;
+
+    if (live && (unsigned)b.hx < (unsigned)xw && (unsigned)b.hy < (unsigned)yw)
+        atomicAdd(hit + (b.hx * yw + b.hy), 1);
+
+    // bounding box of what the y-major beams of this warp can touch in the scratch plane
+    const bool steep_live = live && b.steep;
+    if (__any_sync(0xffffffffu, steep_live)) {
+        const int very_neg = (int)0x80808080;
+        int nx0 = very_neg, x1 = very_neg, ny0 = very_neg, y1 = very_neg;
+        if (steep_live) {
+            nx0 = -max(0, min(b.sx, b.hx));
+            x1 = min(xw - 1, max(b.sx, b.hx));
+            ny0 = -max(0, min(b.sy, b.hy));
+            y1 = min(yw - 1, max(b.sy, b.hy));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            nx0 = max(nx0, __shfl_xor_sync(0xffffffffu, nx0, o));
+            x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+            ny0 = max(ny0, __shfl_xor_sync(0xffffffffu, ny0, o));
+            y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+        }
+        if (lane == 0) {
+            atomicMax(&ws->bbox[0], nx0);
+            atomicMax(&ws->bbox[1], x1);
+            atomicMax(&ws->bbox[2], ny0);
+            atomicMax(&ws->bbox[3], y1);
+        }
+    }
+
+    const int wmaj = b.steep ? yw : xw;
+    const unsigned wmin = (unsigned)(b.steep ? xw : yw);
+    const unsigned pitch = wmin;  // both planes are stored major-row by major-row for their beams
+    int32_t *plane = b.steep ? scratch_t : miss;
+    const int delay = (live && b.hit_k == 0) ? (tmax - span) : 0;
+    int dmax = delay;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    int k_lo = max(0, -b.major0), k_hi = min(span, wmaj - 1 - b.major0);
+    if (b.hit_k == 0) k_lo = max(k_lo, 1); else k_hi = min(k_hi, span - 1);
+    const bool any = live && k_hi >= k_lo;
+    const int t_em = any ? delay + k_lo : 0x3fffffff;
+    const unsigned em_len = any ? (unsigned)(k_hi - k_lo) : 0u;
+
+    double acc = 0.0;
+    unsigned cmaj = (unsigned)b.major0 * pitch;
+    int minor = b.minor0;
+    const int inc = b.inc;
+    const unsigned steep_bit = b.steep ? 1u : 0u;
+    const unsigned dead_key = 0x80000000u | lane;  // cells < 2^30, so live keys stay below 2^31
+    const unsigned lane_bit = 1u << lane;
+    const double slope = b.slope;
+
+    int t = 0;
+    for (; t < dmax; ++t)
+        march_step4<true>(t, delay, slope, acc, cmaj, minor, pitch, inc, wmin, t_em, em_len, steep_bit, dead_key,
+                          lane, lane_bit, plane);
+#pragma unroll 4
+    for (; t <= tmax; ++t)
+        march_step4<false>(t, delay, slope, acc, cmaj, minor, pitch, inc, wmin, t_em, em_len, steep_bit, dead_key,
+                           lane, lane_bit, plane);
+}
+
+// miss[x][y] += scratch_t[y][x] over the recorded bounding box, scratch_t cleared on the way.
+__global__ void __launch_bounds__(256)
+grid_fold_kernel(int32_t *__restrict__ miss, int32_t *__restrict__ scratch_t, const GridWorkspace *__restrict__ ws,
+                 int xw, int yw)
+{
+    __shared__ int tile[32][33];
+    const int xmin = -ws->bbox[0], xmax = ws->bbox[1], ymin = -ws->bbox[2], ymax = ws->bbox[3];
+    if (xmax < 0 || ymax < 0) return;  // no y-major beam in this launch
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    if (x0 > xmax || x0 + 31 < xmin || y0 > ymax || y0 + 31 < ymin) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    int any_nz = 0;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int y = y0 + r, x = x0 + tx;
+        int v = 0;
+        if (y < yw && x < xw) {
+            const size_t at = (size_t)y * xw + x;
+            v = scratch_t[at];
+            if (v) scratch_t[at] = 0;
+        }
+        tile[r][tx] = v;
+        any_nz |= v;
+    }
+    if (!__syncthreads_or(any_nz)) return;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int x = x0 + r, y = y0 + tx;
+        const int v = tile[tx][r];
+        if (v && x < xw && y < yw) miss[(size_t)x * yw + y] += v;
     }
 }
 
@@ -330,10 +603,63 @@ extern "C" int b2s_grid_raycast(int32_t *hit, int32_t *miss, int xw, int yw, dou
     if (g_grid_variant == 1)
         grid_raycast_v1<<<(unsigned)blocks, threads, 0, st>>>(hit, miss, xw, yw, cells_per_m, off_x, off_y,
                                                               ox, oy, cx, cy, total, beams, counters);
-    else
+    else if (g_grid_variant == 2)
         grid_raycast_v2<<<(unsigned)blocks, threads, 0, st>>>(hit, miss, xw, yw, cells_per_m, off_x, off_y,
                                                               ox, oy, cx, cy, total, beams, counters);
+    else if (g_grid_variant == 3 || g_grid_variant == 4)
+        grid_raycast_v3<0><<<(unsigned)blocks, threads, 0, st>>>(hit, miss, xw, yw, cells_per_m, off_x, off_y,
+                                                                 ox, oy, cx, cy, total, beams, counters);
+    else  // 99: timing experiment only -- the march without its REDs (results are wrong by design)
+        grid_raycast_v3<1><<<(unsigned)blocks, threads, 0, st>>>(hit, miss, xw, yw, cells_per_m, off_x, off_y,
+                                                                 ox, oy, cx, cy, total, beams, counters);
     B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+
+extern "C" size_t b2s_grid_workspace_bytes(int xw, int yw)
+{
+    if (xw <= 0 || yw <= 0) return 0;
+    return sizeof(GridWorkspace) + (size_t)xw * yw * sizeof(int32_t);
+}
+
+extern "C" int b2s_grid_workspace_init(void *workspace, int xw, int yw, void *stream)
+{
+    B2S_REQUIRE(workspace && xw > 0 && yw > 0, "b2s_grid_workspace_init: bad arguments");
+    B2S_REQUIRE((uintptr_t)workspace % 16 == 0, "b2s_grid_workspace_init: workspace must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    B2S_CUDA(cudaMemsetAsync(workspace, 0x80, sizeof(GridWorkspace), st));
+    B2S_CUDA(cudaMemsetAsync((char *)workspace + sizeof(GridWorkspace), 0, (size_t)xw * yw * sizeof(int32_t), st));
+    return B2S_OK;
+}
+
+extern "C" int b2s_grid_raycast_ws(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m,
+                                   double off_x, double off_y, const float *ox, const float *oy,
+                                   const float *cx, const float *cy, int scans, int beams,
+                                   int32_t *counters, void *workspace, void *stream)
+{
+    if (workspace == nullptr || g_grid_variant != 4)
+        return b2s_grid_raycast(hit, miss, xw, yw, cells_per_m, off_x, off_y, ox, oy, cx, cy, scans, beams,
+                                counters, stream);
+    B2S_REQUIRE(hit && miss && ox && oy && cx && cy, "b2s_grid_raycast_ws: null pointer");
+    B2S_REQUIRE(xw > 0 && yw > 0 && (long long)xw * yw < (1ll << 30), "b2s_grid_raycast_ws: grid size");
+    B2S_REQUIRE(scans >= 0 && beams >= 0, "b2s_grid_raycast_ws: negative count");
+    B2S_REQUIRE(cells_per_m == cells_per_m && off_x == off_x && off_y == off_y, "b2s_grid_raycast_ws: NaN scale");
+    B2S_REQUIRE((uintptr_t)workspace % 16 == 0, "b2s_grid_raycast_ws: workspace must be 16-byte aligned");
+    const long long total = (long long)scans * beams;
+    if (total == 0) return B2S_OK;
+    const int threads = 256;
+    const long long blocks = (total + threads - 1) / threads;
+    B2S_REQUIRE(blocks < (1ll << 31), "b2s_grid_raycast_ws: too many beams for one launch");
+    cudaStream_t st = (cudaStream_t)stream;
+    GridWorkspace *ws = (GridWorkspace *)workspace;
+    int32_t *scratch_t = (int32_t *)((char *)workspace + sizeof(GridWorkspace));
+    grid_raycast_v4<<<(unsigned)blocks, threads, 0, st>>>(hit, miss, scratch_t, ws, xw, yw, cells_per_m, off_x,
+                                                          off_y, ox, oy, cx, cy, total, beams, counters);
+    B2S_CUDA(cudaGetLastError());
+    dim3 fgrid((xw + 31) / 32, (yw + 31) / 32);
+    grid_fold_kernel<<<fgrid, 256, 0, st>>>(miss, scratch_t, ws, xw, yw);
+    B2S_CUDA(cudaGetLastError());
+    B2S_CUDA(cudaMemsetAsync(ws, 0x80, sizeof(GridWorkspace), st));
     return B2S_OK;
 }
 

@@ -98,6 +98,7 @@ struct b2s_mapping {
     cudaStream_t stream;
     int32_t *hit, *miss;
     int32_t *counters;
+    void *workspace;
     Buf d_in, d_datamap, d_pmap;
 };
 
@@ -132,7 +133,7 @@ extern "C" int b2s_tune(const char *key, int value)
 {
     B2S_REQUIRE(key, "b2s_tune: null key");
     if (strcmp(key, "grid_variant") == 0) {
-        B2S_REQUIRE(value >= 1 && value <= 2, "b2s_tune: grid_variant must be 1 or 2");
+        B2S_REQUIRE((value >= 1 && value <= 4) || value == 99, "b2s_tune: grid_variant must be 1..4");
         g_grid_variant = value;
         return B2S_OK;
     }
@@ -281,7 +282,7 @@ extern "C" int b2s_mapping_create(b2s_mapping **out, int xw, int yw, double xyre
 {
     B2S_REQUIRE(out, "b2s_mapping_create: null pointer");
     *out = nullptr;
-    B2S_REQUIRE(xw > 0 && yw > 0 && (long long)xw * yw < (1ll << 31), "b2s_mapping_create: grid size");
+    B2S_REQUIRE(xw > 0 && yw > 0 && (long long)xw * yw < (1ll << 30), "b2s_mapping_create: grid size");
     B2S_REQUIRE(xyreso > 0.0 && isfinite(xyreso), "b2s_mapping_create: xyreso must be positive");
     int ndev = 0;
     B2S_CUDA(cudaGetDeviceCount(&ndev));
@@ -306,11 +307,14 @@ extern "C" int b2s_mapping_create(b2s_mapping **out, int xw, int yw, double xyre
     m->w_miss = w_miss;
     m->thresh = thresh;
     m->hit = m->miss = m->counters = nullptr;
+    m->workspace = nullptr;
     const size_t plane = (size_t)xw * yw * sizeof(int32_t);
     cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->hit, plane);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->miss, plane);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->counters, B2S_CNT_WORDS * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&m->workspace, b2s_grid_workspace_bytes(xw, yw));
+    if (e == cudaSuccess && b2s_grid_workspace_init(m->workspace, xw, yw, m->stream) != B2S_OK) e = cudaErrorUnknown;
     if (e == cudaSuccess) e = cudaMemsetAsync(m->hit, 0, plane, m->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(m->miss, 0, plane, m->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(m->counters, 0, B2S_CNT_WORDS * sizeof(int32_t), m->stream);
@@ -332,6 +336,7 @@ extern "C" int b2s_mapping_destroy(b2s_mapping *m)
     if (m->hit) cudaFree(m->hit);
     if (m->miss) cudaFree(m->miss);
     if (m->counters) cudaFree(m->counters);
+    if (m->workspace) cudaFree(m->workspace);
     m->d_in.release(); m->d_datamap.release(); m->d_pmap.release();
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
@@ -382,8 +387,8 @@ extern "C" int b2s_mapping_update(b2s_mapping *m, const float *ox, const float *
             return B2S_ERR_NONFINITE;
         }
         B2S_CUDA(cudaMemsetAsync(m->counters, 0, B2S_CNT_WORDS * sizeof(int32_t), m->stream));
-        rc = b2s_grid_raycast(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y, d_ox, d_oy,
-                              d_cx, d_cy, scans, beams, m->counters, m->stream);
+        rc = b2s_grid_raycast_ws(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y, d_ox, d_oy,
+                                 d_cx, d_cy, scans, beams, m->counters, m->workspace, m->stream);
         if (rc) return rc;
     }
     if (pmap_out) {

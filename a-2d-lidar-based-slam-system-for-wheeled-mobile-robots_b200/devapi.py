@@ -29,16 +29,25 @@ def new_planes(xw, yw, device=None):
     return hit, miss
 
 
-def grid_raycast(hit, miss, cells_per_m, off_x, off_y, ox, oy, cx, cy, counters=None):
-    """b2s_grid_raycast: hit/miss int32 (xw,yw); ox, oy float32 (K,N); cx, cy float32 (K,)."""
+def new_workspace(xw, yw, device=None):
+    """Workspace for grid_raycast(..., workspace=): b2s_grid_workspace_bytes, initialised."""
+    nbytes = _lib.lib().b2s_grid_workspace_bytes(int(xw), int(yw))
+    ws = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=device or "cuda")
+    _lib.check(_lib.lib().b2s_grid_workspace_init(ws.data_ptr(), int(xw), int(yw), _stream()))
+    return ws
+
+
+def grid_raycast(hit, miss, cells_per_m, off_x, off_y, ox, oy, cx, cy, counters=None, workspace=None):
+    """b2s_grid_raycast[_ws]: hit/miss int32 (xw,yw); ox, oy float32 (K,N); cx, cy float32 (K,)."""
     xw, yw = hit.shape
     K, N = ox.shape
-    rc = _lib.lib().b2s_grid_raycast(
+    rc = _lib.lib().b2s_grid_raycast_ws(
         _chk(hit, torch.int32, "hit"), _chk(miss, torch.int32, "miss"), xw, yw,
         float(cells_per_m), float(off_x), float(off_y),
         _chk(ox, torch.float32, "ox"), _chk(oy, torch.float32, "oy"),
         _chk(cx, torch.float32, "cx"), _chk(cy, torch.float32, "cy"), K, N,
-        None if counters is None else _chk(counters, torch.int32, "counters"), _stream())
+        None if counters is None else _chk(counters, torch.int32, "counters"),
+        None if workspace is None else _chk(workspace, torch.int32, "workspace"), _stream())
     _lib.check(rc)
 
 

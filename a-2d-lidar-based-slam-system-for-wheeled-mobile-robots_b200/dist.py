@@ -104,6 +104,7 @@ class ShardedMapping(object):
         self.weights = (float(hit_weight), float(miss_weight), float(occ_threshold))
         self.hit, self.miss = devapi.new_planes(self.xw, self.yw)        # global counts
         self.d_hit, self.d_miss = devapi.new_planes(self.xw, self.yw)    # this call's deltas
+        self.workspace = devapi.new_workspace(self.xw, self.yw)
         self.pmap_dev = torch.empty((self.xw, self.yw), dtype=torch.int8, device="cuda")
         self.pmap_host = torch.empty((self.xw, self.yw), dtype=torch.int8).pin_memory()
         self._in = None
@@ -118,7 +119,7 @@ class ShardedMapping(object):
         self.d_hit.zero_()
         self.d_miss.zero_()
         S, Hx, Hy = self.scale
-        self._dev.grid_raycast(self.d_hit, self.d_miss, S, Hx, Hy, *self._in)
+        self._dev.grid_raycast(self.d_hit, self.d_miss, S, Hx, Hy, *self._in, workspace=self.workspace)
         allreduce_counts(self.d_hit, self.d_miss)
         self.hit += self.d_hit
         self.miss += self.d_miss

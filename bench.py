@@ -246,6 +246,7 @@ def bench_grid(args, rank, world, torch, devapi, bdist, synth):
     host = synth.grid_scans(12001 + rank, K, N)
     ox, oy, cx, cy = (torch.from_numpy(a).cuda() for a in host)
     hit, miss = devapi.new_planes(G, G)
+    ws = devapi.new_workspace(G, G)
     pmap = torch.empty((G, G), dtype=torch.int8, device="cuda")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
@@ -254,7 +255,7 @@ def bench_grid(args, rank, world, torch, devapi, bdist, synth):
         miss.zero_()
         if ev:
             ev[0].record()
-        devapi.grid_raycast(hit, miss, S, Hx, Hy, ox, oy, cx, cy)
+        devapi.grid_raycast(hit, miss, S, Hx, Hy, ox, oy, cx, cy, workspace=ws)
         if ev:
             ev[1].record()
         bdist.allreduce_counts(hit, miss)
@@ -330,7 +331,7 @@ def bench_grid(args, rank, world, torch, devapi, bdist, synth):
                    "parallelism": "scan streams sharded by rank, int32 count deltas all-reduced (NCCL)" if world > 1
                    else "single GPU"},
         "dtype": "int32 counts / f64 cell+error arithmetic",
-        "roofline": {"bound": "hbm", "kernel": "grid_raycast", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "grid_raycast (+ fold of the transposed scratch plane)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": ray_avg_ms,
                      "cell_visits_per_s": visits / (ray_avg_ms * 1e-3)},
@@ -338,7 +339,7 @@ def bench_grid(args, rank, world, torch, devapi, bdist, synth):
                 "h2d_bytes_per_step": 8 * K * N + 8 * K, "d2h_bytes_per_step": G * G,
                 "api": "Mapping.update_batch (b2s_mapping_update)" if world == 1 else "dist.ShardedMapping.update_batch",
                 "ms_per_step": e2e_s / e2e_steps * 1e3},
-        "gpu_launches": 2 * args.steps,
+        "gpu_launches": 3 * args.steps,
         "clocks": clocks,
     }
     return res

@@ -51,7 +51,8 @@ const char *b2s_status_string(int status);
 const char *b2s_last_error(void); /* thread-local, valid until the next call on this thread */
 int b2s_device_count(int *count);
 /* Kernel-variant switch for benchmarking (key "grid_variant": 1 = one RED per visit, 2 = warp-
- * aggregated runs, the default).  Not part of the reference surface. */
+ * aggregated runs, 3 = lean loop, 4 = transposed scratch plane, the default).  Not part of the
+ * reference surface. */
 int b2s_tune(const char *key, int value);
 
 /* ===================================================================== layer 1: device */
@@ -85,6 +86,20 @@ int b2s_grid_raycast(int32_t *hit, int32_t *miss, int xw, int yw, double cells_p
                      double off_x, double off_y, const float *ox, const float *oy,
                      const float *cx, const float *cy, int scans, int beams, int32_t *counters,
                      void *stream);
+
+/* Same update with a caller-provided workspace, which enables the fastest kernel: y-major beams
+ * accumulate into a transposed scratch plane inside the workspace (so that the 32 beams of a warp
+ * touch consecutive words in either orientation) and a transpose-add folds it into `miss` before the
+ * call's work completes on the stream.  Result and planes are identical to b2s_grid_raycast.
+ * workspace: device memory of b2s_grid_workspace_bytes(xw, yw) bytes, 16-byte aligned, prepared once
+ * by b2s_grid_workspace_init and reusable across calls on the same stream; NULL falls back to
+ * b2s_grid_raycast. */
+size_t b2s_grid_workspace_bytes(int xw, int yw);
+int b2s_grid_workspace_init(void *workspace, int xw, int yw, void *stream);
+int b2s_grid_raycast_ws(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m,
+                        double off_x, double off_y, const float *ox, const float *oy,
+                        const float *cx, const float *cy, int scans, int beams, int32_t *counters,
+                        void *workspace, void *stream);
 
 /* Screening of a batch before it is applied: flags[0] |= 1 if a NaN is present, flags[1] |= 1 if
  * oy or a sensor position holds an inf -- the values int() raises on in [MAP]:33-36 (ValueError /

@@ -27,10 +27,10 @@ def env():
 
 
 def _variants(env):
-    for v in (1, 2):
+    for v in (1, 2, 3, 4):
         assert env.lib.lib().b2s_tune(b"grid_variant", v) == 0
         yield v
-    env.lib.lib().b2s_tune(b"grid_variant", 2)
+    env.lib.lib().b2s_tune(b"grid_variant", 4)
 
 
 # ----------------------------------------------------------------------------- bresenham (A7)
@@ -151,7 +151,14 @@ def test_cfg3_counts_bit_exact_vs_oracle(env):
     for v in _variants(env):
         hit, miss = env.dev.new_planes(G, G)
         cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
-        env.dev.grid_raycast(hit, miss, S, Hx, Hy, *devt, counters=cnt)
+        ws = env.dev.new_workspace(G, G) if v == 4 else None
+        env.dev.grid_raycast(hit, miss, S, Hx, Hy, *devt, counters=cnt, workspace=ws)
+        if ws is not None:  # the workspace comes back clean and is reusable
+            torch.cuda.synchronize()
+            assert int(ws[16:].abs().sum().item()) == 0 and ws[:4].tolist() == [-2139062144] * 4
+            env.dev.grid_raycast(hit, miss, S, Hx, Hy, *devt, workspace=ws)
+            hit //= 2
+            miss //= 2
         torch.cuda.synchronize()
         assert int(hit.sum().item() + miss.sum().item()) == visits
         assert np.array_equal(hit.cpu().numpy(), oh), "variant %d" % v
@@ -181,6 +188,17 @@ def test_cfg3_full_size_properties(env):
     h2, m2 = env.dev.new_planes(G, G)
     env.dev.grid_raycast(h2, m2, S, Hx, Hy, ox, oy, cx, cy)
     assert torch.equal(h1, h2) and torch.equal(m1, m2)
+    env.lib.lib().b2s_tune(b"grid_variant", 3)
+    h2.zero_()
+    m2.zero_()
+    env.dev.grid_raycast(h2, m2, S, Hx, Hy, ox, oy, cx, cy)
+    assert torch.equal(h1, h2) and torch.equal(m1, m2)
+    env.lib.lib().b2s_tune(b"grid_variant", 4)
+    ws = env.dev.new_workspace(G, G)
+    h2.zero_()
+    m2.zero_()
+    env.dev.grid_raycast(h2, m2, S, Hx, Hy, ox, oy, cx, cy, workspace=ws)
+    assert torch.equal(h1, h2) and torch.equal(m1, m2)
     # every beam of this workload ends inside the grid -> exactly one hit per non-degenerate beam
     assert int(h2.sum().item()) <= K * N and int(h2.sum().item()) > 0.99 * K * N
     # 4 emulated ranks: private delta planes summed == single pass (integer sums commute)
@@ -189,7 +207,7 @@ def test_cfg3_full_size_properties(env):
         lo, hi = r * K // 4, (r + 1) * K // 4
         dh, dm = env.dev.new_planes(G, G)
         env.dev.grid_raycast(dh, dm, S, Hx, Hy, ox[lo:hi].contiguous(), oy[lo:hi].contiguous(),
-                             cx[lo:hi].contiguous(), cy[lo:hi].contiguous())
+                             cx[lo:hi].contiguous(), cy[lo:hi].contiguous(), workspace=ws)
         acc_h += dh
         acc_m += dm
     assert torch.equal(acc_h, h2) and torch.equal(acc_m, m2)
@@ -221,19 +239,22 @@ def test_clipping_out_of_grid_and_counters(env):
     assert om.sum() > 0
     for v in _variants(env):
         hit, miss = env.dev.new_planes(G, G)
-        env.dev.grid_raycast(hit, miss, S, Hx, Hy, *[torch.from_numpy(a).cuda() for a in (ox, oy, cx, cy)])
-        assert np.array_equal(hit.cpu().numpy(), oh) and np.array_equal(miss.cpu().numpy(), om)
+        ws = env.dev.new_workspace(G, G) if v == 4 else None
+        env.dev.grid_raycast(hit, miss, S, Hx, Hy, *[torch.from_numpy(a).cuda() for a in (ox, oy, cx, cy)],
+                             workspace=ws)
+        assert np.array_equal(hit.cpu().numpy(), oh) and np.array_equal(miss.cpu().numpy(), om), v
     ox2 = ox.copy()
     oy2 = oy.copy()
     ox2[0, 0] = np.inf
     ox2[0, 1] = np.nan
     oy2[0, 2] = np.inf
     ox2[0, 3] = 3e30
-    hit, miss = env.dev.new_planes(G, G)
-    cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
-    env.dev.grid_raycast(hit, miss, S, Hx, Hy, *[torch.from_numpy(a).cuda() for a in (ox2, oy2, cx, cy)],
-                         counters=cnt)
-    assert cnt.tolist() == [2, 1, 1, 0]
+    for ws in (None, env.dev.new_workspace(G, G)):
+        hit, miss = env.dev.new_planes(G, G)
+        cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
+        env.dev.grid_raycast(hit, miss, S, Hx, Hy, *[torch.from_numpy(a).cuda() for a in (ox2, oy2, cx, cy)],
+                             counters=cnt, workspace=ws)
+        assert cnt.tolist() == [2, 1, 1, 0]
 
 
 def test_cfg5_shape_smoke(env):
@@ -243,7 +264,7 @@ def test_cfg5_shape_smoke(env):
     assert (Hx, Hy) == (409.6, 409.6)
     host, devt = _device_scans(env, 5001, 8, 1080, 300.0)
     hit, miss = env.dev.new_planes(G, G)
-    env.dev.grid_raycast(hit, miss, S, Hx, Hy, *devt)
+    env.dev.grid_raycast(hit, miss, S, Hx, Hy, *devt, workspace=env.dev.new_workspace(G, G))
     oh = np.zeros((G, G), dtype=np.int32)
     om = np.zeros((G, G), dtype=np.int32)
     env.corc.grid_raycast(oh, om, S, Hx, Hy, *host)
