@@ -317,33 +317,59 @@ struct GridWorkspace {      // lives at the front of the caller-provided workspa
     int pad[12];
 };
 
+// One warp-step.  Everything that addresses memory is kept DOUBLED (key2 = 2*cell + plane bit) so the
+// run key, the plane selector and the byte offset (key2 * 2, minus the plane bit folded into the
+// base pointer) come out of one add; SHFL's own in-range predicate marks lane 0 as a run head;
+// the run length is ffs of the head mask funnel-shifted past this lane with a sentinel at lane 32;
+// the RED is predicated, not branched.
 template <bool GUARD_START>
-__device__ __forceinline__ void march_step4(int t, int delay, double slope, double &acc, unsigned &cmaj, int &minor,
-                                            unsigned pitch, int inc, unsigned wmin, int t_em, unsigned em_len,
-                                            unsigned steep_bit, unsigned dead_key, unsigned lane, unsigned lane_bit,
-                                            int32_t *__restrict__ plane)
+__device__ __forceinline__ void march_step4(int t, int delay, double slope, double &acc, unsigned &cmaj2, int &minor2,
+                                            unsigned pitch2, int inc2, unsigned wmin2, int t_em, unsigned em_len,
+                                            unsigned dead_key, unsigned lane1, unsigned long long plane_base)
 {
-    const bool started = !GUARD_START || (t >= delay);
-    const bool emit = ((unsigned)(t - t_em) <= em_len) && ((unsigned)minor < wmin);
-    const unsigned cell = cmaj + (unsigned)minor;  // exact inside the window (mod 2^32 outside)
-    const unsigned key = emit ? ((cell << 1) | steep_bit) : dead_key;
-    if (started) {
-        acc = __dadd_rn(acc, slope);  // [BRES]:51
-        if (acc >= 0.5) {             // [BRES]:53
-            minor += inc;             // [BRES]:54
-            acc = __dadd_rn(acc, -1.0);  // [BRES]:55
-        }
-        cmaj += pitch;
+    const bool emit = ((unsigned)(t - t_em) <= em_len) && ((unsigned)minor2 < wmin2);
+    const unsigned key = emit ? (cmaj2 + (unsigned)minor2) : dead_key;  // exact inside the window
+    if (!GUARD_START || t >= delay) {
+        // [BRES]:51-55, kept as predicated instructions (the compiler otherwise turns the `if` into
+        // an unconditional DADD plus selects): acc += slope; if (acc >= 0.5) { minor += inc; acc -= 1.0; }
+        asm("{\n\t"
+            ".reg .pred p;\n\t"
+            "add.rn.f64 %0, %0, %2;\n\t"
+            "setp.ge.f64 p, %0, 0d3FE0000000000000;\n\t"
+            "@p add.rn.f64 %0, %0, 0dBFF0000000000000;\n\t"
+            "@p add.s32 %1, %1, %3;\n\t"
+            "}"
+            : "+d"(acc), "+r"(minor2)
+            : "d"(slope), "r"(inc2));
+        cmaj2 += pitch2;
     }
-    const unsigned left = __shfl_up_sync(0xffffffffu, key, 1);
-    const bool head = (lane == 0) || (key != left);
+    unsigned left;
+    int in_range;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "shfl.sync.up.b32 %0|p, %2, 1, 0, 0xffffffff;\n\t"
+        "selp.s32 %1, 1, 0, p;\n\t"
+        "}"
+        : "=r"(left), "=r"(in_range)
+        : "r"(key));
+    const bool head = !in_range || (key != left);
     const unsigned heads = __ballot_sync(0xffffffffu, head);
-    const unsigned ahead = ((__brev(heads) << lane) << 1) | lane_bit;
-    const int run = __clz(ahead) + 1;
-    if (head && emit) atomicAdd(plane + cell, run);
+    // heads of the lanes after this one, with a sentinel head at virtual lane 32
+    const int run = __ffs(__funnelshift_rc(heads, 1u, lane1));
+    // byte offset of the int32 cell = (key >> 1) * 4 = key * 2 - 2 * (plane bit); the latter is folded into plane_base
+    const unsigned long long addr = plane_base + (unsigned long long)key * 2ull;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.s32 q, %2, 0;\n\t"
+        "@q red.global.add.s32 [%0], %1;\n\t"
+        "}" ::"l"(addr),
+        "r"(run), "r"((int)(head && emit))
+        : "memory");
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 grid_raycast_v4(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int32_t *__restrict__ scratch_t,
                 GridWorkspace *__restrict__ ws, int xw, int yw, double cells_per_m, double off_x, double off_y,
                 const float *__restrict__ ox, const float *__restrict__ oy, const float *__restrict__ cx,
@@ -399,8 +425,10 @@ grid_raycast_v4(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int32_t *
 
     const int wmaj = b.steep ? yw : xw;
     const unsigned wmin = (unsigned)(b.steep ? xw : yw);
-    const unsigned pitch = wmin;  // both planes are stored major-row by major-row for their beams
-    int32_t *plane = b.steep ? scratch_t : miss;
+    const unsigned steep_bit = b.steep ? 1u : 0u;
+    // both planes are stored major-row by major-row for their beams; offsets are kept doubled
+    const unsigned pitch2 = 2u * wmin;
+    const unsigned long long plane_base = (unsigned long long)(uintptr_t)(b.steep ? scratch_t : miss) - 2ull * steep_bit;
     const int delay = (live && b.hit_k == 0) ? (tmax - span) : 0;
     int dmax = delay;
 #pragma unroll
@@ -412,22 +440,23 @@ grid_raycast_v4(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int32_t *
     const unsigned em_len = any ? (unsigned)(k_hi - k_lo) : 0u;
 
     double acc = 0.0;
-    unsigned cmaj = (unsigned)b.major0 * pitch;
-    int minor = b.minor0;
-    const int inc = b.inc;
-    const unsigned steep_bit = b.steep ? 1u : 0u;
+    unsigned cmaj2 = (unsigned)b.major0 * pitch2 + steep_bit;  // 2 * (major part of the cell offset) + plane bit
+    // |minor0| < 2^30, so 2 * minor0 fits an int; only values in [0, 2 * wmin) ever reach memory
+    int minor2 = 2 * b.minor0;
+    const int inc2 = 2 * b.inc;
+    const unsigned wmin2 = 2u * wmin;
     const unsigned dead_key = 0x80000000u | lane;  // cells < 2^30, so live keys stay below 2^31
-    const unsigned lane_bit = 1u << lane;
+    const unsigned lane1 = lane + 1;
     const double slope = b.slope;
 
     int t = 0;
     for (; t < dmax; ++t)
-        march_step4<true>(t, delay, slope, acc, cmaj, minor, pitch, inc, wmin, t_em, em_len, steep_bit, dead_key,
-                          lane, lane_bit, plane);
+        march_step4<true>(t, delay, slope, acc, cmaj2, minor2, pitch2, inc2, wmin2, t_em, em_len, dead_key, lane1,
+                          plane_base);
 #pragma unroll 4
     for (; t <= tmax; ++t)
-        march_step4<false>(t, delay, slope, acc, cmaj, minor, pitch, inc, wmin, t_em, em_len, steep_bit, dead_key,
-                           lane, lane_bit, plane);
+        march_step4<false>(t, delay, slope, acc, cmaj2, minor2, pitch2, inc2, wmin2, t_em, em_len, dead_key, lane1,
+                           plane_base);
 }
 
 // miss[x][y] += scratch_t[y][x] over the recorded bounding box, scratch_t cleared on the way.

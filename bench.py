@@ -267,7 +267,7 @@ def bench_grid(args, rank, world, torch, devapi, bdist, synth):
     torch.cuda.synchronize()
     # algorithmic bytes of one ray-cast launch: endpoints + poses + 8 B per in-grid cell visit
     hit.zero_(); miss.zero_()
-    devapi.grid_raycast(hit, miss, S, Hx, Hy, ox, oy, cx, cy)
+    devapi.grid_raycast(hit, miss, S, Hx, Hy, ox, oy, cx, cy, workspace=ws)
     visits = int(hit.sum(dtype=torch.int64).item() + miss.sum(dtype=torch.int64).item())
     algo_bytes = 8 * K + 8 * K * N + 8 * visits
 
