@@ -35,6 +35,7 @@ int sm_count()
 }
 
 extern int g_grid_variant;
+extern int g_icp_src_per_thread;
 
 // Growable device / pinned-host staging buffer.
 struct Buf {
@@ -135,6 +136,11 @@ extern "C" int b2s_tune(const char *key, int value)
     if (strcmp(key, "grid_variant") == 0) {
         B2S_REQUIRE((value >= 1 && value <= 4) || value == 99, "b2s_tune: grid_variant must be 1..4");
         g_grid_variant = value;
+        return B2S_OK;
+    }
+    if (strcmp(key, "icp_src_per_thread") == 0) {
+        B2S_REQUIRE(value == 0 || (value >= 2 && value <= 4), "b2s_tune: icp_src_per_thread must be 0, 2, 3 or 4");
+        g_icp_src_per_thread = value;
         return B2S_OK;
     }
     set_error("b2s_tune: unknown key %s", key);

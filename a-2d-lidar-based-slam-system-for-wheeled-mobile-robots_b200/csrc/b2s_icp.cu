@@ -22,7 +22,8 @@
 
 namespace b2s {
 
-constexpr int SRC_PER_THREAD = 4;
+constexpr int FIT_SUMS = 9;
+constexpr int SCRATCH_DOUBLES = FIT_SUMS * 32;
 
 // Closed-form Kabsch for row-matched sets given centred sums; returns T (row-major 2x3 part).
 __device__ __forceinline__ void rotation_from_w(double w00, double w01, double w10, double w11,
@@ -44,51 +45,61 @@ __device__ __forceinline__ void rotation_from_w(double w00, double w01, double w
     T[5] = cby - (s * cax + c * cay);
 }
 
-// Fit of per-thread registers a[r] -> b[r] over the CTA (getTransform, [ICP]:149-179).
-// valid[r] marks the slots that hold a point.  Four __syncthreads() inside.
-__device__ __forceinline__ void cta_rigid_fit(const double (&ax)[SRC_PER_THREAD],
-                                              const double (&ay)[SRC_PER_THREAD],
-                                              const double (&bx)[SRC_PER_THREAD],
-                                              const double (&by)[SRC_PER_THREAD], int count, int n,
-                                              double *scratch, double (&T)[6])
+// getTransform ([ICP]:149-179) over the CTA for points held in registers: a[r] -> b[r].
+//
+// The reference centres both sets on their means and then forms W = BB^T.AA, which needs two
+// reductions.  Here every coordinate is taken relative to a FIXED per-pair shift close to the
+// centroids (sa, sb: the centroids of the original source / of the target scan), the first and
+// second moments are reduced together in ONE block reduction, and the exact identity
+//     sum (b-cb)(a-ca)^T = sum (b-sb)(a-sa)^T - n (cb-sb)(ca-sa)^T
+// removes the offset.  Because |c - s| is of the order of the scan-to-scan motion while the spread
+// of a scan is metres, the subtracted term is ~1e-3 of W and costs no accuracy (the parity tests hold
+// the result to 1e-9 of the reference).  `extra` rides along in the same reduction (the distance sum).
+template <int R>
+__device__ __forceinline__ void cta_rigid_fit(const double (&ax)[R], const double (&ay)[R],
+                                              const double (&bx)[R], const double (&by)[R], int count,
+                                              int n, double sax, double say, double sbx, double sby,
+                                              double &extra, double *scratch, double (&T)[6])
 {
-    double s4[4] = {0.0, 0.0, 0.0, 0.0};
+    double v[FIT_SUMS];
 #pragma unroll
-    for (int r = 0; r < SRC_PER_THREAD; ++r)
+    for (int k = 0; k < FIT_SUMS; ++k) v[k] = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
         if (r < count) {
-            s4[0] += ax[r];
-            s4[1] += ay[r];
-            s4[2] += bx[r];
-            s4[3] += by[r];
+            const double px = ax[r] - sax, py = ay[r] - say;
+            const double qx = bx[r] - sbx, qy = by[r] - sby;
+            v[0] += px;
+            v[1] += py;
+            v[2] += qx;
+            v[3] += qy;
+            v[4] = fma(qx, px, v[4]);  // W = BB^T . AA  ([ICP]:160)
+            v[5] = fma(qx, py, v[5]);
+            v[6] = fma(qy, px, v[6]);
+            v[7] = fma(qy, py, v[7]);
         }
-    block_sum<4>(s4, scratch);
+    v[8] = extra;
+    block_sum<FIT_SUMS>(v, scratch);
     const double inv = 1.0 / (double)n;
-    const double cax = s4[0] * inv, cay = s4[1] * inv, cbx = s4[2] * inv, cby = s4[3] * inv;
-    double w4[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int r = 0; r < SRC_PER_THREAD; ++r)
-        if (r < count) {
-            const double px = ax[r] - cax, py = ay[r] - cay;
-            const double qx = bx[r] - cbx, qy = by[r] - cby;
-            w4[0] = fma(qx, px, w4[0]);  // W = BB^T . AA  ([ICP]:160)
-            w4[1] = fma(qx, py, w4[1]);
-            w4[2] = fma(qy, px, w4[2]);
-            w4[3] = fma(qy, py, w4[3]);
-        }
-    block_sum<4>(w4, scratch);
-    rotation_from_w(w4[0], w4[1], w4[2], w4[3], cax, cay, cbx, cby, T);
+    const double mpx = v[0] * inv, mpy = v[1] * inv, mqx = v[2] * inv, mqy = v[3] * inv;
+    const double w00 = v[4] - v[2] * mpx, w01 = v[5] - v[2] * mpy;
+    const double w10 = v[6] - v[3] * mpx, w11 = v[7] - v[3] * mpy;
+    (void)mqx;
+    (void)mqy;
+    rotation_from_w(w00, w01, w10, w11, sax + mpx, say + mpy, sbx + mqx, sby + mqy, T);
+    extra = v[8];
 }
 
-template <typename TIn>
+template <typename TIn, int R>
 __global__ void icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__restrict__ src_xy, int n,
                                  int m, int max_iter, double tol, double *__restrict__ T_out,
                                  int32_t *__restrict__ iters_out, int use_bulk)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [mbarrier 16 B][scratch 4*32 doubles][tar double2 * m][staging TIn * 2m]
+    // layout: [mbarrier 16 B][scratch][tar double2 * m][staging TIn * 2m]
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     double *scratch = reinterpret_cast<double *>(smem_raw + 16);
-    double2 *tar = reinterpret_cast<double2 *>(smem_raw + 16 + 4 * 32 * sizeof(double));
+    double2 *tar = reinterpret_cast<double2 *>(smem_raw + 16 + SCRATCH_DOUBLES * sizeof(double));
     TIn *stage = reinterpret_cast<TIn *>(tar + m);
 
     const int pair = blockIdx.x;
@@ -113,17 +124,20 @@ __global__ void icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__re
     }
 
     // ---- this thread's source points (registers for the whole solve); overlaps the copy
-    double ox_[SRC_PER_THREAD], oy_[SRC_PER_THREAD];  // original
-    double sx[SRC_PER_THREAD], sy[SRC_PER_THREAD];    // moved
+    double ox_[R], oy_[R];  // original
+    double sx[R], sy[R];    // moved
     int count = 0;
+    double first[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int r = 0; r < SRC_PER_THREAD; ++r) {
+    for (int r = 0; r < R; ++r) {
         const int i = tid + r * blockDim.x;
         ox_[r] = oy_[r] = 0.0;
         if (i < n) {
             ox_[r] = (double)src_g[i];
             oy_[r] = (double)src_g[n + i];
             count = r + 1;
+            first[0] += ox_[r];
+            first[1] += oy_[r];
         }
         sx[r] = ox_[r];
         sy[r] = oy_[r];
@@ -131,17 +145,25 @@ __global__ void icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__re
 
     if (use_bulk) mbar_wait(bar, 0);
     else __syncthreads();
-    for (int j = tid; j < m; j += blockDim.x) tar[j] = make_double2((double)stage[j], (double)stage[m + j]);
-    __syncthreads();
+    for (int j = tid; j < m; j += blockDim.x) {
+        const double2 t = make_double2((double)stage[j], (double)stage[m + j]);
+        tar[j] = t;
+        first[2] += t.x;
+        first[3] += t.y;
+    }
+    // fixed shifts for the one-pass fits: centroid of the original source, centroid of the target scan
+    block_sum<4>(first, scratch);  // its barriers also publish tar[]
+    const double sax = first[0] / (double)n, say = first[1] / (double)n;
+    const double sbx = first[2] / (double)m, sby = first[3] / (double)m;
 
     double prev_err = 0.0;
     int iters = 0;
     for (int it = 0; it < max_iter; ++it) {
         // ---- nearest neighbour ([ICP]:99-106)
-        double best[SRC_PER_THREAD];
-        int arg[SRC_PER_THREAD];
+        double best[R];
+        int arg[R];
 #pragma unroll
-        for (int r = 0; r < SRC_PER_THREAD; ++r) {
+        for (int r = 0; r < R; ++r) {
             best[r] = INFINITY;
             arg[r] = 0;
         }
@@ -149,7 +171,7 @@ __global__ void icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__re
         for (int j = 0; j < m; ++j) {
             const double2 t = tar[j];
 #pragma unroll
-            for (int r = 0; r < SRC_PER_THREAD; ++r) {
+            for (int r = 0; r < R; ++r) {
                 const double dx = sx[r] - t.x, dy = sy[r] - t.y;
                 const double d2 = fma(dy, dy, dx * dx);
                 if (d2 < best[r]) {
@@ -159,33 +181,33 @@ __global__ void icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__re
             }
         }
         // ---- matched targets, distances ([ICP]:69,75)
-        double bx[SRC_PER_THREAD], by[SRC_PER_THREAD];
-        double dsum[1] = {0.0};
+        double bx[R], by[R];
+        double dsum = 0.0;
 #pragma unroll
-        for (int r = 0; r < SRC_PER_THREAD; ++r) {
+        for (int r = 0; r < R; ++r) {
             const double2 t = tar[arg[r]];
             bx[r] = t.x;
             by[r] = t.y;
-            if (r < count) dsum[0] += (best[r] == INFINITY) ? 0.0 : sqrt(best[r]);
+            if (r < count) dsum += (best[r] == INFINITY) ? 0.0 : sqrt(best[r]);
         }
         double T[6];
-        cta_rigid_fit(sx, sy, bx, by, count, n, scratch, T);
-        block_sum<1>(dsum, scratch);
+        cta_rigid_fit<R>(sx, sy, bx, by, count, n, sax, say, sbx, sby, dsum, scratch, T);
         // ---- src <- T . src ([ICP]:71)
 #pragma unroll
-        for (int r = 0; r < SRC_PER_THREAD; ++r) {
+        for (int r = 0; r < R; ++r) {
             const double x = sx[r], y = sy[r];
             sx[r] = T[0] * x + T[1] * y + T[2];
             sy[r] = T[3] * x + T[4] * y + T[5];
         }
         ++iters;
-        const double err = dsum[0] / (double)n;
+        const double err = dsum / (double)n;
         if (fabs(prev_err - err) < tol) break;  // [ICP]:76, uniform across the CTA
         prev_err = err;
     }
 
     double T[6];
-    cta_rigid_fit(ox_, oy_, sx, sy, count, n, scratch, T);  // [ICP]:81
+    double unused = 0.0;
+    cta_rigid_fit<R>(ox_, oy_, sx, sy, count, n, sax, say, sax, say, unused, scratch, T);  // [ICP]:81
     if (tid == 0) {
         double *o = T_out + (size_t)pair * 9;
         o[0] = T[0]; o[1] = T[1]; o[2] = T[2];
@@ -268,6 +290,34 @@ rigid_fit_kernel(const double *__restrict__ src_xy, const double *__restrict__ t
     }
 }
 
+int g_icp_src_per_thread = 0;  // 0: choose per problem size; 2..4 force (tuning hook)
+
+template <typename TIn, int R>
+static int launch_icp_r(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_src, int n_tar, int max_iter,
+                        double tol, double *T_out, int32_t *iters_out, void *stream)
+{
+    int threads = (n_src + R - 1) / R;
+    threads = ((threads + 31) / 32) * 32;
+    if (threads < 64) threads = 64;
+    B2S_REQUIRE(threads <= 1024, "b2s_icp_batch: too many source points per scan");
+    const size_t smem = 16 + SCRATCH_DOUBLES * sizeof(double) + (size_t)n_tar * sizeof(double2) +
+                        (size_t)n_tar * 2 * sizeof(TIn);
+    B2S_REQUIRE(smem <= 227 * 1024, "b2s_icp_batch: n_tar too large for shared memory");
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        B2S_CUDA(cudaFuncSetAttribute(icp_batch_kernel<TIn, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        configured = smem;
+    }
+    // bulk copy needs 16-byte aligned source and size: every pair's target block must qualify
+    const size_t pair_bytes = (size_t)2 * n_tar * sizeof(TIn);
+    const int use_bulk = ((uintptr_t)tar_xy % 16 == 0) && (pair_bytes % 16 == 0);
+    icp_batch_kernel<TIn, R><<<pairs, threads, smem, (cudaStream_t)stream>>>(
+        tar_xy, src_xy, n_src, n_tar, max_iter, tol, T_out, iters_out, use_bulk);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+
 template <typename TIn>
 static int launch_icp(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_src, int n_tar,
                       int max_iter, double tol, double *T_out, int32_t *iters_out, void *stream)
@@ -276,27 +326,30 @@ static int launch_icp(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_src
     if (pairs == 0) return B2S_OK;
     B2S_REQUIRE(tar_xy && src_xy && T_out, "b2s_icp_batch: null pointer");
     B2S_REQUIRE(tol == tol, "b2s_icp_batch: NaN tolerance");
-    int threads = (n_src + SRC_PER_THREAD - 1) / SRC_PER_THREAD;
-    threads = ((threads + 31) / 32) * 32;
-    if (threads < 64) threads = 64;
-    B2S_REQUIRE(threads <= 1024, "b2s_icp_batch: n_src above 4096 points per scan is not supported");
-    const size_t smem = 16 + 4 * 32 * sizeof(double) + (size_t)n_tar * sizeof(double2) +
-                        (size_t)n_tar * 2 * sizeof(TIn);
-    B2S_REQUIRE(smem <= 227 * 1024, "b2s_icp_batch: n_tar too large for shared memory");
-    static size_t configured[2] = {0, 0};
-    const int slot = sizeof(TIn) == 8;
-    if (smem > 48 * 1024 && smem > configured[slot]) {
-        B2S_CUDA(cudaFuncSetAttribute(icp_batch_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-        configured[slot] = smem;
+    B2S_REQUIRE(n_src <= 4096, "b2s_icp_batch: n_src above 4096 points per scan is not supported");
+    int r = g_icp_src_per_thread;
+    if (r == 0) {
+        // fewest idle register slots wins; ties go to 3, then 4, then 2 (measured order on B200)
+        int best_waste = 1 << 30;
+        const int order[3] = {3, 4, 2};
+        for (int k = 0; k < 3; ++k) {
+            const int c = order[k];
+            int threads = ((((n_src + c - 1) / c) + 31) / 32) * 32;
+            if (threads < 64) threads = 64;
+            if (threads > 1024) continue;
+            const int waste = threads * c - n_src;
+            if (waste < best_waste) {
+                best_waste = waste;
+                r = c;
+            }
+        }
+        if (r == 0) r = 4;
     }
-    // bulk copy needs 16-byte aligned source and size: every pair's target block must qualify
-    const size_t pair_bytes = (size_t)2 * n_tar * sizeof(TIn);
-    const int use_bulk = ((uintptr_t)tar_xy % 16 == 0) && (pair_bytes % 16 == 0);
-    icp_batch_kernel<TIn><<<pairs, threads, smem, (cudaStream_t)stream>>>(
-        tar_xy, src_xy, n_src, n_tar, max_iter, tol, T_out, iters_out, use_bulk);
-    B2S_CUDA(cudaGetLastError());
-    return B2S_OK;
+    switch (r) {
+    case 2: return launch_icp_r<TIn, 2>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream);
+    case 3: return launch_icp_r<TIn, 3>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream);
+    default: return launch_icp_r<TIn, 4>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream);
+    }
 }
 
 }  // namespace b2s

@@ -447,6 +447,7 @@ def main():
     ap.add_argument("--scans", type=int, default=16384, help="grid scans per GPU per step")
     ap.add_argument("--icp-scans", type=int, default=ICP_SCANS)
     ap.add_argument("--grid-variant", type=int, default=0)
+    ap.add_argument("--icp-r", type=int, default=0, help="force ICP source points per thread (tuning)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only", default="both", choices=["both", "primary"])
     args = ap.parse_args()
@@ -463,6 +464,8 @@ def main():
     rank, local_rank, world = bdist.init()
     if args.grid_variant:
         _lib.check(_lib.lib().b2s_tune(b"grid_variant", args.grid_variant))
+    if args.icp_r:
+        _lib.check(_lib.lib().b2s_tune(b"icp_src_per_thread", args.icp_r))
 
     results = {}
     order = ["grid", "icp"] if args.workload == "grid" else ["icp", "grid"]

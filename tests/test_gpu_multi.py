@@ -1,0 +1,72 @@
+"""Multi-GPU path on real devices (skipped with fewer than 2 GPUs): torchrun, NCCL all-reduce of the
+int32 count deltas, rank-sharded ICP pairs.  The single-GPU emulation of the same logic is in
+test_gpu_grid.py::test_cfg3_full_size_properties; the gloo version in test_dist_gloo.py."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+WORKER = r'''
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.environ["B2S_ROOT"])
+import b2slam.dist as bdist
+from b2slam import devapi, synth
+rank, local, world = bdist.init()
+G = 2048
+sm = bdist.ShardedMapping(G, G, 0.05)
+streams = 2 * world
+lo, hi = bdist.shard_bounds(streams, rank, world)
+for rnd in range(2):
+    parts = [synth.grid_scans(5001 + s + 100 * rnd, 24, 1080, half_extent_m=40.0) for s in range(lo, hi)]
+    ox, oy, cx, cy = (np.concatenate([p[k] for p in parts]) for k in range(4))
+    pm = sm.update_batch(ox, oy, cx, cy)
+hit, miss = sm.counts()
+xy, _ = synth.room_sequence(9001, 41, 360)
+plo, phi = bdist.sequence_pair_bounds(41, rank, world)
+tar = torch.from_numpy(np.ascontiguousarray(xy[plo:phi])).cuda()
+src = torch.from_numpy(np.ascontiguousarray(xy[plo + 1:phi + 1])).cuda()
+T, it = devapi.icp_batch(tar, src)
+counts = [b - a for a, b in (bdist.sequence_pair_bounds(41, q, world) for q in range(world))]
+allT = bdist.gather_transforms(T, counts)
+torch.cuda.synchronize()
+np.savez(os.path.join(os.environ["B2S_OUT"], "rank%d.npz" % rank), hit=hit, miss=miss, pm=pm, T=allT.cpu().numpy())
+bdist.barrier()
+torch.distributed.destroy_process_group()
+'''
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
+def test_two_gpu_grid_merge_and_icp_sharding(tmp_path):
+    world = 2
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, B2S_ROOT=ROOT, B2S_OUT=str(tmp_path))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", "29733", str(script)]
+    subprocess.run(cmd, check=True, env=env, timeout=600)
+    from oracle import corc
+    import b2slam.synth as synth
+    G = 2048
+    S, Hx, Hy = 20.0, G * 0.05 / 2.0, G * 0.05 / 2.0
+    oh = np.zeros((G, G), dtype=np.int32)
+    om = np.zeros((G, G), dtype=np.int32)
+    for rnd in range(2):
+        for s in range(2 * world):
+            ox, oy, cx, cy = synth.grid_scans(5001 + s + 100 * rnd, 24, 1080, half_extent_m=40.0)
+            corc.grid_raycast(oh, om, S, Hx, Hy, ox, oy, cx, cy)
+    xy, _ = synth.room_sequence(9001, 41, 360)
+    want_T, _ = corc.icp_batch(xy[:-1], xy[1:], 30, 1e-3)
+    for r in range(world):
+        z = np.load(tmp_path / ("rank%d.npz" % r))
+        assert np.array_equal(z["hit"], oh) and np.array_equal(z["miss"], om)   # bit-identical to one pass
+        assert np.array_equal(z["pm"], corc.grid_finalize(oh, om)[1])
+        np.testing.assert_allclose(z["T"], want_T, rtol=0, atol=1e-9)
