@@ -33,6 +33,10 @@ inline int cuda_fail(cudaError_t e, const char *what)
 
 int sm_count();
 
+int grid_raycast_signed(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m, double off_x,
+                        double off_y, const float *ox, const float *oy, const float *cx, const float *cy,
+                        int scans, int beams, int32_t *counters, void *workspace, int sign, void *stream);
+
 // ---------------------------------------------------------------- warp / block reductions
 
 __device__ __forceinline__ double warp_sum(double v)

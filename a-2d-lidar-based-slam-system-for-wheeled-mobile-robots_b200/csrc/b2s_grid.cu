@@ -322,7 +322,7 @@ struct GridWorkspace {      // lives at the front of the caller-provided workspa
 // base pointer) come out of one add; SHFL's own in-range predicate marks lane 0 as a run head;
 // the run length is ffs of the head mask funnel-shifted past this lane with a sentinel at lane 32;
 // the RED is predicated, not branched.
-template <bool GUARD_START>
+template <bool GUARD_START, int SIGN>
 __device__ __forceinline__ void march_step4(int t, int delay, double slope, double &acc, unsigned &cmaj2, int &minor2,
                                             unsigned pitch2, int inc2, unsigned wmin2, int t_em, unsigned em_len,
                                             unsigned dead_key, unsigned lane1, unsigned long long plane_base)
@@ -356,7 +356,7 @@ __device__ __forceinline__ void march_step4(int t, int delay, double slope, doub
     const bool head = !in_range || (key != left);
     const unsigned heads = __ballot_sync(0xffffffffu, head);
     // heads of the lanes after this one, with a sentinel head at virtual lane 32
-    const int run = __ffs(__funnelshift_rc(heads, 1u, lane1));
+    const int run = SIGN * __ffs(__funnelshift_rc(heads, 1u, lane1));
     // byte offset of the int32 cell = (key >> 1) * 4 = key * 2 - 2 * (plane bit); the latter is folded into plane_base
     const unsigned long long addr = plane_base + (unsigned long long)key * 2ull;
     asm volatile(
@@ -369,6 +369,8 @@ __device__ __forceinline__ void march_step4(int t, int delay, double slope, doub
         : "memory");
 }
 
+// SIGN = +1 applies a batch, SIGN = -1 takes the same batch back out (exact inverse: integer adds).
+template <int SIGN>
 __global__ void __launch_bounds__(256, 8)
 grid_raycast_v4(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int32_t *__restrict__ scratch_t,
                 GridWorkspace *__restrict__ ws, int xw, int yw, double cells_per_m, double off_x, double off_y,
@@ -385,7 +387,7 @@ grid_raycast_v4(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int32_t *
         const int s = (int)(i / beams);
         st = beam_setup(__ldg(ox + i), __ldg(oy + i), __ldg(cx + s), __ldg(cy + s), xw, yw,
                         cells_per_m, off_x, off_y, b);
-        if (st != BEAM_OK) count_status(st, counters);
+        if (st != BEAM_OK && SIGN > 0) count_status(st, counters);
     }
     const bool live = (st == BEAM_OK);
     const int span = live ? b.span : -1;
@@ -395,7 +397,7 @@ grid_raycast_v4(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int32_t *
     if (tmax < 0) return;
 
     if (live && (unsigned)b.hx < (unsigned)xw && (unsigned)b.hy < (unsigned)yw)
-        atomicAdd(hit + (b.hx * yw + b.hy), 1);
+        atomicAdd(hit + (b.hx * yw + b.hy), SIGN);
 
     // bounding box of what the y-major beams of this warp can touch in the scratch plane
     const bool steep_live = live && b.steep;
@@ -451,11 +453,11 @@ grid_raycast_v4(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int32_t *
 
     int t = 0;
     for (; t < dmax; ++t)
-        march_step4<true>(t, delay, slope, acc, cmaj2, minor2, pitch2, inc2, wmin2, t_em, em_len, dead_key, lane1,
+        march_step4<true, SIGN>(t, delay, slope, acc, cmaj2, minor2, pitch2, inc2, wmin2, t_em, em_len, dead_key, lane1,
                           plane_base);
 #pragma unroll 4
     for (; t <= tmax; ++t)
-        march_step4<false>(t, delay, slope, acc, cmaj2, minor2, pitch2, inc2, wmin2, t_em, em_len, dead_key, lane1,
+        march_step4<false, SIGN>(t, delay, slope, acc, cmaj2, minor2, pitch2, inc2, wmin2, t_em, em_len, dead_key, lane1,
                            plane_base);
 }
 
@@ -661,15 +663,13 @@ extern "C" int b2s_grid_workspace_init(void *workspace, int xw, int yw, void *st
     return B2S_OK;
 }
 
-extern "C" int b2s_grid_raycast_ws(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m,
-                                   double off_x, double off_y, const float *ox, const float *oy,
-                                   const float *cx, const float *cy, int scans, int beams,
-                                   int32_t *counters, void *workspace, void *stream)
+namespace b2s {
+// Shared by b2s_grid_raycast_ws (sign +1) and the host layer's roll-back of a rejected batch (sign -1).
+int grid_raycast_signed(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m, double off_x,
+                        double off_y, const float *ox, const float *oy, const float *cx, const float *cy,
+                        int scans, int beams, int32_t *counters, void *workspace, int sign, void *stream)
 {
-    if (workspace == nullptr || g_grid_variant != 4)
-        return b2s_grid_raycast(hit, miss, xw, yw, cells_per_m, off_x, off_y, ox, oy, cx, cy, scans, beams,
-                                counters, stream);
-    B2S_REQUIRE(hit && miss && ox && oy && cx && cy, "b2s_grid_raycast_ws: null pointer");
+    B2S_REQUIRE(hit && miss && ox && oy && cx && cy && workspace, "b2s_grid_raycast_ws: null pointer");
     B2S_REQUIRE(xw > 0 && yw > 0 && (long long)xw * yw < (1ll << 30), "b2s_grid_raycast_ws: grid size");
     B2S_REQUIRE(scans >= 0 && beams >= 0, "b2s_grid_raycast_ws: negative count");
     B2S_REQUIRE(cells_per_m == cells_per_m && off_x == off_x && off_y == off_y, "b2s_grid_raycast_ws: NaN scale");
@@ -682,14 +682,31 @@ extern "C" int b2s_grid_raycast_ws(int32_t *hit, int32_t *miss, int xw, int yw, 
     cudaStream_t st = (cudaStream_t)stream;
     GridWorkspace *ws = (GridWorkspace *)workspace;
     int32_t *scratch_t = (int32_t *)((char *)workspace + sizeof(GridWorkspace));
-    grid_raycast_v4<<<(unsigned)blocks, threads, 0, st>>>(hit, miss, scratch_t, ws, xw, yw, cells_per_m, off_x,
-                                                          off_y, ox, oy, cx, cy, total, beams, counters);
+    if (sign >= 0)
+        grid_raycast_v4<1><<<(unsigned)blocks, threads, 0, st>>>(hit, miss, scratch_t, ws, xw, yw, cells_per_m, off_x,
+                                                                 off_y, ox, oy, cx, cy, total, beams, counters);
+    else
+        grid_raycast_v4<-1><<<(unsigned)blocks, threads, 0, st>>>(hit, miss, scratch_t, ws, xw, yw, cells_per_m,
+                                                                  off_x, off_y, ox, oy, cx, cy, total, beams, counters);
     B2S_CUDA(cudaGetLastError());
     dim3 fgrid((xw + 31) / 32, (yw + 31) / 32);
     grid_fold_kernel<<<fgrid, 256, 0, st>>>(miss, scratch_t, ws, xw, yw);
     B2S_CUDA(cudaGetLastError());
     B2S_CUDA(cudaMemsetAsync(ws, 0x80, sizeof(GridWorkspace), st));
     return B2S_OK;
+}
+}  // namespace b2s
+
+extern "C" int b2s_grid_raycast_ws(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m,
+                                   double off_x, double off_y, const float *ox, const float *oy,
+                                   const float *cx, const float *cy, int scans, int beams,
+                                   int32_t *counters, void *workspace, void *stream)
+{
+    if (workspace == nullptr || g_grid_variant != 4)
+        return b2s_grid_raycast(hit, miss, xw, yw, cells_per_m, off_x, off_y, ox, oy, cx, cy, scans, beams,
+                                counters, stream);
+    return grid_raycast_signed(hit, miss, xw, yw, cells_per_m, off_x, off_y, ox, oy, cx, cy, scans, beams,
+                               counters, workspace, +1, stream);
 }
 
 extern "C" int b2s_grid_validate(const float *ox, const float *oy, const float *cx, const float *cy,

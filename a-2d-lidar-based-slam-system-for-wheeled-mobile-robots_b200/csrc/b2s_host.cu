@@ -96,7 +96,8 @@ struct b2s_mapping {
     int xw, yw;
     double xyreso, cells_per_m, off_x, off_y;
     double w_hit, w_miss, thresh;
-    cudaStream_t stream;
+    cudaStream_t stream, copy_stream;
+    cudaEvent_t chunk_ready[8], inputs_free;
     int32_t *hit, *miss;
     int32_t *counters;
     void *workspace;
@@ -314,16 +315,22 @@ extern "C" int b2s_mapping_create(b2s_mapping **out, int xw, int yw, double xyre
     m->thresh = thresh;
     m->hit = m->miss = m->counters = nullptr;
     m->workspace = nullptr;
+    m->stream = m->copy_stream = nullptr;
+    for (int k = 0; k < 8; ++k) m->chunk_ready[k] = nullptr;
+    m->inputs_free = nullptr;
     const size_t plane = (size_t)xw * yw * sizeof(int32_t);
     cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 8 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&m->chunk_ready[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->inputs_free, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->hit, plane);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->miss, plane);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&m->counters, B2S_CNT_WORDS * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&m->counters, 2 * B2S_CNT_WORDS * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&m->workspace, b2s_grid_workspace_bytes(xw, yw));
     if (e == cudaSuccess && b2s_grid_workspace_init(m->workspace, xw, yw, m->stream) != B2S_OK) e = cudaErrorUnknown;
     if (e == cudaSuccess) e = cudaMemsetAsync(m->hit, 0, plane, m->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(m->miss, 0, plane, m->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(m->counters, 0, B2S_CNT_WORDS * sizeof(int32_t), m->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->counters, 0, 2 * B2S_CNT_WORDS * sizeof(int32_t), m->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
     if (e != cudaSuccess) {
         int rc = cuda_fail(e, "b2s_mapping_create");
@@ -344,6 +351,10 @@ extern "C" int b2s_mapping_destroy(b2s_mapping *m)
     if (m->counters) cudaFree(m->counters);
     if (m->workspace) cudaFree(m->workspace);
     m->d_in.release(); m->d_datamap.release(); m->d_pmap.release();
+    for (int k = 0; k < 8; ++k)
+        if (m->chunk_ready[k]) cudaEventDestroy(m->chunk_ready[k]);
+    if (m->inputs_free) cudaEventDestroy(m->inputs_free);
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
     return B2S_OK;
@@ -368,6 +379,9 @@ extern "C" int b2s_mapping_update(b2s_mapping *m, const float *ox, const float *
     DeviceGuard g(m->device);
     const size_t total = (size_t)scans * beams;
     int rc;
+    int nchunk = 0;
+    float *d_ox = nullptr, *d_oy = nullptr, *d_cx = nullptr, *d_cy = nullptr;
+    int lo[9];
     if (total > 0) {
         B2S_REQUIRE(ox && oy && cx && cy, "b2s_mapping_update: null pointer");
         const size_t pts = total * sizeof(float), ctr = (size_t)scans * sizeof(float);
@@ -375,28 +389,47 @@ extern "C" int b2s_mapping_update(b2s_mapping *m, const float *ox, const float *
         const size_t a_pts = (pts + 15) & ~(size_t)15, a_ctr = (ctr + 15) & ~(size_t)15;
         if ((rc = m->d_in.reserve(2 * a_pts + 2 * a_ctr))) return rc;
         char *base = (char *)m->d_in.p;
-        float *d_ox = (float *)base, *d_oy = (float *)(base + a_pts);
-        float *d_cx = (float *)(base + 2 * a_pts), *d_cy = (float *)(base + 2 * a_pts + a_ctr);
-        B2S_CUDA(cudaMemsetAsync(m->counters, 0, B2S_CNT_WORDS * sizeof(int32_t), m->stream));
-        B2S_CUDA(cudaMemcpyAsync(d_ox, ox, pts, cudaMemcpyHostToDevice, m->stream));
-        B2S_CUDA(cudaMemcpyAsync(d_oy, oy, pts, cudaMemcpyHostToDevice, m->stream));
-        B2S_CUDA(cudaMemcpyAsync(d_cx, cx, ctr, cudaMemcpyHostToDevice, m->stream));
-        B2S_CUDA(cudaMemcpyAsync(d_cy, cy, ctr, cudaMemcpyHostToDevice, m->stream));
-        // screen the whole batch on the device BEFORE any beam is applied: the reference raises
-        // (ValueError on NaN, OverflowError on inf) where int() meets such a value, [MAP]:33-36
-        int32_t flags[2] = {0, 0};
-        if ((rc = b2s_grid_validate(d_ox, d_oy, d_cx, d_cy, scans, beams, m->counters + 2, m->stream))) return rc;
-        B2S_CUDA(cudaMemcpyAsync(flags, m->counters + 2, sizeof(flags), cudaMemcpyDeviceToHost, m->stream));
-        B2S_CUDA(cudaStreamSynchronize(m->stream));
-        if (flags[0] || flags[1]) {
-            set_error(flags[0] ? "cannot convert float NaN to integer" : "cannot convert float infinity to integer");
-            return B2S_ERR_NONFINITE;
+        d_ox = (float *)base;
+        d_oy = (float *)(base + a_pts);
+        d_cx = (float *)(base + 2 * a_pts);
+        d_cy = (float *)(base + 2 * a_pts + a_ctr);
+        // counters[0..3]: the ray-cast kernel's own (B2S_CNT_*); counters[4], [5]: NaN / inf seen by the screening
+        B2S_CUDA(cudaMemsetAsync(m->counters, 0, 2 * B2S_CNT_WORDS * sizeof(int32_t), m->stream));
+        // Pipeline: the batch is cut into up to 8 chunks of scans; chunk k+1 crosses PCIe on the copy
+        // stream while chunk k is screened and ray-cast on the compute stream.
+        nchunk = (int)((total + (1u << 21) - 1) >> 21);  // ~2M beams (16 MB of endpoints) per chunk
+        if (nchunk > 8) nchunk = 8;
+        if (nchunk > scans) nchunk = scans;
+        if (nchunk < 1) nchunk = 1;
+        for (int k = 0; k <= nchunk; ++k) lo[k] = (int)((long long)scans * k / nchunk);
+        for (int k = 0; k < nchunk; ++k) {
+            const size_t s0 = (size_t)lo[k], ns = (size_t)(lo[k + 1] - lo[k]);
+            cudaStream_t cs = m->copy_stream;
+            B2S_CUDA(cudaMemcpyAsync(d_ox + s0 * beams, ox + s0 * beams, ns * beams * sizeof(float), cudaMemcpyHostToDevice, cs));
+            B2S_CUDA(cudaMemcpyAsync(d_oy + s0 * beams, oy + s0 * beams, ns * beams * sizeof(float), cudaMemcpyHostToDevice, cs));
+            B2S_CUDA(cudaMemcpyAsync(d_cx + s0, cx + s0, ns * sizeof(float), cudaMemcpyHostToDevice, cs));
+            B2S_CUDA(cudaMemcpyAsync(d_cy + s0, cy + s0, ns * sizeof(float), cudaMemcpyHostToDevice, cs));
+            B2S_CUDA(cudaEventRecord(m->chunk_ready[k], cs));
         }
-        B2S_CUDA(cudaMemsetAsync(m->counters, 0, B2S_CNT_WORDS * sizeof(int32_t), m->stream));
-        rc = b2s_grid_raycast_ws(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y, d_ox, d_oy,
-                                 d_cx, d_cy, scans, beams, m->counters, m->workspace, m->stream);
-        if (rc) return rc;
+        for (int k = 0; k < nchunk; ++k) {
+            const size_t s0 = (size_t)lo[k];
+            const int ns = lo[k + 1] - lo[k];
+            B2S_CUDA(cudaStreamWaitEvent(m->stream, m->chunk_ready[k], 0));
+            // screening like the reference's int() ([MAP]:33-36): flags accumulate over the chunks
+            if ((rc = b2s_grid_validate(d_ox + s0 * beams, d_oy + s0 * beams, d_cx + s0, d_cy + s0, ns, beams,
+                                        m->counters + B2S_CNT_WORDS, m->stream)))
+                return rc;
+            // beams the screening flags are skipped by the kernel itself, so applying a chunk before the
+            // verdict on the whole batch is known is safe: a rejected batch is taken back out below
+            rc = grid_raycast_signed(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y,
+                                     d_ox + s0 * beams, d_oy + s0 * beams, d_cx + s0, d_cy + s0, ns, beams,
+                                     m->counters, m->workspace, +1, m->stream);
+            if (rc) return rc;
+        }
     }
+    int32_t cnt[2 * B2S_CNT_WORDS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (total > 0)
+        B2S_CUDA(cudaMemcpyAsync(cnt, m->counters, sizeof(cnt), cudaMemcpyDeviceToHost, m->stream));
     if (pmap_out) {
         const size_t cells = (size_t)m->xw * m->yw;
         if ((rc = m->d_pmap.reserve(cells))) return rc;
@@ -405,12 +438,30 @@ extern "C" int b2s_mapping_update(b2s_mapping *m, const float *ox, const float *
         if (rc) return rc;
         B2S_CUDA(cudaMemcpyAsync(pmap_out, m->d_pmap.p, cells, cudaMemcpyDeviceToHost, m->stream));
     }
-    int32_t cnt[B2S_CNT_WORDS] = {0, 0, 0, 0};
-    if (total > 0)
-        B2S_CUDA(cudaMemcpyAsync(cnt, m->counters, sizeof(cnt), cudaMemcpyDeviceToHost, m->stream));
     B2S_CUDA(cudaStreamSynchronize(m->stream));
-    if (cnt[B2S_CNT_TOO_LONG] > 0) {
-        set_error("%d beam(s) longer than %d cells were dropped", cnt[B2S_CNT_TOO_LONG], B2S_MAX_PATH_CELLS);
+    const int saw_nan = cnt[B2S_CNT_WORDS], saw_inf = cnt[B2S_CNT_WORDS + 1];
+    if (saw_nan || saw_inf || cnt[B2S_CNT_TOO_LONG] > 0) {
+        // all-or-nothing like a Python exception before the loop: take the whole batch back out
+        for (int k = 0; k < nchunk; ++k) {
+            const size_t s0 = (size_t)lo[k];
+            rc = grid_raycast_signed(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y,
+                                     d_ox + s0 * beams, d_oy + s0 * beams, d_cx + s0, d_cy + s0, lo[k + 1] - lo[k],
+                                     beams, nullptr, m->workspace, -1, m->stream);
+            if (rc) return rc;
+        }
+        if (pmap_out) {
+            const size_t cells = (size_t)m->xw * m->yw;
+            rc = b2s_grid_finalize(m->hit, m->miss, m->xw, m->yw, m->w_hit, m->w_miss, m->thresh, nullptr,
+                                   (int8_t *)m->d_pmap.p, m->stream);
+            if (rc) return rc;
+            B2S_CUDA(cudaMemcpyAsync(pmap_out, m->d_pmap.p, cells, cudaMemcpyDeviceToHost, m->stream));
+        }
+        B2S_CUDA(cudaStreamSynchronize(m->stream));
+        if (saw_nan || saw_inf) {
+            set_error(saw_nan ? "cannot convert float NaN to integer" : "cannot convert float infinity to integer");
+            return B2S_ERR_NONFINITE;
+        }
+        set_error("%d beam(s) longer than %d cells: batch rejected", cnt[B2S_CNT_TOO_LONG], B2S_MAX_PATH_CELLS);
         return B2S_ERR_TOO_LONG;
     }
     return B2S_OK;

@@ -106,6 +106,36 @@ def test_mapping_edge_cases(env):
     assert (m.counts()[1] == 0).all() and (m.pmap == 50).all()
 
 
+def test_rejected_batch_is_rolled_back_exactly(env):
+    """A batch with a NaN deep inside is applied chunk by chunk while it streams in; the error must
+    leave the counts exactly as they were (the kernel takes the chunks back out with sign -1)."""
+    G = 1024
+    ox, oy, cx, cy = env.synth.grid_scans(77, 6000, 1080, half_extent_m=20.0)   # > 2 chunks
+    m = env.b2slam.Mapping(G, G, 0.05)
+    m.update_batch(ox[:500], oy[:500], cx[:500], cy[:500])
+    h0, m0 = m.counts()
+    bad = oy.copy()
+    bad[5500, 17] = np.nan
+    with pytest.raises(ValueError):
+        m.update_batch(ox, bad, cx, cy)
+    h1, m1 = m.counts()
+    assert np.array_equal(h0, h1) and np.array_equal(m0, m1)
+    bad[5500, 17] = np.inf
+    with pytest.raises(OverflowError):
+        m.update_batch(ox, bad, cx, cy)
+    h1, m1 = m.counts()
+    assert np.array_equal(h0, h1) and np.array_equal(m0, m1)
+    pm = m.update_batch(ox, oy, cx, cy)                                       # and the good batch lands
+    oh = np.zeros((G, G), dtype=np.int32)
+    om = np.zeros((G, G), dtype=np.int32)
+    S, Hx, Hy = env.dev.grid_scale(G, G, 0.05)
+    env.corc.grid_raycast(oh, om, S, Hx, Hy, ox[:500], oy[:500], cx[:500], cy[:500])
+    env.corc.grid_raycast(oh, om, S, Hx, Hy, ox, oy, cx, cy)
+    h2, m2 = m.counts()
+    assert np.array_equal(h2, oh) and np.array_equal(m2, om)
+    assert np.array_equal(pm, env.corc.grid_finalize(oh, om)[1])
+
+
 def test_mapping_threshold_stream(env):
     """1000 traversals stay free, the 1001st flips the cell (reference golden, [MAP]:47)."""
     z = load_golden("mapping.npz")
