@@ -44,6 +44,12 @@ SIGNATURES = {
     "b2s_grid_pack_ros": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "b2s_bresenham_paths": (_i32, [_vp, _i32, _vp, _vp, _vp]),
     "b2s_grid_allreduce": (_i32, [_vp, _vp, _sz, _vp, _vp]),
+    "b2s_grid_merge_p2p": (_i32, [_vp, _vp, _vp, _i32, _sz, _sz, _vp, _vp, _dbl, _dbl, _dbl, _vp]),
+    "b2s_device_alloc": (_i32, [_pp, _sz]),
+    "b2s_device_free": (_i32, [_vp]),
+    "b2s_ipc_export": (_i32, [_vp, _vp]),
+    "b2s_ipc_open": (_i32, [_vp, _pp]),
+    "b2s_ipc_close": (_i32, [_vp]),
     "b2s_nccl_unique_id": (_i32, [_vp]),
     "b2s_nccl_comm_init": (_i32, [_pp, _i32, _i32, _vp]),
     "b2s_nccl_comm_destroy": (_i32, [_vp]),

@@ -18,6 +18,23 @@ def _chk(t, dtype, name):
     return t.data_ptr()
 
 
+class _CudaView(object):
+    """Minimal __cuda_array_interface__ carrier for memory torch did not allocate."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+_TYPESTR = {torch.int32: "<i4", torch.int8: "|i1", torch.float32: "<f4", torch.float64: "<f8", torch.uint8: "|u1"}
+
+
+def tensor_from_ptr(ptr, shape, dtype, device=None):
+    """A torch view of device memory owned by someone else (b2s_device_alloc, a peer's IPC mapping)."""
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    return torch.as_tensor(_CudaView(ptr, shape, _TYPESTR[dtype]), device=dev)
+
+
 def grid_scale(xw, yw, xyreso):
     """(cells_per_m, off_x, off_y) exactly as b2s_mapping_create derives them."""
     return 1.0 / xyreso, xw * xyreso / 2.0, yw * xyreso / 2.0

@@ -131,3 +131,140 @@ class ShardedMapping(object):
 
     def counts(self):
         return self.hit.cpu().numpy(), self.miss.cpu().numpy()
+
+
+class ShardedMappingP2P(object):
+    """ShardedMapping with the merge fused over NVLink peer memory (b2s_grid_merge_p2p).
+
+    Every rank ray-casts its scans into private int32 delta planes that its peers can read (CUDA
+    IPC).  One kernel per rank then sums its shard of all ranks' deltas, adds the sums into its
+    shard of the global counts, finalizes that shard and stores the int8 occupancy into every rank's
+    map -- reduce-scatter, finalize and all-gather in one pass.  The global counts stay sharded
+    (1/world of the grid per rank); every rank holds the full occupancy map.  Two one-element
+    all-reduces on the same stream fence the kernel against the peers' ray-casts and map writes.
+    """
+
+    def __init__(self, xw, yw, xyreso, hit_weight=20.0, miss_weight=0.01, occ_threshold=10.0):
+        import ctypes
+        from b2slam import _lib, devapi
+        self._lib, self._dev, self._ct = _lib, devapi, ctypes
+        self.xw, self.yw = int(xw), int(yw)
+        self.cells = self.xw * self.yw
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.scale = devapi.grid_scale(self.xw, self.yw, float(xyreso))
+        self.weights = (float(hit_weight), float(miss_weight), float(occ_threshold))
+        blocks = self.cells // 4096
+        if blocks * 4096 != self.cells:
+            raise ValueError("ShardedMappingP2P needs xw*yw to be a multiple of 4096 cells")
+        lo, hi = shard_bounds(blocks, self.rank, self.world)
+        self.cell_lo, self.cell_hi = lo * 4096, hi * 4096
+        L = _lib.lib()
+        self._own = []
+        ptrs = []
+        for nbytes in (self.cells * 4, self.cells * 4, self.cells):
+            p = ctypes.c_void_p()
+            _lib.check(L.b2s_device_alloc(ctypes.byref(p), nbytes))
+            self._own.append(p.value)
+            ptrs.append(p.value)
+        self.d_hit = devapi.tensor_from_ptr(ptrs[0], (self.xw, self.yw), torch.int32)
+        self.d_miss = devapi.tensor_from_ptr(ptrs[1], (self.xw, self.yw), torch.int32)
+        self.pmap_dev = devapi.tensor_from_ptr(ptrs[2], (self.xw, self.yw), torch.int8)
+        self.d_hit.zero_()
+        self.d_miss.zero_()
+        self.pmap_dev.fill_(50)
+        handles = []
+        for p in ptrs:
+            buf = ctypes.create_string_buffer(64)
+            _lib.check(L.b2s_ipc_export(ctypes.c_void_p(p), buf))
+            handles.append(buf.raw)
+        everyone = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(everyone, handles)
+        else:
+            everyone[0] = handles
+        self._opened = []
+        table = [[0] * self.world for _ in range(3)]
+        for r in range(self.world):
+            for k in range(3):
+                if r == self.rank:
+                    table[k][r] = ptrs[k]
+                else:
+                    q = ctypes.c_void_p()
+                    _lib.check(L.b2s_ipc_open(ctypes.create_string_buffer(everyone[r][k], 64), ctypes.byref(q)))
+                    self._opened.append(q.value)
+                    table[k][r] = q.value
+        arr = ctypes.c_void_p * self.world
+        self._hit_ptrs, self._miss_ptrs, self._pmap_ptrs = (arr(*table[k]) for k in range(3))
+        n = self.cell_hi - self.cell_lo
+        self.g_hit = torch.zeros(max(n, 4096), dtype=torch.int32, device="cuda")
+        self.g_miss = torch.zeros(max(n, 4096), dtype=torch.int32, device="cuda")
+        self.workspace = devapi.new_workspace(self.xw, self.yw)
+        self.pmap_host = torch.empty((self.xw, self.yw), dtype=torch.int8).pin_memory()
+        self._token = torch.zeros(1, dtype=torch.int32, device="cuda")
+        self._in = None
+        torch.cuda.synchronize()
+        barrier()
+
+    def _fence(self):
+        if self.world > 1:
+            dist.all_reduce(self._token)  # stream-ordered: completes only when every rank got here
+
+    def update_device(self, ox, oy, cx, cy, events=None):
+        """Scans already on the device (float32 CUDA tensors).  Leaves the merged map in pmap_dev.
+        `events`: optional (start, stop) torch.cuda.Event pair recorded around the ray-cast."""
+        self.d_hit.zero_()
+        self.d_miss.zero_()
+        S, Hx, Hy = self.scale
+        if events:
+            events[0].record()
+        self._dev.grid_raycast(self.d_hit, self.d_miss, S, Hx, Hy, ox, oy, cx, cy, workspace=self.workspace)
+        if events:
+            events[1].record()
+        self._fence()
+        w_hit, w_miss, thr = self.weights
+        self._lib.check(self._lib.lib().b2s_grid_merge_p2p(
+            self._hit_ptrs, self._miss_ptrs, self._pmap_ptrs, self.world, self.cell_lo, self.cell_hi,
+            self.g_hit.data_ptr(), self.g_miss.data_ptr(), w_hit, w_miss, thr,
+            torch.cuda.current_stream().cuda_stream))
+        self._fence()
+
+    def update_batch(self, ox, oy, cx, cy):
+        """ox, oy (K,N), cx, cy (K,) float32 host arrays -> merged int8 occupancy (host, pinned)."""
+        host = [torch.from_numpy(a) if not isinstance(a, torch.Tensor) else a for a in (ox, oy, cx, cy)]
+        if self._in is None or self._in[0].shape != host[0].shape:
+            self._in = [torch.empty(h.shape, dtype=torch.float32, device="cuda") for h in host]
+        for d, h in zip(self._in, host):
+            d.copy_(h, non_blocking=True)
+        self.update_device(*self._in)
+        self.pmap_host.copy_(self.pmap_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.pmap_host.numpy()
+
+    def counts(self):
+        """Full (hit, miss) planes assembled from the ranks' shards (for checks; not a hot path)."""
+        n = self.cell_hi - self.cell_lo
+        parts_h = [None] * self.world
+        parts_m = [None] * self.world
+        mine = (self.g_hit[:n].cpu().numpy(), self.g_miss[:n].cpu().numpy())
+        if self.world > 1:
+            dist.all_gather_object(parts_h, mine[0])
+            dist.all_gather_object(parts_m, mine[1])
+        else:
+            parts_h[0], parts_m[0] = mine
+        import numpy as np
+        return (np.concatenate(parts_h).reshape(self.xw, self.yw),
+                np.concatenate(parts_m).reshape(self.xw, self.yw))
+
+    def close(self):
+        torch.cuda.synchronize()
+        barrier()
+        L = self._lib.lib()
+        for p in self._opened:
+            L.b2s_ipc_close(self._ct.c_void_p(p))
+        self._opened = []
+        barrier()
+        self.d_hit = self.d_miss = self.pmap_dev = None
+        for p in self._own:
+            L.b2s_device_free(self._ct.c_void_p(p))
+        self._own = []

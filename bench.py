@@ -250,7 +250,12 @@ def bench_grid(args, rank, world, torch, devapi, bdist, synth):
     pmap = torch.empty((G, G), dtype=torch.int8, device="cuda")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
+    p2p = bdist.ShardedMappingP2P(G, G, GRID_RESO) if (world > 1 and args.merge == "p2p") else None
+
     def step(ev=None):
+        if p2p is not None:  # ray-cast, then ONE peer-memory kernel: reduce-scatter + finalize + all-gather
+            p2p.update_device(ox, oy, cx, cy, events=ev)
+            return
         hit.zero_()
         miss.zero_()
         if ev:
@@ -303,7 +308,7 @@ def bench_grid(args, rank, world, torch, devapi, bdist, synth):
             m.reset()
             m.update_batch(h_ox, h_oy, h_cx, h_cy, want_pmap=True)
     else:
-        sm = bdist.ShardedMapping(G, G, GRID_RESO)
+        sm = p2p if p2p is not None else bdist.ShardedMapping(G, G, GRID_RESO)
 
         def e2e_step():
             sm.update_batch(h_ox, h_oy, h_cx, h_cy)
@@ -319,6 +324,8 @@ def bench_grid(args, rank, world, torch, devapi, bdist, synth):
 
     peak, peak_src = measured_peaks()
     achieved = algo_bytes / (ray_avg_ms * 1e-3) / 1e9
+    if p2p is not None:
+        p2p.close()
     res = {
         "metric": "grid_beam_updates_per_s", "unit": "beams/s",
         "value": world * K * N * args.steps / (total_ms * 1e-3),
@@ -328,8 +335,10 @@ def bench_grid(args, rank, world, torch, devapi, bdist, synth):
                    "hit_weight": 20.0, "cell_visits_per_step_per_gpu": visits,
                    "l2": "working set %.0f MB per step > L2 and a 256 MB buffer is rewritten between timed steps"
                          % ((2 * G * G * 4 + 8 * K * N) / 1e6),
-                   "parallelism": "scan streams sharded by rank, int32 count deltas all-reduced (NCCL)" if world > 1
-                   else "single GPU"},
+                   "parallelism": ("single GPU" if world == 1 else
+                                   "scan streams sharded by rank; count deltas merged by one peer-memory kernel "
+                                   "(reduce-scatter + finalize + all-gather over NVLink)" if p2p is not None else
+                                   "scan streams sharded by rank, int32 count deltas all-reduced (NCCL)")},
         "dtype": "int32 counts / f64 cell+error arithmetic",
         "roofline": {"bound": "hbm", "kernel": "grid_raycast (+ fold of the transposed scratch plane)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -337,9 +346,10 @@ def bench_grid(args, rank, world, torch, devapi, bdist, synth):
                      "cell_visits_per_s": visits / (ray_avg_ms * 1e-3)},
         "e2e": {"value": world * K * N * e2e_steps / e2e_s, "unit": "beams/s",
                 "h2d_bytes_per_step": 8 * K * N + 8 * K, "d2h_bytes_per_step": G * G,
-                "api": "Mapping.update_batch (b2s_mapping_update)" if world == 1 else "dist.ShardedMapping.update_batch",
+                "api": ("Mapping.update_batch (b2s_mapping_update)" if world == 1 else
+                        "dist.ShardedMappingP2P.update_batch" if p2p is not None else "dist.ShardedMapping.update_batch"),
                 "ms_per_step": e2e_s / e2e_steps * 1e3},
-        "gpu_launches": 3 * args.steps,
+        "gpu_launches": (3 if world == 1 or p2p is not None else 3) * args.steps,
         "clocks": clocks,
     }
     return res
@@ -448,6 +458,7 @@ def main():
     ap.add_argument("--icp-scans", type=int, default=ICP_SCANS)
     ap.add_argument("--grid-variant", type=int, default=0)
     ap.add_argument("--icp-r", type=int, default=0, help="force ICP source points per thread (tuning)")
+    ap.add_argument("--merge", default="p2p", choices=["p2p", "nccl"], help="multi-GPU grid merge")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only", default="both", choices=["both", "primary"])
     args = ap.parse_args()
@@ -456,6 +467,8 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # keep stdout to the one JSON line: NCCL's version / debug banner goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     from b2slam import _lib, devapi, synth
     from b2slam import dist as bdist

@@ -126,6 +126,26 @@ int b2s_bresenham_paths(const int32_t *segs, int count, const int64_t *offsets, 
  * In-place ncclAllReduce(int32, sum) of both planes on an existing communicator. */
 int b2s_grid_allreduce(int32_t *hit, int32_t *miss, size_t cells, void *nccl_comm, void *stream);
 
+/* Fused merge over NVLink peer memory (one process per GPU; no reference counterpart): ONE kernel
+ * reduce-scatters the ranks' delta planes (this rank sums cells [cell_lo, cell_hi) of every rank's
+ * delta_hit / delta_miss -- its own pointer for itself, CUDA-IPC-mapped pointers for the peers), adds
+ * the sums into its shard of the global counts (global_*_shard, int32 [cell_hi - cell_lo]), applies the
+ * evidence rule of [MAP]:42-50 and all-gathers the int8 occupancy by storing its shard into every
+ * rank's full map pmap[r].  Shard bounds are multiples of 4096 cells.  The caller orders the launch
+ * after every rank's ray-cast and fences the maps afterwards (dist.ShardedMappingP2P uses two tiny
+ * stream-ordered all-reduces). */
+int b2s_grid_merge_p2p(const int32_t *const *delta_hit, const int32_t *const *delta_miss,
+                       int8_t *const *pmap, int nranks, size_t cell_lo, size_t cell_hi,
+                       int32_t *global_hit_shard, int32_t *global_miss_shard, double w_hit,
+                       double w_miss, double thresh, void *stream);
+
+/* cudaMalloc'ed (IPC-exportable) device memory and CUDA IPC handles (64 bytes) for the peer mapping. */
+int b2s_device_alloc(void **out, size_t bytes);
+int b2s_device_free(void *p);
+int b2s_ipc_export(const void *dev_ptr, void *handle64);
+int b2s_ipc_open(const void *handle64, void **dev_ptr_out);
+int b2s_ipc_close(void *dev_ptr);
+
 /* NCCL plumbing for callers that do not bring their own communicator. */
 int b2s_nccl_unique_id(void *id128);
 int b2s_nccl_comm_init(void **comm_out, int nranks, int rank, const void *id128);

@@ -30,6 +30,13 @@ for rnd in range(2):
     ox, oy, cx, cy = (np.concatenate([p[k] for p in parts]) for k in range(4))
     pm = sm.update_batch(ox, oy, cx, cy)
 hit, miss = sm.counts()
+p2p = bdist.ShardedMappingP2P(G, G, 0.05)
+for rnd in range(2):
+    parts = [synth.grid_scans(5001 + s + 100 * rnd, 24, 1080, half_extent_m=40.0) for s in range(lo, hi)]
+    ox, oy, cx, cy = (np.concatenate([p[k] for p in parts]) for k in range(4))
+    pm2 = p2p.update_batch(ox, oy, cx, cy).copy()
+hit2, miss2 = p2p.counts()
+p2p.close()
 xy, _ = synth.room_sequence(9001, 41, 360)
 plo, phi = bdist.sequence_pair_bounds(41, rank, world)
 tar = torch.from_numpy(np.ascontiguousarray(xy[plo:phi])).cuda()
@@ -38,7 +45,8 @@ T, it = devapi.icp_batch(tar, src)
 counts = [b - a for a, b in (bdist.sequence_pair_bounds(41, q, world) for q in range(world))]
 allT = bdist.gather_transforms(T, counts)
 torch.cuda.synchronize()
-np.savez(os.path.join(os.environ["B2S_OUT"], "rank%d.npz" % rank), hit=hit, miss=miss, pm=pm, T=allT.cpu().numpy())
+np.savez(os.path.join(os.environ["B2S_OUT"], "rank%d.npz" % rank), hit=hit, miss=miss, pm=pm, T=allT.cpu().numpy(),
+         hit2=hit2, miss2=miss2, pm2=pm2)
 bdist.barrier()
 torch.distributed.destroy_process_group()
 '''
@@ -69,4 +77,26 @@ def test_two_gpu_grid_merge_and_icp_sharding(tmp_path):
         z = np.load(tmp_path / ("rank%d.npz" % r))
         assert np.array_equal(z["hit"], oh) and np.array_equal(z["miss"], om)   # bit-identical to one pass
         assert np.array_equal(z["pm"], corc.grid_finalize(oh, om)[1])
+        # fused peer-memory merge: same counts (sharded across ranks), same map on every rank
+        assert np.array_equal(z["hit2"], oh) and np.array_equal(z["miss2"], om)
+        assert np.array_equal(z["pm2"], corc.grid_finalize(oh, om)[1])
         np.testing.assert_allclose(z["T"], want_T, rtol=0, atol=1e-9)
+
+
+def test_p2p_merge_single_rank_degenerates_to_finalize():
+    """world = 1: the fused kernel is just accumulate + finalize (no peers), checked against the oracle."""
+    import b2slam.dist as bdist
+    import b2slam.synth as synth
+    from oracle import corc
+    G = 1024
+    sm = bdist.ShardedMappingP2P(G, G, 0.05)
+    oh = np.zeros((G, G), dtype=np.int32)
+    om = np.zeros((G, G), dtype=np.int32)
+    for seed in (1, 2):
+        ox, oy, cx, cy = synth.grid_scans(seed, 40, 360, half_extent_m=15.0)
+        pm = sm.update_batch(ox, oy, cx, cy).copy()
+        corc.grid_raycast(oh, om, 20.0, 25.6, 25.6, ox, oy, cx, cy)
+    h, m = sm.counts()
+    assert np.array_equal(h, oh) and np.array_equal(m, om)
+    assert np.array_equal(pm, corc.grid_finalize(oh, om)[1])
+    sm.close()
