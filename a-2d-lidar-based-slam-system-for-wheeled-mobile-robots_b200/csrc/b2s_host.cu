@@ -36,6 +36,7 @@ int sm_count()
 
 extern int g_grid_variant;
 extern int g_icp_src_per_thread;
+extern int g_icp_prune;
 
 // Growable device / pinned-host staging buffer.
 struct Buf {
@@ -87,7 +88,8 @@ using namespace b2s;
 
 struct b2s_icp {
     int device;
-    cudaStream_t stream;
+    cudaStream_t stream, copy_stream;
+    cudaEvent_t chunk_ready[8];
     Buf d_tar, d_src, d_T, d_iters, d_aux;
 };
 
@@ -139,6 +141,11 @@ extern "C" int b2s_tune(const char *key, int value)
         g_grid_variant = value;
         return B2S_OK;
     }
+    if (strcmp(key, "icp_prune") == 0) {
+        B2S_REQUIRE(value == 0 || value == 1, "b2s_tune: icp_prune must be 0 or 1");
+        g_icp_prune = value;
+        return B2S_OK;
+    }
     if (strcmp(key, "icp_src_per_thread") == 0) {
         B2S_REQUIRE(value == 0 || (value >= 2 && value <= 4), "b2s_tune: icp_src_per_thread must be 0, 2, 3 or 4");
         g_icp_src_per_thread = value;
@@ -186,10 +193,15 @@ extern "C" int b2s_icp_create(b2s_icp **out, int device)
     b2s_icp *c = new (std::nothrow) b2s_icp();
     if (!c) return B2S_ERR_NOMEM;
     c->device = device;
+    c->stream = c->copy_stream = nullptr;
+    for (int k = 0; k < 8; ++k) c->chunk_ready[k] = nullptr;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 8 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&c->chunk_ready[k], cudaEventDisableTiming);
     if (e != cudaSuccess) {
-        delete c;
-        return cuda_fail(e, "cudaStreamCreate");
+        int rc = cuda_fail(e, "b2s_icp_create");
+        b2s_icp_destroy(c);
+        return rc;
     }
     *out = c;
     return B2S_OK;
@@ -199,9 +211,13 @@ extern "C" int b2s_icp_destroy(b2s_icp *c)
 {
     if (!c) return B2S_OK;
     DeviceGuard g(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     c->d_tar.release(); c->d_src.release(); c->d_T.release(); c->d_iters.release(); c->d_aux.release();
-    cudaStreamDestroy(c->stream);
+    for (int k = 0; k < 8; ++k)
+        if (c->chunk_ready[k]) cudaEventDestroy(c->chunk_ready[k]);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return B2S_OK;
 }
@@ -222,15 +238,34 @@ extern "C" int b2s_icp_process(b2s_icp *c, const void *tar_xy, const void *src_x
     if ((rc = c->d_src.reserve(sb))) return rc;
     if ((rc = c->d_T.reserve((size_t)pairs * 9 * sizeof(double)))) return rc;
     if ((rc = c->d_iters.reserve((size_t)pairs * sizeof(int32_t)))) return rc;
-    B2S_CUDA(cudaMemcpyAsync(c->d_tar.p, tar_xy, tb, cudaMemcpyHostToDevice, c->stream));
-    B2S_CUDA(cudaMemcpyAsync(c->d_src.p, src_xy, sb, cudaMemcpyHostToDevice, c->stream));
-    if (is_f64)
-        rc = b2s_icp_batch_f64((const double *)c->d_tar.p, (const double *)c->d_src.p, pairs, n_src, n_tar,
-                               max_iter, tol, (double *)c->d_T.p, (int32_t *)c->d_iters.p, c->stream);
-    else
-        rc = b2s_icp_batch_f32((const float *)c->d_tar.p, (const float *)c->d_src.p, pairs, n_src, n_tar,
-                               max_iter, tol, (double *)c->d_T.p, (int32_t *)c->d_iters.p, c->stream);
-    if (rc) return rc;
+    // Pipeline: up to 8 chunks of pairs; chunk k+1 crosses PCIe on the copy stream while chunk k is solved.
+    int nchunk = (int)((tb + sb + (8u << 20) - 1) / (8u << 20));  // ~8 MB of points per chunk
+    if (nchunk > 8) nchunk = 8;
+    if (nchunk > pairs) nchunk = pairs;
+    if (nchunk < 1) nchunk = 1;
+    const size_t tpair = (size_t)2 * n_tar * el, spair = (size_t)2 * n_src * el;
+    // (every call ends with a synchronize, so the device input buffers are free to overwrite here)
+    for (int k = 0; k < nchunk; ++k) {
+        const size_t p0 = (size_t)pairs * k / nchunk, p1 = (size_t)pairs * (k + 1) / nchunk;
+        B2S_CUDA(cudaMemcpyAsync((char *)c->d_tar.p + p0 * tpair, (const char *)tar_xy + p0 * tpair, (p1 - p0) * tpair,
+                                 cudaMemcpyHostToDevice, c->copy_stream));
+        B2S_CUDA(cudaMemcpyAsync((char *)c->d_src.p + p0 * spair, (const char *)src_xy + p0 * spair, (p1 - p0) * spair,
+                                 cudaMemcpyHostToDevice, c->copy_stream));
+        B2S_CUDA(cudaEventRecord(c->chunk_ready[k], c->copy_stream));
+    }
+    for (int k = 0; k < nchunk; ++k) {
+        const size_t p0 = (size_t)pairs * k / nchunk, p1 = (size_t)pairs * (k + 1) / nchunk;
+        B2S_CUDA(cudaStreamWaitEvent(c->stream, c->chunk_ready[k], 0));
+        double *dT = (double *)c->d_T.p + p0 * 9;
+        int32_t *dI = (int32_t *)c->d_iters.p + p0;
+        if (is_f64)
+            rc = b2s_icp_batch_f64((const double *)((char *)c->d_tar.p + p0 * tpair), (const double *)((char *)c->d_src.p + p0 * spair),
+                                   (int)(p1 - p0), n_src, n_tar, max_iter, tol, dT, dI, c->stream);
+        else
+            rc = b2s_icp_batch_f32((const float *)((char *)c->d_tar.p + p0 * tpair), (const float *)((char *)c->d_src.p + p0 * spair),
+                                   (int)(p1 - p0), n_src, n_tar, max_iter, tol, dT, dI, c->stream);
+        if (rc) return rc;
+    }
     B2S_CUDA(cudaMemcpyAsync(T_out, c->d_T.p, (size_t)pairs * 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (iters_out)
         B2S_CUDA(cudaMemcpyAsync(iters_out, c->d_iters.p, (size_t)pairs * sizeof(int32_t), cudaMemcpyDeviceToHost,

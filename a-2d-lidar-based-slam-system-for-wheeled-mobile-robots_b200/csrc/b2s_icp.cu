@@ -90,7 +90,9 @@ __device__ __forceinline__ void cta_rigid_fit(const double (&ax)[R], const doubl
     extra = v[8];
 }
 
-template <typename TIn, int R>
+constexpr int NN_BLK = 16;  // targets per pruning block
+
+template <typename TIn, int R, bool PRUNE>
 __global__ void icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__restrict__ src_xy, int n,
                                  int m, int max_iter, double tol, double *__restrict__ T_out,
                                  int32_t *__restrict__ iters_out, int use_bulk)
@@ -156,28 +158,118 @@ __global__ void icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__re
     const double sax = first[0] / (double)n, say = first[1] / (double)n;
     const double sbx = first[2] / (double)m, sby = first[3] / (double)m;
 
+    // ---- pruning bounds: the target scan is cut into blocks of NN_BLK consecutive points, each with the
+    // centre of its bounding box and a radius that covers it (inflated by 1e-9 so rounding can only make
+    // the test below more conservative).  The staging area is free again and holds them: [nblk][4] doubles.
+    const int nblk = (m + NN_BLK - 1) / NN_BLK;
+    double4 *bnd = reinterpret_cast<double4 *>(stage);
+    if (PRUNE) {
+        for (int b = tid; b < nblk; b += blockDim.x) {
+            const int j0 = b * NN_BLK, j1 = min(m, j0 + NN_BLK);
+            double x0 = tar[j0].x, x1 = x0, y0 = tar[j0].y, y1 = y0;
+            for (int j = j0 + 1; j < j1; ++j) {
+                x0 = fmin(x0, tar[j].x); x1 = fmax(x1, tar[j].x);
+                y0 = fmin(y0, tar[j].y); y1 = fmax(y1, tar[j].y);
+            }
+            const double cx = 0.5 * (x0 + x1), cy = 0.5 * (y0 + y1);
+            double rad2 = 0.0;
+            bool finite = true;
+            for (int j = j0; j < j1; ++j) {
+                const double dx = tar[j].x - cx, dy = tar[j].y - cy;
+                const double d2 = fma(dy, dy, dx * dx);
+                finite = finite && (d2 == d2) && (d2 < INFINITY);
+                rad2 = fmax(rad2, d2);
+            }
+            // a block with a NaN / inf point gets an infinite radius: it is never skipped
+            const double rad = finite ? sqrt(rad2) * 1.000000001 + 1e-300 : INFINITY;
+            bnd[b] = make_double4(cx, cy, rad, 0.0);
+        }
+        __syncthreads();
+    }
+
+    // previous match of every source point; seeds the pruning bound (first pass: the target with the
+    // proportional index, which is the same beam when both scans have the same beam count)
+    int arg[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const long long i = tid + r * blockDim.x;
+        arg[r] = (int)min((long long)(m - 1), i * m / n);
+    }
+
     double prev_err = 0.0;
     int iters = 0;
     for (int it = 0; it < max_iter; ++it) {
         // ---- nearest neighbour ([ICP]:99-106)
         double best[R];
-        int arg[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            best[r] = INFINITY;
-            arg[r] = 0;
-        }
-#pragma unroll 4
-        for (int j = 0; j < m; ++j) {
-            const double2 t = tar[j];
+        if (!PRUNE) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const double dx = sx[r] - t.x, dy = sy[r] - t.y;
-                const double d2 = fma(dy, dy, dx * dx);
-                if (d2 < best[r]) {
-                    best[r] = d2;
-                    arg[r] = j;
+                best[r] = INFINITY;
+                arg[r] = 0;
+            }
+#pragma unroll 4
+            for (int j = 0; j < m; ++j) {
+                const double2 t = tar[j];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const double dx = sx[r] - t.x, dy = sy[r] - t.y;
+                    const double d2 = fma(dy, dy, dx * dx);
+                    if (d2 < best[r]) {
+                        best[r] = d2;
+                        arg[r] = j;
+                    }
                 }
+            }
+        } else {
+            // Exact search with pruning.  ANY target gives an upper bound ub on the nearest distance; a block
+            // whose every point is provably farther than sqrt(ub) cannot contain the nearest point nor tie
+            // with it, so it is skipped.  Blocks are visited in ascending order and their points compared
+            // with the same strict '<', so the winner (lowest index among equals) is the brute-force one.
+            // The 32 lanes of a warp hold 32 consecutive source points for a given r, so they agree on almost
+            // all blocks; a block is evaluated by the whole warp as soon as one lane needs it.
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const bool real = r < count;
+                const double px = sx[r], py = sy[r];
+                const double2 g = tar[arg[r]];
+                const double gx = px - g.x, gy = py - g.y;
+                const double ub = fma(gy, gy, gx * gx);
+                const double su = sqrt(ub) * 1.000000001;  // NaN stays NaN: then nothing is skipped
+                double bst = INFINITY;
+                int bj = 0;
+                for (int b = 0; b < nblk; ++b) {
+                    const double4 c = bnd[b];
+                    const double cxd = px - c.x, cyd = py - c.y;
+                    const double dc2 = fma(cyd, cyd, cxd * cxd);
+                    const double reach = c.z + su;
+                    const bool skip = !real || (dc2 > reach * reach);
+                    if (__all_sync(0xffffffffu, skip)) continue;
+                    const int j0 = b * NN_BLK;
+                    if (j0 + NN_BLK <= m) {
+#pragma unroll
+                        for (int jj = 0; jj < NN_BLK; ++jj) {
+                            const double2 t = tar[j0 + jj];
+                            const double dx = px - t.x, dy = py - t.y;
+                            const double d2 = fma(dy, dy, dx * dx);
+                            if (d2 < bst) {
+                                bst = d2;
+                                bj = j0 + jj;
+                            }
+                        }
+                    } else {
+                        for (int j = j0; j < m; ++j) {
+                            const double2 t = tar[j];
+                            const double dx = px - t.x, dy = py - t.y;
+                            const double d2 = fma(dy, dy, dx * dx);
+                            if (d2 < bst) {
+                                bst = d2;
+                                bj = j;
+                            }
+                        }
+                    }
+                }
+                best[r] = bst;
+                arg[r] = bj;
             }
         }
         // ---- matched targets, distances ([ICP]:69,75)
@@ -185,6 +277,7 @@ __global__ void icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__re
         double dsum = 0.0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
+            if (PRUNE && r >= count) arg[r] = 0;  // idle slot: keep the index in range
             const double2 t = tar[arg[r]];
             bx[r] = t.x;
             by[r] = t.y;
@@ -291,9 +384,10 @@ rigid_fit_kernel(const double *__restrict__ src_xy, const double *__restrict__ t
 }
 
 int g_icp_src_per_thread = 0;  // 0: choose per problem size; 2..4 force (tuning hook)
+int g_icp_prune = 1;           // 1: exact search with block pruning (default); 0: plain brute force
 
-template <typename TIn, int R>
-static int launch_icp_r(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_src, int n_tar, int max_iter,
+template <typename TIn, int R, bool PRUNE>
+static int launch_icp_rp(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_src, int n_tar, int max_iter,
                         double tol, double *T_out, int32_t *iters_out, void *stream)
 {
     int threads = (n_src + R - 1) / R;
@@ -305,17 +399,28 @@ static int launch_icp_r(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_s
     B2S_REQUIRE(smem <= 227 * 1024, "b2s_icp_batch: n_tar too large for shared memory");
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        B2S_CUDA(cudaFuncSetAttribute(icp_batch_kernel<TIn, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        B2S_CUDA(cudaFuncSetAttribute(icp_batch_kernel<TIn, R, PRUNE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
         configured = smem;
     }
     // bulk copy needs 16-byte aligned source and size: every pair's target block must qualify
     const size_t pair_bytes = (size_t)2 * n_tar * sizeof(TIn);
     const int use_bulk = ((uintptr_t)tar_xy % 16 == 0) && (pair_bytes % 16 == 0);
-    icp_batch_kernel<TIn, R><<<pairs, threads, smem, (cudaStream_t)stream>>>(
+    icp_batch_kernel<TIn, R, PRUNE><<<pairs, threads, smem, (cudaStream_t)stream>>>(
         tar_xy, src_xy, n_src, n_tar, max_iter, tol, T_out, iters_out, use_bulk);
     B2S_CUDA(cudaGetLastError());
     return B2S_OK;
+}
+
+template <typename TIn, int R>
+static int launch_icp_r(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_src, int n_tar, int max_iter,
+                        double tol, double *T_out, int32_t *iters_out, void *stream)
+{
+    // the block bounds live in the staging area: [ceil(m/16)][4] doubles must fit in 2*m*sizeof(TIn)
+    const bool fits = (size_t)((n_tar + NN_BLK - 1) / NN_BLK) * 32 <= (size_t)2 * n_tar * sizeof(TIn);
+    if (g_icp_prune && fits)
+        return launch_icp_rp<TIn, R, true>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream);
+    return launch_icp_rp<TIn, R, false>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream);
 }
 
 template <typename TIn>

@@ -415,10 +415,12 @@ def bench_icp(args, rank, world, torch, devapi, bdist, synth):
         "dtype": "f64",
         "roofline": {"bound": "hbm", "kernel": "icp_batch_kernel", "achieved": hbm_bytes / step_s / 1e9, "peak": peak,
                      "unit": "GB/s", "frac": hbm_bytes / step_s / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                     "note": "compute bound by design: HBM fraction is expected to be << 1%",
-                     "pair_evals_per_s": evals / step_s, "fp64_tflops": flops / step_s / 1e12,
-                     "fp64_peak_tflops_nominal": FP64_PEAK_TFLOPS,
-                     "fp64_frac_nominal": flops / step_s / 1e12 / FP64_PEAK_TFLOPS},
+                     "note": "compute (FP64 issue) bound by design: each pair reads 8(N+M)+76 B once and iterates on chip, "
+                             "so the HBM fraction is expected to be << 1%",
+                     "nn_search": "exact, block-pruned (identical correspondences to the N x M brute force)",
+                     "brute_force_equivalent_pair_evals_per_s": evals / step_s,
+                     "brute_force_equivalent_fp64_tflops": flops / step_s / 1e12,
+                     "fp64_peak_tflops_nominal": FP64_PEAK_TFLOPS},
         "e2e": {"value": world * P * e2e_steps / e2e_s, "unit": "pairs/s",
                 "h2d_bytes_per_step": int(h_tar.nbytes + h_src.nbytes), "d2h_bytes_per_step": P * 76,
                 "api": "ICP.process_batch (b2s_icp_process)", "ms_per_step": e2e_s / e2e_steps * 1e3},
@@ -458,6 +460,7 @@ def main():
     ap.add_argument("--icp-scans", type=int, default=ICP_SCANS)
     ap.add_argument("--grid-variant", type=int, default=0)
     ap.add_argument("--icp-r", type=int, default=0, help="force ICP source points per thread (tuning)")
+    ap.add_argument("--icp-prune", type=int, default=-1, help="0: brute-force NN, 1: pruned exact NN (tuning)")
     ap.add_argument("--merge", default="p2p", choices=["p2p", "nccl"], help="multi-GPU grid merge")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only", default="both", choices=["both", "primary"])
@@ -477,6 +480,8 @@ def main():
     rank, local_rank, world = bdist.init()
     if args.grid_variant:
         _lib.check(_lib.lib().b2s_tune(b"grid_variant", args.grid_variant))
+    if args.icp_prune >= 0:
+        _lib.check(_lib.lib().b2s_tune(b"icp_prune", args.icp_prune))
     if args.icp_r:
         _lib.check(_lib.lib().b2s_tune(b"icp_src_per_thread", args.icp_r))
 
