@@ -123,3 +123,22 @@ def test_device_pointer_abi_and_sequence_chain(env):
     for t in want_T:
         st = pyref.compose_pose(st, t)
     assert np.allclose(traj[-1], st, rtol=0, atol=1e-7)
+
+
+def test_cfg4_shape_sample_vs_oracle(env):
+    """cfg 4 shape (1080-beam independent pairs) at a size the oracle finishes in seconds, plus a
+    size-independent check on a larger batch: every pair of a batch gives the result it gives alone."""
+    tar, src, _ = env.synth.icp_pairs(4001, 2048, 1080)
+    T, it = env.icp.process_batch(tar, src)
+    pick = np.linspace(0, 2047, 24).astype(int)
+    want_T, want_it = env.corc.icp_batch(tar[pick], src[pick], 30, 1e-3)
+    assert np.array_equal(it[pick], want_it)
+    np.testing.assert_allclose(T[pick], want_T, rtol=0, atol=T_ATOL)
+    T2, it2 = env.icp.process_batch(tar[1000:1100], src[1000:1100])     # batch position must not matter
+    assert np.array_equal(it2, it[1000:1100]) and np.array_equal(T2, T[1000:1100])
+    assert env.lib.lib().b2s_tune(b"icp_prune", 0) == 0                  # pruned == brute force, bit for bit
+    try:
+        T3, it3 = env.icp.process_batch(tar[:256], src[:256])
+    finally:
+        env.lib.lib().b2s_tune(b"icp_prune", 1)
+    assert np.array_equal(it3, it[:256]) and np.array_equal(T3, T[:256])
