@@ -39,6 +39,8 @@ SIGNATURES = {
     "b2s_grid_workspace_init": (_i32, [_vp, _i32, _i32, _vp]),
     "b2s_grid_raycast_ws": (_i32, [_vp, _vp, _i32, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp,
                                    _i32, _i32, _vp, _vp, _vp]),
+    "b2s_grid_raycast_ranges": (_i32, [_vp, _vp, _i32, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp, _dbl,
+                                       _i32, _i32, _vp, _vp, _vp]),
     "b2s_grid_validate": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "b2s_grid_finalize": (_i32, [_vp, _vp, _i32, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
     "b2s_grid_pack_ros": (_i32, [_vp, _i32, _i32, _vp, _vp]),
@@ -64,6 +66,7 @@ SIGNATURES = {
     "b2s_mapping_destroy": (_i32, [_vp]),
     "b2s_mapping_reset": (_i32, [_vp]),
     "b2s_mapping_update": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "b2s_mapping_update_ranges": (_i32, [_vp, _vp, _vp, _vp, _dbl, _i32, _i32, _vp]),
     "b2s_mapping_read": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "b2s_mapping_planes": (_i32, [_vp, _pp, _pp, _pp]),
     "b2s_bresenham_host": (_i32, [_vp, _i32, _vp, _vp]),

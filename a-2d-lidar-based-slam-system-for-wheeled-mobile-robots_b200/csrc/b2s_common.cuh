@@ -37,6 +37,10 @@ int sm_count();
 int grid_raycast_signed(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m, double off_x,
                         double off_y, const float *ox, const float *oy, const float *cx, const float *cy,
                         int scans, int beams, int32_t *counters, void *workspace, int sign, void *stream);
+int grid_raycast_ranges_signed(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m, double off_x,
+                               double off_y, const float *ranges, const double *pose4, const double *beam_cs,
+                               double clamp, int scans, int beams, int32_t *counters, void *workspace, int sign,
+                               void *stream);
 
 // ---------------------------------------------------------------- warp / block reductions
 

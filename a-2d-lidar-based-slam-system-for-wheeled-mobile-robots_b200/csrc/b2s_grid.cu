@@ -31,19 +31,22 @@ struct Beam {
     int sx, sy;   // sensor cell (the path's first element)
 };
 
-enum BeamStatus { BEAM_OK = 0, BEAM_NOOP = 1, BEAM_NONFINITE = 2, BEAM_TOO_LONG = 3, BEAM_INF_SKIP = 4 };
+enum BeamStatus { BEAM_OK = 0, BEAM_NOOP = 1, BEAM_NAN = 2, BEAM_TOO_LONG = 3, BEAM_INF_SKIP = 4, BEAM_OVERFLOW = 5 };
 
 // [MAP]:33-36  int(S * (v + H)): float64 add, then multiply, then truncate toward zero.
-__device__ __forceinline__ double cell_coord(float v, double cells_per_m, double off)
+__device__ __forceinline__ double cell_coord(double v, double cells_per_m, double off)
 {
-    return __dmul_rn(cells_per_m, __dadd_rn((double)v, off));
+    return __dmul_rn(cells_per_m, __dadd_rn(v, off));
 }
 
-__device__ __forceinline__ int beam_setup(float fox, float foy, float fcx, float fcy, int xw, int yw,
+// Coordinates arrive as float64: float32 endpoints are upcast exactly by the callers, the fused
+// ingestion path (ranges + pose) computes them in float64 like the reference does.
+__device__ __forceinline__ int beam_setup(double fox, double foy, double fcx, double fcy, int xw, int yw,
                                           double cells_per_m, double off_x, double off_y, Beam &b)
 {
     if (isinf(fox)) return BEAM_INF_SKIP;  // [MAP]:30 tests ox only
-    if (isnan(fox) || !isfinite(foy) || !isfinite(fcx) || !isfinite(fcy)) return BEAM_NONFINITE;
+    if (isnan(fox) || isnan(foy) || isnan(fcx) || isnan(fcy)) return BEAM_NAN;  // int(nan): ValueError
+    if (isinf(foy) || isinf(fcx) || isinf(fcy)) return BEAM_OVERFLOW;            // int(inf): OverflowError
     const double dxo = cell_coord(fox, cells_per_m, off_x), dyo = cell_coord(foy, cells_per_m, off_y);
     const double dxc = cell_coord(fcx, cells_per_m, off_x), dyc = cell_coord(fcy, cells_per_m, off_y);
     const double lim = 1073741824.0;  // 2^30: keeps every difference inside int32
@@ -81,7 +84,8 @@ __device__ __forceinline__ int beam_setup(float fox, float foy, float fcx, float
 __device__ __forceinline__ void count_status(int st, int32_t *counters)
 {
     if (counters == nullptr) return;
-    if (st == BEAM_NONFINITE) atomicAdd(&counters[B2S_CNT_NONFINITE], 1);
+    if (st == BEAM_NAN) atomicAdd(&counters[B2S_CNT_NONFINITE], 1);
+    if (st == BEAM_OVERFLOW) atomicAdd(&counters[B2S_CNT_OVERFLOW], 1);
     if (st == BEAM_TOO_LONG) atomicAdd(&counters[B2S_CNT_TOO_LONG], 1);
     if (st == BEAM_INF_SKIP) atomicAdd(&counters[B2S_CNT_SKIPPED_INF], 1);
 }
@@ -369,13 +373,51 @@ __device__ __forceinline__ void march_step4(int t, int delay, double slope, doub
         : "memory");
 }
 
+// Where a beam's endpoints come from.  FUSED = false: world-frame endpoints ox, oy + sensor position
+// cx, cy (the arguments of Mapping.update).  FUSED = true: raw ranges + pose, i.e. the node's
+// laserToNumpy ([SLAM]:115-123) and `u2T(xEst).dot(np_msg)` ([SLAM]:130-137,89) evaluated per beam in
+// float64: p = (cos a * r, sin a * r) with inf -> clamp, o = (cw*px + (-sw)*py) + x, (sw*px + cw*py) + y.
+// cos/sin of the beam angles and of the yaw are computed by the host exactly as the reference
+// computes them (NumPy / math), so the device only multiplies and adds.
+struct ScanInput {
+    const float *ox, *oy, *cx, *cy;  // endpoints mode
+    const float *ranges;             // fused mode: [scans][beams]
+    const double *pose4;             // fused mode: [scans][4] = x, y, cos(yaw), sin(yaw)
+    const double *beam_cs;           // fused mode: [beams][2] = cos(angle), sin(angle)
+    double clamp;                    // fused mode: replacement for +inf ranges (MAX_LASER_RANGE), <= 0: none
+};
+
+template <bool FUSED>
+__device__ __forceinline__ void load_beam(const ScanInput &in, long long i, int beams, double &fox, double &foy,
+                                          double &fcx, double &fcy)
+{
+    const int s = (int)(i / beams);
+    if (!FUSED) {
+        fox = (double)__ldg(in.ox + i);
+        foy = (double)__ldg(in.oy + i);
+        fcx = (double)__ldg(in.cx + s);
+        fcy = (double)__ldg(in.cy + s);
+    } else {
+        const int j = (int)(i - (long long)s * beams);
+        double r = (double)__ldg(in.ranges + i);
+        if (in.clamp > 0.0 && r == INFINITY) r = in.clamp;  // [SLAM]:119 (only +inf compares equal)
+        const double2 cs = __ldg(reinterpret_cast<const double2 *>(in.beam_cs) + j);
+        const double px = __dmul_rn(cs.x, r), py = __dmul_rn(cs.y, r);  // [SLAM]:122
+        const double2 xy = __ldg(reinterpret_cast<const double2 *>(in.pose4) + 2 * s);
+        const double2 cw = __ldg(reinterpret_cast<const double2 *>(in.pose4) + 2 * s + 1);
+        fox = __dadd_rn(__dadd_rn(__dmul_rn(cw.x, px), __dmul_rn(-cw.y, py)), xy.x);  // [SLAM]:134,89
+        foy = __dadd_rn(__dadd_rn(__dmul_rn(cw.y, px), __dmul_rn(cw.x, py)), xy.y);   // [SLAM]:135,89
+        fcx = xy.x;
+        fcy = xy.y;
+    }
+}
+
 // SIGN = +1 applies a batch, SIGN = -1 takes the same batch back out (exact inverse: integer adds).
-template <int SIGN>
+template <int SIGN, bool FUSED>
 __global__ void __launch_bounds__(256, 8)
 grid_raycast_v4(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int32_t *__restrict__ scratch_t,
                 GridWorkspace *__restrict__ ws, int xw, int yw, double cells_per_m, double off_x, double off_y,
-                const float *__restrict__ ox, const float *__restrict__ oy, const float *__restrict__ cx,
-                const float *__restrict__ cy, long long total, int beams, int32_t *counters)
+                const ScanInput in, long long total, int beams, int32_t *counters)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31;
@@ -384,9 +426,9 @@ grid_raycast_v4(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int32_t *
     b.slope = 0.0;
     int st = BEAM_NOOP;
     if (i < total) {
-        const int s = (int)(i / beams);
-        st = beam_setup(__ldg(ox + i), __ldg(oy + i), __ldg(cx + s), __ldg(cy + s), xw, yw,
-                        cells_per_m, off_x, off_y, b);
+        double fox, foy, fcx, fcy;
+        load_beam<FUSED>(in, i, beams, fox, foy, fcx, fcy);
+        st = beam_setup(fox, foy, fcx, fcy, xw, yw, cells_per_m, off_x, off_y, b);
         if (st != BEAM_OK && SIGN > 0) count_status(st, counters);
     }
     const bool live = (st == BEAM_OK);
@@ -664,12 +706,13 @@ extern "C" int b2s_grid_workspace_init(void *workspace, int xw, int yw, void *st
 }
 
 namespace b2s {
-// Shared by b2s_grid_raycast_ws (sign +1) and the host layer's roll-back of a rejected batch (sign -1).
-int grid_raycast_signed(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m, double off_x,
-                        double off_y, const float *ox, const float *oy, const float *cx, const float *cy,
-                        int scans, int beams, int32_t *counters, void *workspace, int sign, void *stream)
+// Shared by b2s_grid_raycast_ws / b2s_grid_raycast_ranges (sign +1) and the host layer's roll-back of a
+// rejected batch (sign -1).
+static int raycast_v4_launch(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m, double off_x,
+                             double off_y, const ScanInput &in, bool fused, int scans, int beams, int32_t *counters,
+                             void *workspace, int sign, void *stream)
 {
-    B2S_REQUIRE(hit && miss && ox && oy && cx && cy && workspace, "b2s_grid_raycast_ws: null pointer");
+    B2S_REQUIRE(hit && miss && workspace, "b2s_grid_raycast_ws: null pointer");
     B2S_REQUIRE(xw > 0 && yw > 0 && (long long)xw * yw < (1ll << 30), "b2s_grid_raycast_ws: grid size");
     B2S_REQUIRE(scans >= 0 && beams >= 0, "b2s_grid_raycast_ws: negative count");
     B2S_REQUIRE(cells_per_m == cells_per_m && off_x == off_x && off_y == off_y, "b2s_grid_raycast_ws: NaN scale");
@@ -682,12 +725,15 @@ int grid_raycast_signed(int32_t *hit, int32_t *miss, int xw, int yw, double cell
     cudaStream_t st = (cudaStream_t)stream;
     GridWorkspace *ws = (GridWorkspace *)workspace;
     int32_t *scratch_t = (int32_t *)((char *)workspace + sizeof(GridWorkspace));
-    if (sign >= 0)
-        grid_raycast_v4<1><<<(unsigned)blocks, threads, 0, st>>>(hit, miss, scratch_t, ws, xw, yw, cells_per_m, off_x,
-                                                                 off_y, ox, oy, cx, cy, total, beams, counters);
-    else
-        grid_raycast_v4<-1><<<(unsigned)blocks, threads, 0, st>>>(hit, miss, scratch_t, ws, xw, yw, cells_per_m,
-                                                                  off_x, off_y, ox, oy, cx, cy, total, beams, counters);
+#define B2S_V4(SG, FU)                                                                                           \
+    grid_raycast_v4<SG, FU><<<(unsigned)blocks, threads, 0, st>>>(hit, miss, scratch_t, ws, xw, yw, cells_per_m, \
+                                                                   off_x, off_y, in, total, beams, counters)
+    if (sign >= 0) {
+        if (fused) B2S_V4(1, true); else B2S_V4(1, false);
+    } else {
+        if (fused) B2S_V4(-1, true); else B2S_V4(-1, false);
+    }
+#undef B2S_V4
     B2S_CUDA(cudaGetLastError());
     dim3 fgrid((xw + 31) / 32, (yw + 31) / 32);
     grid_fold_kernel<<<fgrid, 256, 0, st>>>(miss, scratch_t, ws, xw, yw);
@@ -695,7 +741,39 @@ int grid_raycast_signed(int32_t *hit, int32_t *miss, int xw, int yw, double cell
     B2S_CUDA(cudaMemsetAsync(ws, 0x80, sizeof(GridWorkspace), st));
     return B2S_OK;
 }
+
+int grid_raycast_signed(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m, double off_x,
+                        double off_y, const float *ox, const float *oy, const float *cx, const float *cy,
+                        int scans, int beams, int32_t *counters, void *workspace, int sign, void *stream)
+{
+    B2S_REQUIRE(ox && oy && cx && cy, "b2s_grid_raycast_ws: null pointer");
+    ScanInput in = {ox, oy, cx, cy, nullptr, nullptr, nullptr, 0.0};
+    return raycast_v4_launch(hit, miss, xw, yw, cells_per_m, off_x, off_y, in, false, scans, beams, counters,
+                             workspace, sign, stream);
+}
+
+int grid_raycast_ranges_signed(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m, double off_x,
+                               double off_y, const float *ranges, const double *pose4, const double *beam_cs,
+                               double clamp, int scans, int beams, int32_t *counters, void *workspace, int sign,
+                               void *stream)
+{
+    B2S_REQUIRE(ranges && pose4 && beam_cs, "b2s_grid_raycast_ranges: null pointer");
+    B2S_REQUIRE((uintptr_t)pose4 % 16 == 0 && (uintptr_t)beam_cs % 16 == 0,
+                "b2s_grid_raycast_ranges: pose and beam tables must be 16-byte aligned");
+    ScanInput in = {nullptr, nullptr, nullptr, nullptr, ranges, pose4, beam_cs, clamp};
+    return raycast_v4_launch(hit, miss, xw, yw, cells_per_m, off_x, off_y, in, true, scans, beams, counters,
+                             workspace, sign, stream);
+}
 }  // namespace b2s
+
+extern "C" int b2s_grid_raycast_ranges(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m,
+                                       double off_x, double off_y, const float *ranges, const double *pose4,
+                                       const double *beam_cs, double clamp_inf_to, int scans, int beams,
+                                       int32_t *counters, void *workspace, void *stream)
+{
+    return grid_raycast_ranges_signed(hit, miss, xw, yw, cells_per_m, off_x, off_y, ranges, pose4, beam_cs,
+                                      clamp_inf_to, scans, beams, counters, workspace, +1, stream);
+}
 
 extern "C" int b2s_grid_raycast_ws(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m,
                                    double off_x, double off_y, const float *ox, const float *oy,

@@ -406,33 +406,65 @@ extern "C" int b2s_mapping_reset(b2s_mapping *m)
     return B2S_OK;
 }
 
-extern "C" int b2s_mapping_update(b2s_mapping *m, const float *ox, const float *oy, const float *cx,
-                                  const float *cy, int scans, int beams, int8_t *pmap_out)
+namespace {
+// One host batch in either input form.
+struct HostBatch {
+    bool fused;
+    const float *ox, *oy, *cx, *cy;  // endpoints form
+    const float *ranges;             // fused form
+    const double *pose4, *beam_cs;
+    double clamp;
+};
+
+// Mapping.update for a batch, all-or-nothing like a Python exception raised before the loop.
+//   * the batch is cut into up to 8 chunks of scans; chunk k+1 crosses PCIe on the copy stream while
+//     chunk k is screened and ray-cast on the compute stream
+//   * beams that int() would raise on ([MAP]:33-36) are skipped and counted by the kernels, so applying
+//     a chunk before the verdict on the whole batch is known is safe: a rejected batch is taken back
+//     out with the sign -1 kernel (integer adds: exact inverse)
+int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beams, int8_t *pmap_out)
 {
-    B2S_REQUIRE(m, "b2s_mapping_update: null handle");
-    B2S_REQUIRE(scans >= 0 && beams >= 0, "b2s_mapping_update: negative count");
     DeviceGuard g(m->device);
     const size_t total = (size_t)scans * beams;
     int rc;
     int nchunk = 0;
-    float *d_ox = nullptr, *d_oy = nullptr, *d_cx = nullptr, *d_cy = nullptr;
-    int lo[9];
+    int lo[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    float *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_d = nullptr;  // ox|oy|cx|cy  or  ranges
+    double *d_pose = nullptr, *d_cs = nullptr;
+    auto launch = [&](int k, int sign, int32_t *counters) -> int {
+        const size_t s0 = (size_t)lo[k];
+        const int ns = lo[k + 1] - lo[k];
+        if (hb.fused)
+            return grid_raycast_ranges_signed(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y,
+                                              d_a + s0 * beams, d_pose + 4 * s0, d_cs, hb.clamp, ns, beams, counters,
+                                              m->workspace, sign, m->stream);
+        return grid_raycast_signed(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y,
+                                   d_a + s0 * beams, d_b + s0 * beams, d_c + s0, d_d + s0, ns, beams, counters,
+                                   m->workspace, sign, m->stream);
+    };
     if (total > 0) {
-        B2S_REQUIRE(ox && oy && cx && cy, "b2s_mapping_update: null pointer");
-        const size_t pts = total * sizeof(float), ctr = (size_t)scans * sizeof(float);
-        // one device block: [ox | oy | cx | cy], each section 16-byte aligned
-        const size_t a_pts = (pts + 15) & ~(size_t)15, a_ctr = (ctr + 15) & ~(size_t)15;
-        if ((rc = m->d_in.reserve(2 * a_pts + 2 * a_ctr))) return rc;
-        char *base = (char *)m->d_in.p;
-        d_ox = (float *)base;
-        d_oy = (float *)(base + a_pts);
-        d_cx = (float *)(base + 2 * a_pts);
-        d_cy = (float *)(base + 2 * a_pts + a_ctr);
+        const size_t pts = total * sizeof(float), a_pts = (pts + 15) & ~(size_t)15;
+        char *base;
+        if (hb.fused) {
+            const size_t poses = (size_t)scans * 4 * sizeof(double), table = (size_t)beams * 2 * sizeof(double);
+            if ((rc = m->d_in.reserve(a_pts + poses + table))) return rc;
+            base = (char *)m->d_in.p;
+            d_a = (float *)base;
+            d_pose = (double *)(base + a_pts);
+            d_cs = (double *)(base + a_pts + poses);
+            B2S_CUDA(cudaMemcpyAsync(d_cs, hb.beam_cs, table, cudaMemcpyHostToDevice, m->copy_stream));
+        } else {
+            const size_t ctr = (size_t)scans * sizeof(float), a_ctr = (ctr + 15) & ~(size_t)15;
+            if ((rc = m->d_in.reserve(2 * a_pts + 2 * a_ctr))) return rc;
+            base = (char *)m->d_in.p;
+            d_a = (float *)base;
+            d_b = (float *)(base + a_pts);
+            d_c = (float *)(base + 2 * a_pts);
+            d_d = (float *)(base + 2 * a_pts + a_ctr);
+        }
         // counters[0..3]: the ray-cast kernel's own (B2S_CNT_*); counters[4], [5]: NaN / inf seen by the screening
         B2S_CUDA(cudaMemsetAsync(m->counters, 0, 2 * B2S_CNT_WORDS * sizeof(int32_t), m->stream));
-        // Pipeline: the batch is cut into up to 8 chunks of scans; chunk k+1 crosses PCIe on the copy
-        // stream while chunk k is screened and ray-cast on the compute stream.
-        nchunk = (int)((total + (1u << 21) - 1) >> 21);  // ~2M beams (16 MB of endpoints) per chunk
+        nchunk = (int)((total + (1u << 21) - 1) >> 21);  // ~2M beams per chunk
         if (nchunk > 8) nchunk = 8;
         if (nchunk > scans) nchunk = scans;
         if (nchunk < 1) nchunk = 1;
@@ -440,33 +472,27 @@ extern "C" int b2s_mapping_update(b2s_mapping *m, const float *ox, const float *
         for (int k = 0; k < nchunk; ++k) {
             const size_t s0 = (size_t)lo[k], ns = (size_t)(lo[k + 1] - lo[k]);
             cudaStream_t cs = m->copy_stream;
-            B2S_CUDA(cudaMemcpyAsync(d_ox + s0 * beams, ox + s0 * beams, ns * beams * sizeof(float), cudaMemcpyHostToDevice, cs));
-            B2S_CUDA(cudaMemcpyAsync(d_oy + s0 * beams, oy + s0 * beams, ns * beams * sizeof(float), cudaMemcpyHostToDevice, cs));
-            B2S_CUDA(cudaMemcpyAsync(d_cx + s0, cx + s0, ns * sizeof(float), cudaMemcpyHostToDevice, cs));
-            B2S_CUDA(cudaMemcpyAsync(d_cy + s0, cy + s0, ns * sizeof(float), cudaMemcpyHostToDevice, cs));
+            if (hb.fused) {
+                B2S_CUDA(cudaMemcpyAsync(d_a + s0 * beams, hb.ranges + s0 * beams, ns * beams * sizeof(float), cudaMemcpyHostToDevice, cs));
+                B2S_CUDA(cudaMemcpyAsync(d_pose + 4 * s0, hb.pose4 + 4 * s0, ns * 4 * sizeof(double), cudaMemcpyHostToDevice, cs));
+            } else {
+                B2S_CUDA(cudaMemcpyAsync(d_a + s0 * beams, hb.ox + s0 * beams, ns * beams * sizeof(float), cudaMemcpyHostToDevice, cs));
+                B2S_CUDA(cudaMemcpyAsync(d_b + s0 * beams, hb.oy + s0 * beams, ns * beams * sizeof(float), cudaMemcpyHostToDevice, cs));
+                B2S_CUDA(cudaMemcpyAsync(d_c + s0, hb.cx + s0, ns * sizeof(float), cudaMemcpyHostToDevice, cs));
+                B2S_CUDA(cudaMemcpyAsync(d_d + s0, hb.cy + s0, ns * sizeof(float), cudaMemcpyHostToDevice, cs));
+            }
             B2S_CUDA(cudaEventRecord(m->chunk_ready[k], cs));
         }
         for (int k = 0; k < nchunk; ++k) {
-            const size_t s0 = (size_t)lo[k];
-            const int ns = lo[k + 1] - lo[k];
             B2S_CUDA(cudaStreamWaitEvent(m->stream, m->chunk_ready[k], 0));
-            // screening like the reference's int() ([MAP]:33-36): flags accumulate over the chunks
-            if ((rc = b2s_grid_validate(d_ox + s0 * beams, d_oy + s0 * beams, d_cx + s0, d_cy + s0, ns, beams,
-                                        m->counters + B2S_CNT_WORDS, m->stream)))
-                return rc;
-            // beams the screening flags are skipped by the kernel itself, so applying a chunk before the
-            // verdict on the whole batch is known is safe: a rejected batch is taken back out below
-            rc = grid_raycast_signed(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y,
-                                     d_ox + s0 * beams, d_oy + s0 * beams, d_cx + s0, d_cy + s0, ns, beams,
-                                     m->counters, m->workspace, +1, m->stream);
-            if (rc) return rc;
+            if ((rc = launch(k, +1, m->counters))) return rc;
         }
     }
-    int32_t cnt[2 * B2S_CNT_WORDS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int32_t cnt[B2S_CNT_WORDS] = {0, 0, 0, 0};
     if (total > 0)
         B2S_CUDA(cudaMemcpyAsync(cnt, m->counters, sizeof(cnt), cudaMemcpyDeviceToHost, m->stream));
+    const size_t cells = (size_t)m->xw * m->yw;
     if (pmap_out) {
-        const size_t cells = (size_t)m->xw * m->yw;
         if ((rc = m->d_pmap.reserve(cells))) return rc;
         rc = b2s_grid_finalize(m->hit, m->miss, m->xw, m->yw, m->w_hit, m->w_miss, m->thresh, nullptr,
                                (int8_t *)m->d_pmap.p, m->stream);
@@ -474,18 +500,11 @@ extern "C" int b2s_mapping_update(b2s_mapping *m, const float *ox, const float *
         B2S_CUDA(cudaMemcpyAsync(pmap_out, m->d_pmap.p, cells, cudaMemcpyDeviceToHost, m->stream));
     }
     B2S_CUDA(cudaStreamSynchronize(m->stream));
-    const int saw_nan = cnt[B2S_CNT_WORDS], saw_inf = cnt[B2S_CNT_WORDS + 1];
+    const int saw_nan = cnt[B2S_CNT_NONFINITE], saw_inf = cnt[B2S_CNT_OVERFLOW];
     if (saw_nan || saw_inf || cnt[B2S_CNT_TOO_LONG] > 0) {
-        // all-or-nothing like a Python exception before the loop: take the whole batch back out
-        for (int k = 0; k < nchunk; ++k) {
-            const size_t s0 = (size_t)lo[k];
-            rc = grid_raycast_signed(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y,
-                                     d_ox + s0 * beams, d_oy + s0 * beams, d_cx + s0, d_cy + s0, lo[k + 1] - lo[k],
-                                     beams, nullptr, m->workspace, -1, m->stream);
-            if (rc) return rc;
-        }
+        for (int k = 0; k < nchunk; ++k)
+            if ((rc = launch(k, -1, nullptr))) return rc;
         if (pmap_out) {
-            const size_t cells = (size_t)m->xw * m->yw;
             rc = b2s_grid_finalize(m->hit, m->miss, m->xw, m->yw, m->w_hit, m->w_miss, m->thresh, nullptr,
                                    (int8_t *)m->d_pmap.p, m->stream);
             if (rc) return rc;
@@ -493,6 +512,8 @@ extern "C" int b2s_mapping_update(b2s_mapping *m, const float *ox, const float *
         }
         B2S_CUDA(cudaStreamSynchronize(m->stream));
         if (saw_nan || saw_inf) {
+            // the reference raises at the first offending beam in scan order; NaN and inf map to
+            // different exception classes, NaN wins when both occur (documented deviation)
             set_error(saw_nan ? "cannot convert float NaN to integer" : "cannot convert float infinity to integer");
             return B2S_ERR_NONFINITE;
         }
@@ -500,6 +521,28 @@ extern "C" int b2s_mapping_update(b2s_mapping *m, const float *ox, const float *
         return B2S_ERR_TOO_LONG;
     }
     return B2S_OK;
+}
+}  // namespace
+
+extern "C" int b2s_mapping_update(b2s_mapping *m, const float *ox, const float *oy, const float *cx,
+                                  const float *cy, int scans, int beams, int8_t *pmap_out)
+{
+    B2S_REQUIRE(m, "b2s_mapping_update: null handle");
+    B2S_REQUIRE(scans >= 0 && beams >= 0, "b2s_mapping_update: negative count");
+    B2S_REQUIRE((size_t)scans * beams == 0 || (ox && oy && cx && cy), "b2s_mapping_update: null pointer");
+    HostBatch hb = {false, ox, oy, cx, cy, nullptr, nullptr, nullptr, 0.0};
+    return mapping_update_impl(m, hb, scans, beams, pmap_out);
+}
+
+extern "C" int b2s_mapping_update_ranges(b2s_mapping *m, const float *ranges, const double *pose4,
+                                         const double *beam_cs, double clamp_inf_to, int scans, int beams,
+                                         int8_t *pmap_out)
+{
+    B2S_REQUIRE(m, "b2s_mapping_update_ranges: null handle");
+    B2S_REQUIRE(scans >= 0 && beams >= 0, "b2s_mapping_update_ranges: negative count");
+    B2S_REQUIRE((size_t)scans * beams == 0 || (ranges && pose4 && beam_cs), "b2s_mapping_update_ranges: null pointer");
+    HostBatch hb = {true, nullptr, nullptr, nullptr, nullptr, ranges, pose4, beam_cs, clamp_inf_to};
+    return mapping_update_impl(m, hb, scans, beams, pmap_out);
 }
 
 extern "C" int b2s_mapping_read(b2s_mapping *m, int32_t *hit, int32_t *miss, float *datamap, int8_t *pmap)

@@ -68,6 +68,23 @@ def grid_raycast(hit, miss, cells_per_m, off_x, off_y, ox, oy, cx, cy, counters=
     _lib.check(rc)
 
 
+def grid_raycast_ranges(hit, miss, cells_per_m, off_x, off_y, ranges, pose4, beam_cs, clamp_inf_to=30.0,
+                        counters=None, workspace=None):
+    """b2s_grid_raycast_ranges: ranges float32 (K,N), pose4 float64 (K,4), beam_cs float64 (N,2)."""
+    xw, yw = hit.shape
+    K, N = ranges.shape
+    if workspace is None:
+        raise ValueError("the fused-ingestion kernel needs a workspace (new_workspace)")
+    rc = _lib.lib().b2s_grid_raycast_ranges(
+        _chk(hit, torch.int32, "hit"), _chk(miss, torch.int32, "miss"), xw, yw,
+        float(cells_per_m), float(off_x), float(off_y), _chk(ranges, torch.float32, "ranges"),
+        _chk(pose4, torch.float64, "pose4"), _chk(beam_cs, torch.float64, "beam_cs"),
+        float(clamp_inf_to or 0.0), K, N,
+        None if counters is None else _chk(counters, torch.int32, "counters"),
+        _chk(workspace, torch.int32, "workspace"), _stream())
+    _lib.check(rc)
+
+
 def grid_finalize(hit, miss, w_hit=20.0, w_miss=0.01, thresh=10.0, datamap=None, pmap=None):
     xw, yw = hit.shape
     rc = _lib.lib().b2s_grid_finalize(

@@ -91,9 +91,37 @@ class Mapping(object):
         rc = self._L.b2s_mapping_update(self._h, _lib.ptr(ox), _lib.ptr(oy), _lib.ptr(cx),
                                         _lib.ptr(cy), ox.shape[0], ox.shape[1], _lib.ptr(out))
         if rc == _lib.ERR_NONFINITE:
-            bad_nan = np.isnan(ox).any() or np.isnan(oy).any() or np.isnan(cx).any() \
-                or np.isnan(cy).any()
-            if bad_nan:
+            if "NaN" in self._L.b2s_last_error().decode():
+                raise ValueError("cannot convert float NaN to integer")
+            raise OverflowError("cannot convert float infinity to integer")
+        _lib.check(rc)
+        return self._pmap8 if want_pmap else None
+
+    def update_scans(self, ranges, poses, angle_min, angle_max, clamp_inf_to=30.0, want_pmap=True):
+        """Fused ingestion: raw scans + poses instead of world-frame endpoints.
+
+        Does what slam_ekf.py:89-90 does around Mapping.update -- laserToNumpy (inf -> 30 m,
+        slam_ekf.py:115-123), obs = u2T(pose).dot(np_msg) (slam_ekf.py:130-137), update(obs[0], obs[1],
+        x, y) -- in one kernel, in float64, for K scans: ranges (K,N) float32, poses (K,3) = x, y, yaw.
+        Half the bytes of the endpoint form cross PCIe.  Returns the int8 occupancy like update_batch.
+        """
+        from b2slam import scan
+        ranges = np.ascontiguousarray(ranges, dtype=np.float32)
+        if ranges.ndim == 1:
+            ranges = ranges.reshape(1, -1)
+        pose4 = scan.pose_table(poses)
+        if pose4.shape[0] != ranges.shape[0]:
+            raise ValueError("need one pose per scan, got %d poses for %d scans" % (pose4.shape[0], ranges.shape[0]))
+        key = (float(angle_min), float(angle_max), ranges.shape[1])
+        if getattr(self, "_beam_key", None) != key:
+            self._beam_cs = scan.beam_table(angle_min, angle_max, ranges.shape[1])
+            self._beam_key = key
+        out = self._pmap8 if want_pmap else None
+        rc = self._L.b2s_mapping_update_ranges(self._h, _lib.ptr(ranges), _lib.ptr(pose4), _lib.ptr(self._beam_cs),
+                                               float(clamp_inf_to or 0.0), ranges.shape[0], ranges.shape[1],
+                                               _lib.ptr(out))
+        if rc == _lib.ERR_NONFINITE:
+            if "NaN" in self._L.b2s_last_error().decode():
                 raise ValueError("cannot convert float NaN to integer")
             raise OverflowError("cannot convert float infinity to integer")
         _lib.check(rc)

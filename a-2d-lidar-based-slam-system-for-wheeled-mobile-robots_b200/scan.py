@@ -52,3 +52,22 @@ def compose_odometry(state, transforms):
         x, y, th = nx, ny, th + dyaw
         out[i + 1] = (x, y, th)
     return out
+
+
+def beam_table(angle_min, angle_max, beams):
+    """(beams, 2) float64 [cos a, sin a] of the beam angles, evaluated like laserToNumpy does
+    (np.linspace, np.cos, np.sin: slam_ekf.py:121-122) -- the table b2s_grid_raycast_ranges consumes."""
+    a = np.linspace(angle_min, angle_max, beams)
+    return np.ascontiguousarray(np.stack([np.cos(a), np.sin(a)], axis=1))
+
+
+def pose_table(poses):
+    """(K, 4) float64 [x, y, cos yaw, sin yaw] from (K, 3) poses, with math.cos / math.sin like u2T
+    (slam_ekf.py:130-137)."""
+    poses = np.asarray(poses, dtype=np.float64).reshape(-1, 3)
+    out = np.empty((poses.shape[0], 4))
+    out[:, 0] = poses[:, 0]
+    out[:, 1] = poses[:, 1]
+    out[:, 2] = [math.cos(w) for w in poses[:, 2]]
+    out[:, 3] = [math.sin(w) for w in poses[:, 2]]
+    return out

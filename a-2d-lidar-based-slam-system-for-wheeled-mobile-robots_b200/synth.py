@@ -137,15 +137,10 @@ def room_sequence(seed, scans, n_beams, chunk=512):
 
 # ------------------------------------------------------------------ cfg 3 / 5: grid streams
 
-def grid_scans(seed, scans, n_beams, half_extent_m=80.0, step_m=0.1):
-    """cfg 3 (seed 12001) / cfg 5 (seeds 5001..): world-frame beam endpoints from known poses.
-
-    Poses follow a seeded random walk (heading noise, forward step `step_m`) reflected
-    inside +-half_extent_m.  Returns ox, oy float32 (scans, n_beams) world-frame endpoints
-    and cx, cy float32 (scans,) sensor positions.
-    """
+def grid_scan_ranges(seed, scans, n_beams, half_extent_m=80.0, step_m=0.1):
+    """Raw form of the cfg 3 / cfg 5 streams: ranges float32 (scans, n_beams) and poses float64
+    (scans, 3) = x, y, yaw -- what the node holds before laserToNumpy / u2T (slam_ekf.py:89)."""
     rng = _rng(seed)
-    phi = beam_angles(n_beams)[None, :]
     r = noisy(rng, clean_ranges(rng, scans, n_beams))
     turn = np.cumsum(rng.normal(0.0, 0.05, size=scans))
     th = rng.uniform(-np.pi, np.pi) + turn
@@ -160,8 +155,24 @@ def grid_scans(seed, scans, n_beams, half_extent_m=80.0, step_m=0.1):
 
     x = reflect(x)
     y = reflect(y)
+    # positions and ranges are float32-representable so both input forms describe the same scans
+    x = x.astype(np.float32).astype(np.float64)
+    y = y.astype(np.float32).astype(np.float64)
+    return r.astype(np.float32), np.stack([x, y, th], axis=1)
+
+
+def grid_scans(seed, scans, n_beams, half_extent_m=80.0, step_m=0.1):
+    """cfg 3 (seed 12001) / cfg 5 (seeds 5001..): world-frame beam endpoints from known poses.
+
+    Poses follow a seeded random walk (heading noise, forward step `step_m`) reflected
+    inside +-half_extent_m.  Returns ox, oy float32 (scans, n_beams) world-frame endpoints
+    and cx, cy float32 (scans,) sensor positions.
+    """
+    r, poses = grid_scan_ranges(seed, scans, n_beams, half_extent_m, step_m)
+    phi = beam_angles(n_beams)[None, :]
+    x, y, th = poses[:, 0], poses[:, 1], poses[:, 2]
     ang = phi + th[:, None]
-    ox = x[:, None] + r * np.cos(ang)
-    oy = y[:, None] + r * np.sin(ang)
+    ox = x[:, None] + r.astype(np.float64) * np.cos(ang)
+    oy = y[:, None] + r.astype(np.float64) * np.sin(ang)
     return (ox.astype(np.float32), oy.astype(np.float32),
             x.astype(np.float32), y.astype(np.float32))

@@ -322,6 +322,25 @@ def bench_grid(args, rank, world, torch, devapi, bdist, synth):
     e2e_s = bdist.max_over_ranks(time.perf_counter() - t0)
     bdist.barrier()
 
+    # ---- the same scans in raw form (ranges + poses) through the fused-ingestion call: half the H2D bytes
+    fused = None
+    if world == 1:
+        import math
+        ranges, poses = synth.grid_scan_ranges(12001 + rank, K, N)
+        keep_r, h_ranges = pinned(ranges)
+        m.reset()
+        m.update_scans(h_ranges, poses, -math.pi, math.pi)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            m.reset()
+            m.update_scans(h_ranges, poses, -math.pi, math.pi)
+        torch.cuda.synchronize()
+        fs = time.perf_counter() - t0
+        fused = {"value": K * N * e2e_steps / fs, "unit": "beams/s", "h2d_bytes_per_step": 4 * K * N + 32 * K,
+                 "d2h_bytes_per_step": G * G, "api": "Mapping.update_scans (b2s_mapping_update_ranges)",
+                 "ms_per_step": fs / e2e_steps * 1e3}
+
     peak, peak_src = measured_peaks()
     achieved = algo_bytes / (ray_avg_ms * 1e-3) / 1e9
     if p2p is not None:
@@ -349,9 +368,11 @@ def bench_grid(args, rank, world, torch, devapi, bdist, synth):
                 "api": ("Mapping.update_batch (b2s_mapping_update)" if world == 1 else
                         "dist.ShardedMappingP2P.update_batch" if p2p is not None else "dist.ShardedMapping.update_batch"),
                 "ms_per_step": e2e_s / e2e_steps * 1e3},
-        "gpu_launches": (3 if world == 1 or p2p is not None else 3) * args.steps,
+        "gpu_launches": 3 * args.steps,
         "clocks": clocks,
     }
+    if fused:
+        res["e2e_fused_ingestion"] = fused
     return res
 
 
@@ -507,6 +528,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": prim["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": prim["dtype"],
             "data": "synthetic", "config": prim["config"], "roofline": prim["roofline"], "e2e": prim["e2e"],
+            **({"e2e_fused_ingestion": prim["e2e_fused_ingestion"]} if "e2e_fused_ingestion" in prim else {}),
             "gpu_launches": sum(r["gpu_launches"] for r in results.values()), "clocks": prim["clocks"],
             "cpu_baseline": cpu.get(order[0]),
         }

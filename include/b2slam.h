@@ -41,9 +41,10 @@ extern "C" {
 #define B2S_MAX_PATH_CELLS (1 << 22)
 
 /* index into the optional device counters of b2s_grid_raycast */
-#define B2S_CNT_NONFINITE 0 /* beams dropped: NaN anywhere, inf in oy or the sensor position */
+#define B2S_CNT_NONFINITE 0 /* beams dropped: a NaN coordinate (int(nan) -> ValueError in the reference) */
 #define B2S_CNT_TOO_LONG 1  /* beams dropped: longer than B2S_MAX_PATH_CELLS */
 #define B2S_CNT_SKIPPED_INF 2 /* beams skipped because ox is +-inf ([MAP]:30), not an error */
+#define B2S_CNT_OVERFLOW 3  /* beams dropped: inf in oy or the sensor position (int(inf) -> OverflowError) */
 #define B2S_CNT_WORDS 4
 
 int b2s_version(void);
@@ -100,6 +101,18 @@ int b2s_grid_raycast_ws(int32_t *hit, int32_t *miss, int xw, int yw, double cell
                         double off_x, double off_y, const float *ox, const float *oy,
                         const float *cx, const float *cy, int scans, int beams, int32_t *counters,
                         void *workspace, void *stream);
+
+/* Fused scan ingestion -- replaces laserToNumpy ([SLAM]:115-123), u2T(xEst).dot(np_msg) ([SLAM]:130-137,89)
+ * and Mapping.update ([MAP]:22-51) in one kernel: raw ranges [scans][beams] float32 and, per scan,
+ * pose4 = (x, y, cos yaw, sin yaw) float64; beam_cs [beams][2] = cos / sin of the beam angles
+ * (np.cos / np.sin of np.linspace(angle_min, angle_max, beams), computed by the caller exactly as the
+ * reference does).  Endpoints are formed in float64 with the reference's operation order; +inf ranges are
+ * replaced by clamp_inf_to when it is > 0 (MAX_LASER_RANGE = 30, [SLAM]:18,119).  Half the input bytes of
+ * the endpoint form.  Requires a workspace (see b2s_grid_raycast_ws). */
+int b2s_grid_raycast_ranges(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m,
+                            double off_x, double off_y, const float *ranges, const double *pose4,
+                            const double *beam_cs, double clamp_inf_to, int scans, int beams,
+                            int32_t *counters, void *workspace, void *stream);
 
 /* Screening of a batch before it is applied: flags[0] |= 1 if a NaN is present, flags[1] |= 1 if
  * oy or a sensor position holds an inf -- the values int() raises on in [MAP]:33-36 (ValueError /
@@ -182,6 +195,11 @@ int b2s_mapping_reset(b2s_mapping *map);
  * not NULL it receives the refreshed occupancy [xw][yw]. */
 int b2s_mapping_update(b2s_mapping *map, const float *ox, const float *oy, const float *cx,
                        const float *cy, int scans, int beams, int8_t *pmap_out);
+/* The same for raw scans (fused ingestion, see b2s_grid_raycast_ranges): ranges [scans][beams], pose4
+ * [scans][4], beam_cs [beams][2] on the host. */
+int b2s_mapping_update_ranges(b2s_mapping *map, const float *ranges, const double *pose4,
+                              const double *beam_cs, double clamp_inf_to, int scans, int beams,
+                              int8_t *pmap_out);
 /* Snapshot to host; any pointer may be NULL. */
 int b2s_mapping_read(b2s_mapping *map, int32_t *hit, int32_t *miss, float *datamap, int8_t *pmap);
 /* The planes themselves, for layer-1 calls and collectives. */

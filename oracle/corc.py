@@ -34,6 +34,8 @@ def lib():
         L.orc_bresenham.restype = i64
         L.orc_grid_raycast.argtypes = [vp, vp, i32, i32, dbl, dbl, dbl, vp, vp, vp, vp, i32, i32]
         L.orc_grid_raycast.restype = i64
+        L.orc_grid_raycast_ranges.argtypes = [vp, vp, i32, i32, dbl, dbl, dbl, vp, vp, vp, dbl, i32, i32]
+        L.orc_grid_raycast_ranges.restype = i64
         L.orc_grid_finalize.argtypes = [vp, vp, i64, dbl, dbl, dbl, vp, vp]
         L.orc_grid_finalize.restype = None
         _lib = L
@@ -93,6 +95,20 @@ def grid_raycast(hit, miss, cells_per_m, off_x, off_y, ox, oy, cx, cy):
     K, N = ox.shape
     v = lib().orc_grid_raycast(_p(hit), _p(miss), hit.shape[0], hit.shape[1], float(cells_per_m),
                                float(off_x), float(off_y), _p(ox), _p(oy), _p(cx), _p(cy), K, N)
+    if v < 0:
+        raise ValueError("non-finite coordinate")
+    return int(v)
+
+
+def grid_raycast_ranges(hit, miss, cells_per_m, off_x, off_y, ranges, pose4, beam_cs, clamp=30.0):
+    """Raw scans: ranges (K,N) float32, pose4 (K,4) = x, y, cos yaw, sin yaw, beam_cs (N,2).  Returns visits."""
+    ranges = np.ascontiguousarray(np.atleast_2d(ranges), dtype=np.float32)
+    pose4 = np.ascontiguousarray(np.atleast_2d(pose4), dtype=np.float64)
+    beam_cs = np.ascontiguousarray(beam_cs, dtype=np.float64)
+    K, N = ranges.shape
+    v = lib().orc_grid_raycast_ranges(_p(hit), _p(miss), hit.shape[0], hit.shape[1], float(cells_per_m),
+                                      float(off_x), float(off_y), _p(ranges), _p(pose4), _p(beam_cs),
+                                      float(clamp or 0.0), K, N)
     if v < 0:
         raise ValueError("non-finite coordinate")
     return int(v)

@@ -205,10 +205,48 @@ def mapping_golden():
     np.savez_compressed(os.path.join(OUT, "mapping.npz"), **blob)
 
 
+class _Scan(object):
+    """Duck-typed sensor_msgs/LaserScan."""
+
+    def __init__(self, ranges, angle_min, angle_max):
+        self.ranges = list(ranges)
+        self.angle_min = angle_min
+        self.angle_max = angle_max
+
+
+def ingestion_golden():
+    """(vii) the node's scan ingestion around Mapping.update: laserToNumpy (inf -> 30 m) + u2T(xEst).dot(np_msg)
+    (slam_ekf.py:89-90, 115-137), executed with the reference's own functions on raw float32 ranges."""
+    import math
+    Node, Mapping = ref_loader.load_slam_node_class()
+    rng = np.random.Generator(np.random.PCG64(8401))
+    K, N = 8, 120
+    ranges = np.clip(synth.noisy(rng, synth.clean_ranges(rng, K, N)), 0.1, 30.0).astype(np.float32)
+    ranges[1, 7] = np.inf            # clamped to MAX_LASER_RANGE = 30: ray leaves the 20 m map
+    ranges[3, 50:53] = np.inf
+    poses = np.stack([rng.uniform(-6, 6, K), rng.uniform(-6, 6, K), rng.uniform(-math.pi, math.pi, K)], axis=1)
+    m = Mapping(200, 200, 0.1)
+    oxs, oys = [], []
+    for k in range(K):
+        np_msg = Node.laserToNumpy(None, _Scan(ranges[k].tolist(), -math.pi, math.pi))
+        # the node passes xEst[:3] as a (3,1) column; NumPy >= 1.24 refuses to build u2T's 2x3 array from
+        # 1-element arrays, so the pose goes in as three scalars -- same arithmetic
+        xEst = poses[k]
+        obs = Node.u2T(None, xEst[:3]).dot(np_msg)
+        pm = m.update(obs[0], obs[1], float(xEst[0]), float(xEst[1]))
+        oxs.append(obs[0])
+        oys.append(obs[1])
+    np.savez_compressed(os.path.join(OUT, "ingestion.npz"), ranges=ranges, poses=poses, angle_min=-math.pi,
+                        angle_max=math.pi, ox=np.array(oxs), oy=np.array(oys), datamap=np.array(m.datamap),
+                        pmap=np.array(pm).astype(np.int8))
+    print("ingestion: occupied", int((np.array(pm) == 100).sum()))
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference tree not found at %s" % ref_loader.REF_ROOT)
     os.makedirs(OUT, exist_ok=True)
+    ingestion_golden()
     bresenham_golden()
     nearest_and_fit_golden()
     mapping_golden()

@@ -188,9 +188,53 @@ static inline int64_t to_cell(double v, double cells_per_m, double off)
     return (int64_t)(cells_per_m * (v + off));
 }
 
-/* [MAP]:22-51 in integer form: K scans x N beams into hit/miss [xw][yw] (x-major).
- * Beams whose ox is +-inf are skipped ([MAP]:30).  Returns in-grid cell visits, or -1 on a
- * non-finite coordinate the reference would raise on (NaN anywhere, inf in oy / centre). */
+/* One beam of [MAP]:29-50 in integer form; endpoints and sensor position in float64 world coordinates.
+ * Returns 0, or -1 on a coordinate the reference would raise on (NaN anywhere, inf in fy / centre). */
+static int raycast_beam(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m, double off_x,
+                        double off_y, double fx, double fy, double fcx, double fcy, int64_t *visits)
+{
+    if (isinf(fx)) return 0;                                   /* [MAP]:30 */
+    if (isnan(fx) || !isfinite(fy) || !isfinite(fcx) || !isfinite(fcy)) return -1;
+    int64_t x0 = to_cell(fcx, cells_per_m, off_x), y0 = to_cell(fcy, cells_per_m, off_y);
+    int64_t x1 = to_cell(fx, cells_per_m, off_x), y1 = to_cell(fy, cells_per_m, off_y);
+    if (x0 == x1 && y0 == y1) return 0;
+    const int steep = llabs(y1 - y0) > llabs(x1 - x0);
+    if (steep) {
+        int64_t t = x0; x0 = y0; y0 = t;
+        t = x1; x1 = y1; y1 = t;
+    }
+    const int flipped = x0 > x1;
+    if (flipped) {
+        int64_t t = x0; x0 = x1; x1 = t;
+        t = y0; y0 = y1; y1 = t;
+    }
+    const int64_t span = x1 - x0;
+    const double slope = (double)llabs(y1 - y0) / (double)span;
+    const int64_t inc = (y0 < y1) ? 1 : -1;
+    /* the endpoint (obstacle) is the last canonical cell unless the trace was flipped */
+    const int64_t hit_k = flipped ? 0 : span;
+    double acc = 0.0;
+    int64_t minor = y0;
+    for (int64_t k = 0; k <= span; ++k) {
+        const int64_t major = x0 + k;
+        const int64_t px = steep ? minor : major;
+        const int64_t py = steep ? major : minor;
+        if (px >= 0 && px < xw && py >= 0 && py < yw) {
+            const size_t cell = (size_t)px * (size_t)yw + (size_t)py;
+            if (k == hit_k) hit[cell] += 1; else miss[cell] += 1;
+            ++*visits;
+        }
+        acc += slope;
+        if (acc >= 0.5) {
+            minor += inc;
+            acc -= 1.0;
+        }
+    }
+    return 0;
+}
+
+/* [MAP]:22-51 in integer form: K scans x N beams into hit/miss [xw][yw] (x-major), float32 endpoints.
+ * Returns in-grid cell visits, or -1 on a non-finite coordinate the reference would raise on. */
 int64_t orc_grid_raycast(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m,
                          double off_x, double off_y, const float *ox, const float *oy,
                          const float *cx, const float *cy, int scans, int beams)
@@ -199,48 +243,31 @@ int64_t orc_grid_raycast(int32_t *hit, int32_t *miss, int xw, int yw, double cel
     for (int s = 0; s < scans; ++s) {
         const double fcx = (double)cx[s], fcy = (double)cy[s];
         if (!isfinite(fcx) || !isfinite(fcy)) return -1;
-        const int64_t pcx = to_cell(fcx, cells_per_m, off_x);
-        const int64_t pcy = to_cell(fcy, cells_per_m, off_y);
+        for (int b = 0; b < beams; ++b)
+            if (raycast_beam(hit, miss, xw, yw, cells_per_m, off_x, off_y, (double)ox[(size_t)s * beams + b],
+                             (double)oy[(size_t)s * beams + b], fcx, fcy, &visits))
+                return -1;
+    }
+    return visits;
+}
+
+/* Raw scans: laserToNumpy (slam_ekf.py:115-123) + u2T(xEst).dot(np_msg) (slam_ekf.py:130-137,89) + the update,
+ * per beam in float64, products and sums rounded separately, left to right.  pose4 [scans][4] = x, y,
+ * cos(yaw), sin(yaw); beam_cs [beams][2] = cos, sin of the beam angle; clamp > 0 replaces +inf ranges. */
+int64_t orc_grid_raycast_ranges(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m,
+                                double off_x, double off_y, const float *ranges, const double *pose4,
+                                const double *beam_cs, double clamp, int scans, int beams)
+{
+    int64_t visits = 0;
+    for (int s = 0; s < scans; ++s) {
+        const double x = pose4[4 * s], y = pose4[4 * s + 1], cw = pose4[4 * s + 2], sw = pose4[4 * s + 3];
         for (int b = 0; b < beams; ++b) {
-            const double fx = (double)ox[(size_t)s * beams + b];
-            const double fy = (double)oy[(size_t)s * beams + b];
-            if (isinf(fx)) continue;
-            if (isnan(fx) || !isfinite(fy)) return -1;
-            int64_t x0 = pcx, y0 = pcy;
-            int64_t x1 = to_cell(fx, cells_per_m, off_x), y1 = to_cell(fy, cells_per_m, off_y);
-            if (x0 == x1 && y0 == y1) continue;
-            const int steep = llabs(y1 - y0) > llabs(x1 - x0);
-            if (steep) {
-                int64_t t = x0; x0 = y0; y0 = t;
-                t = x1; x1 = y1; y1 = t;
-            }
-            const int flipped = x0 > x1;
-            if (flipped) {
-                int64_t t = x0; x0 = x1; x1 = t;
-                t = y0; y0 = y1; y1 = t;
-            }
-            const int64_t span = x1 - x0;
-            const double slope = (double)llabs(y1 - y0) / (double)span;
-            const int64_t inc = (y0 < y1) ? 1 : -1;
-            /* the endpoint (obstacle) is the last canonical cell unless the trace was flipped */
-            const int64_t hit_k = flipped ? 0 : span;
-            double acc = 0.0;
-            int64_t minor = y0;
-            for (int64_t k = 0; k <= span; ++k) {
-                const int64_t major = x0 + k;
-                const int64_t px = steep ? minor : major;
-                const int64_t py = steep ? major : minor;
-                if (px >= 0 && px < xw && py >= 0 && py < yw) {
-                    const size_t cell = (size_t)px * (size_t)yw + (size_t)py;
-                    if (k == hit_k) hit[cell] += 1; else miss[cell] += 1;
-                    ++visits;
-                }
-                acc += slope;
-                if (acc >= 0.5) {
-                    minor += inc;
-                    acc -= 1.0;
-                }
-            }
+            double r = (double)ranges[(size_t)s * beams + b];
+            if (clamp > 0.0 && r == INFINITY) r = clamp;
+            const double px = beam_cs[2 * b] * r, py = beam_cs[2 * b + 1] * r;
+            const double fx = (cw * px + (-sw) * py) + x;
+            const double fy = (sw * px + cw * py) + y;
+            if (raycast_beam(hit, miss, xw, yw, cells_per_m, off_x, off_y, fx, fy, x, y, &visits)) return -1;
         }
     }
     return visits;

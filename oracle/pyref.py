@@ -284,6 +284,15 @@ def laser_to_points(ranges, angle_min, angle_max, clamp_inf_to=None):
     return pc
 
 
+def scan_to_world(ranges, pose, angle_min, angle_max, clamp_inf_to=30):
+    """W12 slam_ekf.py:89: obs = u2T(xEst[:3]).dot(laserToNumpy(msg)) -> world-frame (ox, oy), float64."""
+    x, y, w = (float(v) for v in pose)
+    pc = laser_to_points(ranges, angle_min, angle_max, clamp_inf_to)
+    t2 = np.array([[math.cos(w), -math.sin(w), x], [math.sin(w), math.cos(w), y]])  # u2T, slam_ekf.py:130-137
+    obs = t2.dot(pc)
+    return obs[0], obs[1]
+
+
 def compose_pose(state, t_mat):
     """One step of the odometry chain, [ICP]:185-190 / W9 localization.py:79-83."""
     x, y, th = state

@@ -85,6 +85,7 @@ def _install_ros_stubs():
         ("sensor_msgs", ["LaserScan"]),
         ("nav_msgs", ["Odometry", "OccupancyGrid"]),
         ("geometry_msgs", ["TransformStamped"]),
+        ("visualization_msgs", ["MarkerArray", "Marker"]),
     ):
         top = types.ModuleType(pkg)
         msg = types.ModuleType(pkg + ".msg")
@@ -93,6 +94,10 @@ def _install_ros_stubs():
         top.msg = msg
         sys.modules[pkg] = top
         sys.modules[pkg + ".msg"] = msg
+    srv = types.ModuleType("nav_msgs.srv")
+    srv.GetMap = _Anything
+    sys.modules["nav_msgs"].srv = srv
+    sys.modules["nav_msgs.srv"] = srv
 
     if not hasattr(np, "int"):
         np.int = int  # removed in NumPy 1.24; the reference uses dtype=np.int
@@ -170,3 +175,31 @@ def load_mapping_classes():
 def load_mapping_online_classes():
     """(Mapping, bresenham) from w12-mapping-online: endpoint weight +4."""
     return _load_mapping_from(W12_ONLINE, "w4")
+
+
+def load_slam_node_class():
+    """SLAM_EKF from w12-mapping slam_ekf.py, for its laserToNumpy / u2T / T2u helpers (the steps
+    around the hot path).  Sibling modules it imports are stubbed except `mapping` (the real one)."""
+    _install_ros_stubs()
+    Mapping, _ = load_mapping_classes()
+    stubs = {}
+    for name, attrs in (("icp", {"ICP": _Anything}),
+                        ("ekf_lm", {"EKF": _Anything, "STATE_SIZE": 3}),
+                        ("extraction", {"LandMarkSet": _Anything, "Extraction": _Anything}),
+                        ("mapping", {"Mapping": Mapping})):
+        mod = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(mod, k, v)
+        stubs[name] = mod
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        node = _exec_module("_ref_slam_ekf", os.path.join(W12_MAPPING, "slam_ekf.py"), True)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    node.__dict__["print"] = lambda *a, **k: None
+    return node.SLAM_EKF, Mapping

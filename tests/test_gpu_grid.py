@@ -284,7 +284,7 @@ def test_clipping_out_of_grid_and_counters(env):
         cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
         env.dev.grid_raycast(hit, miss, S, Hx, Hy, *[torch.from_numpy(a).cuda() for a in (ox2, oy2, cx, cy)],
                              counters=cnt, workspace=ws)
-        assert cnt.tolist() == [2, 1, 1, 0]
+        assert cnt.tolist() == [1, 1, 1, 1]   # NaN, too long, inf-skipped, inf where int() overflows
 
 
 def test_cfg5_shape_smoke(env):
@@ -301,3 +301,52 @@ def test_cfg5_shape_smoke(env):
     nz = np.nonzero(oh | om)
     assert np.array_equal(hit.cpu().numpy()[nz], oh[nz]) and np.array_equal(miss.cpu().numpy()[nz], om[nz])
     assert int(miss.sum().item()) == int(om.sum())
+
+
+# ----------------------------------------------------------------------------- fused ingestion
+
+def test_update_scans_reproduces_the_reference_node(env):
+    """Raw ranges + poses through the fused kernel == the reference node's laserToNumpy + u2T.dot + update."""
+    import math
+    z = load_golden("ingestion.npz")
+    m = env.b2slam.Mapping(200, 200, 0.1)
+    pm = m.update_scans(z["ranges"], z["poses"], float(z["angle_min"]), float(z["angle_max"]))
+    assert np.array_equal(pm, z["pmap"])
+    np.testing.assert_allclose(m.datamap, z["datamap"], rtol=1e-5, atol=1e-6)
+    hit, miss = m.counts()
+    from b2slam import scan
+    oh = np.zeros((200, 200), dtype=np.int32)
+    om = np.zeros((200, 200), dtype=np.int32)
+    env.corc.grid_raycast_ranges(oh, om, 10.0, 10.0, 10.0, z["ranges"], scan.pose_table(z["poses"]),
+                                 scan.beam_table(-math.pi, math.pi, z["ranges"].shape[1]), 30.0)
+    assert np.array_equal(hit, oh) and np.array_equal(miss, om)
+
+
+def test_update_scans_cfg3_vs_oracle_and_errors(env):
+    import math
+    from b2slam import scan
+    G, K, N = 4096, 300, 1080
+    rng = np.random.Generator(np.random.PCG64(12001))
+    ranges = env.synth.noisy(rng, env.synth.clean_ranges(rng, K, N)).astype(np.float32)
+    ranges[5, 100:110] = np.inf                              # clamped to 30 m
+    poses = np.stack([rng.uniform(-60, 60, K), rng.uniform(-60, 60, K), rng.uniform(-math.pi, math.pi, K)], axis=1)
+    m = env.b2slam.Mapping(G, G, 0.05)
+    pm = m.update_scans(ranges, poses, -math.pi, math.pi)
+    oh = np.zeros((G, G), dtype=np.int32)
+    om = np.zeros((G, G), dtype=np.int32)
+    env.corc.grid_raycast_ranges(oh, om, 20.0, 102.4, 102.4, ranges, scan.pose_table(poses),
+                                 scan.beam_table(-math.pi, math.pi, N), 30.0)
+    hit, miss = m.counts()
+    assert np.array_equal(hit, oh) and np.array_equal(miss, om)
+    assert np.array_equal(pm, env.corc.grid_finalize(oh, om)[1])
+    bad = ranges.copy()
+    bad[200, 3] = np.nan
+    with pytest.raises(ValueError):
+        m.update_scans(bad, poses, -math.pi, math.pi)
+    h2, m2 = m.counts()
+    assert np.array_equal(h2, oh) and np.array_equal(m2, om)   # rejected batch rolled back exactly
+    # without the clamp an infinite range makes ox infinite (beam skipped) or oy infinite (OverflowError)
+    with pytest.raises((OverflowError, ValueError)):
+        m.update_scans(ranges, poses, -math.pi, math.pi, clamp_inf_to=None)
+    h2, m2 = m.counts()
+    assert np.array_equal(h2, oh) and np.array_equal(m2, om)

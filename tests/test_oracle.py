@@ -181,3 +181,23 @@ def test_grid_rejects_nan():
     miss = np.zeros((8, 8), dtype=np.int32)
     with pytest.raises(ValueError):
         corc.grid_raycast(hit, miss, 1.0, 4.0, 4.0, [[np.nan]], [[0.0]], [0.0], [0.0])
+
+
+# ----------------------------------------------------------------------------- scan ingestion (A8 + u2T)
+
+def test_ingestion_oracle_matches_reference_node():
+    """laserToNumpy + u2T(xEst).dot(np_msg) + Mapping.update as run by the reference node (golden)."""
+    import math
+    import b2slam.scan as scan
+    z = load_golden("ingestion.npz")
+    K, N = z["ranges"].shape
+    for k in range(K):
+        ox, oy = pyref.scan_to_world(z["ranges"][k], z["poses"][k], float(z["angle_min"]), float(z["angle_max"]))
+        assert np.array_equal(ox, z["ox"][k]) and np.array_equal(oy, z["oy"][k])   # literal form: bit-equal
+    hit = np.zeros((200, 200), dtype=np.int32)
+    miss = np.zeros((200, 200), dtype=np.int32)
+    corc.grid_raycast_ranges(hit, miss, 10.0, 10.0, 10.0, z["ranges"], scan.pose_table(z["poses"]),
+                             scan.beam_table(-math.pi, math.pi, N), 30.0)
+    score, pmap = corc.grid_finalize(hit, miss)
+    np.testing.assert_allclose(score, z["datamap"], rtol=1e-12, atol=0)
+    assert np.array_equal(pmap, z["pmap"])
