@@ -74,3 +74,16 @@ def test_shard_bounds_cover_everything_once():
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
     assert bdist.sequence_pair_bounds(10000, 0, 1) == (0, 9999)
+
+
+def test_pose_table_uses_the_reference_trigonometry():
+    """u2T calls math.cos / math.sin; the vectorised table must hold the very same doubles."""
+    rng = np.random.Generator(np.random.PCG64(8))
+    poses = np.stack([rng.uniform(-80, 80, 20000), rng.uniform(-80, 80, 20000), rng.uniform(-50, 50, 20000)], axis=1)
+    tab = scan.pose_table(poses)
+    assert np.array_equal(tab[:, 2], np.array([math.cos(w) for w in poses[:, 2]]))
+    assert np.array_equal(tab[:, 3], np.array([math.sin(w) for w in poses[:, 2]]))
+    assert np.array_equal(tab[:, :2], poses[:, :2])
+    cs = scan.beam_table(-math.pi, math.pi, 1080)
+    a = np.linspace(-math.pi, math.pi, 1080)
+    assert np.array_equal(cs[:, 0], np.cos(a)) and np.array_equal(cs[:, 1], np.sin(a))
