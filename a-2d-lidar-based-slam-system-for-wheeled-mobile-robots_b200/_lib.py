@@ -45,6 +45,10 @@ SIGNATURES = {
     "b2s_grid_finalize": (_i32, [_vp, _vp, _i32, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
     "b2s_grid_pack_ros": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "b2s_bresenham_paths": (_i32, [_vp, _i32, _vp, _vp, _vp]),
+    "b2s_pose_chain": (_i32, [_vp, _i32, _dbl, _dbl, _dbl, _vp, _vp]),
+    "b2s_pose_chain_host": (_i32, [_vp, _i32, _dbl, _dbl, _dbl, _vp]),
+    "b2s_virtual_scan": (_i32, [_vp, _vp, _i32, _dbl, _dbl, _dbl, _dbl, _dbl, _i32, _dbl, _vp, _vp]),
+    "b2s_virtual_scan_host": (_i32, [_vp, _vp, _i32, _dbl, _dbl, _dbl, _dbl, _dbl, _i32, _dbl, _vp]),
     "b2s_grid_allreduce": (_i32, [_vp, _vp, _sz, _vp, _vp]),
     "b2s_grid_merge_p2p": (_i32, [_vp, _vp, _vp, _i32, _sz, _sz, _vp, _vp, _dbl, _dbl, _dbl, _vp]),
     "b2s_device_alloc": (_i32, [_pp, _sz]),
@@ -68,6 +72,7 @@ SIGNATURES = {
     "b2s_mapping_update": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "b2s_mapping_update_ranges": (_i32, [_vp, _vp, _vp, _vp, _dbl, _i32, _i32, _vp]),
     "b2s_mapping_read": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "b2s_mapping_write": (_i32, [_vp, _vp, _vp]),
     "b2s_mapping_planes": (_i32, [_vp, _pp, _pp, _pp]),
     "b2s_bresenham_host": (_i32, [_vp, _i32, _vp, _vp]),
 }

@@ -568,6 +568,17 @@ extern "C" int b2s_mapping_read(b2s_mapping *m, int32_t *hit, int32_t *miss, flo
     return B2S_OK;
 }
 
+extern "C" int b2s_mapping_write(b2s_mapping *m, const int32_t *hit, const int32_t *miss)
+{
+    B2S_REQUIRE(m && hit && miss, "b2s_mapping_write: null pointer");
+    DeviceGuard g(m->device);
+    const size_t plane = (size_t)m->xw * m->yw * sizeof(int32_t);
+    B2S_CUDA(cudaMemcpyAsync(m->hit, hit, plane, cudaMemcpyHostToDevice, m->stream));
+    B2S_CUDA(cudaMemcpyAsync(m->miss, miss, plane, cudaMemcpyHostToDevice, m->stream));
+    B2S_CUDA(cudaStreamSynchronize(m->stream));
+    return B2S_OK;
+}
+
 extern "C" int b2s_mapping_planes(b2s_mapping *m, int32_t **hit, int32_t **miss, void **stream)
 {
     B2S_REQUIRE(m, "b2s_mapping_planes: null handle");

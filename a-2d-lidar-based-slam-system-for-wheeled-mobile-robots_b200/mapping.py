@@ -147,6 +147,32 @@ class Mapping(object):
         _lib.check(self._L.b2s_mapping_read(self._h, None, None, None, _lib.ptr(p)))
         return p
 
+    # ------------------------------------------------------------------ checkpoint
+
+    def save(self, path):
+        """Write the int32 count planes and the map parameters to an .npz -- the whole state of the
+        object (the reference keeps its map only in process memory)."""
+        hit, miss = self.counts()
+        np.savez_compressed(path, hit=hit, miss=miss, xw=self.xw, yw=self.yw, xyreso=self.xyreso,
+                            hit_weight=self.hit_weight, miss_weight=self.miss_weight,
+                            occ_threshold=self.occ_threshold)
+
+    @classmethod
+    def load(cls, path, device=-1):
+        """Rebuild a Mapping from save(): same parameters, count planes restored bit for bit."""
+        z = np.load(path)
+        m = cls(int(z["xw"]), int(z["yw"]), float(z["xyreso"]), float(z["hit_weight"]), float(z["miss_weight"]),
+                float(z["occ_threshold"]), device=device)
+        m.set_counts(z["hit"], z["miss"])
+        return m
+
+    def set_counts(self, hit, miss):
+        """Overwrite the device planes with int32 (xw, yw) host arrays (checkpoint restore)."""
+        hit = np.ascontiguousarray(hit, dtype=np.int32).reshape(self.xw, self.yw)
+        miss = np.ascontiguousarray(miss, dtype=np.int32).reshape(self.xw, self.yw)
+        _lib.check(self._L.b2s_mapping_write(self._h, _lib.ptr(hit), _lib.ptr(miss)))
+        _lib.check(self._L.b2s_mapping_read(self._h, None, None, None, _lib.ptr(self._pmap8)))
+
     def reset(self):
         _lib.check(self._L.b2s_mapping_reset(self._h))
         self._pmap8.fill(50)

@@ -72,3 +72,30 @@ def pose_table(poses):
     np.cos(poses[:, 2], out=out[:, 2])
     np.sin(poses[:, 2], out=out[:, 3])
     return out
+
+
+def compose_odometry_gpu(state, transforms):
+    """compose_odometry on the device (b2s_pose_chain): a parallel prefix instead of the sequential loop.
+    Agrees with the loop to summation order (~1e-13 on a 10k-pair chain)."""
+    from b2slam import _lib
+    T = np.ascontiguousarray(transforms, dtype=np.float64).reshape(-1, 9)
+    traj = np.empty((T.shape[0] + 1, 3))
+    _lib.require_device()
+    _lib.check(_lib.lib().b2s_pose_chain_host(_lib.ptr(T) if T.shape[0] else None, T.shape[0], float(state[0]),
+                                              float(state[1]), float(state[2]), _lib.ptr(traj)))
+    return traj
+
+
+def virtual_scan(obstacle_xy, pose, angle_min, angle_increment, beams, far_range=100.0):
+    """laserEstimation, W9 localization.py:128-150, on the device: obstacle_xy (2, C) world coordinates
+    of the occupied map cells (self.obstacle), pose (x, y, yaw) -> ranges (beams,) float64."""
+    from b2slam import _lib
+    ox = np.ascontiguousarray(obstacle_xy[0], dtype=np.float64)
+    oy = np.ascontiguousarray(obstacle_xy[1], dtype=np.float64)
+    out = np.empty(int(beams))
+    _lib.require_device()
+    _lib.check(_lib.lib().b2s_virtual_scan_host(_lib.ptr(ox) if ox.size else None, _lib.ptr(oy) if oy.size else None,
+                                                ox.shape[0], float(pose[0]), float(pose[1]), float(pose[2]),
+                                                float(angle_min), float(angle_increment), int(beams),
+                                                float(far_range), _lib.ptr(out)))
+    return out

@@ -135,6 +135,25 @@ int b2s_grid_pack_ros(const int8_t *pmap, int xw, int yw, int8_t *data, void *st
 int b2s_bresenham_paths(const int32_t *segs, int count, const int64_t *offsets, int32_t *cells_xy,
                         void *stream);
 
+/* Odometry chain over a stream of per-pair transforms -- replaces the sequential accumulation of
+ * [ICP]:185-190 / W9 localization.py:79-83 (x += cos(th) T02 - sin(th) T12; y += sin(th) T02 + cos(th) T12;
+ * th += atan2(T10, T00)) with a parallel prefix.  T [pairs][9] row-major, traj [pairs+1][3] = x, y, th
+ * (traj[0] is the start state).  Equal to the sequential float64 loop up to summation order (~1e-13). */
+int b2s_pose_chain(const double *T, int pairs, double x0, double y0, double th0, double *traj,
+                   void *stream);
+int b2s_pose_chain_host(const double *T, int pairs, double x0, double y0, double th0, double *traj);
+
+/* Virtual scan from the static map -- replaces laserEstimation, W9 localization.py:128-150: for every
+ * obstacle cell centre (obs_x, obs_y) the range hypot(x - ox, y - oy) is min-reduced into bearing bin
+ * int((atan2(oy - y, ox - x) - angle_min - yaw) / angle_increment), wrapped into [0, beams); bins nobody
+ * hits keep far_range (100.0 in the reference).  ranges [beams] float64. */
+int b2s_virtual_scan(const double *obs_x, const double *obs_y, int count, double x, double y,
+                     double yaw, double angle_min, double angle_increment, int beams,
+                     double far_range, double *ranges, void *stream);
+int b2s_virtual_scan_host(const double *obs_x, const double *obs_y, int count, double x, double y,
+                          double yaw, double angle_min, double angle_increment, int beams,
+                          double far_range, double *ranges);
+
 /* Sum of per-GPU count deltas (no reference counterpart: the reference is single-process).
  * In-place ncclAllReduce(int32, sum) of both planes on an existing communicator. */
 int b2s_grid_allreduce(int32_t *hit, int32_t *miss, size_t cells, void *nccl_comm, void *stream);
@@ -202,6 +221,8 @@ int b2s_mapping_update_ranges(b2s_mapping *map, const float *ranges, const doubl
                               int8_t *pmap_out);
 /* Snapshot to host; any pointer may be NULL. */
 int b2s_mapping_read(b2s_mapping *map, int32_t *hit, int32_t *miss, float *datamap, int8_t *pmap);
+/* Overwrite the count planes from host arrays [xw][yw] (checkpoint restore; the reference has none). */
+int b2s_mapping_write(b2s_mapping *map, const int32_t *hit, const int32_t *miss);
 /* The planes themselves, for layer-1 calls and collectives. */
 int b2s_mapping_planes(b2s_mapping *map, int32_t **hit, int32_t **miss, void **stream);
 /* bresenham(start,end).path on host arrays (segs [count][4], cells_xy sized by the caller). */

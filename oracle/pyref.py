@@ -300,3 +300,19 @@ def compose_pose(state, t_mat):
     nx = x + math.cos(th) * t_mat[0, 2] - math.sin(th) * t_mat[1, 2]
     ny = y + math.sin(th) * t_mat[0, 2] + math.cos(th) * t_mat[1, 2]
     return (nx, ny, th + dyaw)
+
+
+def virtual_scan(obstacle_xy, pose, angle_min, angle_increment, beams, far_range=100.0):
+    """laserEstimation, W9 localization.py:128-150: min range per bearing bin over the obstacle cells."""
+    x, y, yaw = (float(v) for v in pose)
+    ranges = [far_range] * beams
+    for i in range(len(obstacle_xy[0])):
+        dist = math.hypot(x - obstacle_xy[0][i], y - obstacle_xy[1][i])
+        index = int((math.atan2(obstacle_xy[1][i] - y, obstacle_xy[0][i] - x) - angle_min - yaw) / angle_increment)
+        while index > beams - 1:
+            index = index - beams
+        while index < 0:
+            index = index + beams
+        if dist < ranges[index]:
+            ranges[index] = dist
+    return np.array(ranges)

@@ -350,3 +350,20 @@ def test_update_scans_cfg3_vs_oracle_and_errors(env):
         m.update_scans(ranges, poses, -math.pi, math.pi, clamp_inf_to=None)
     h2, m2 = m.counts()
     assert np.array_equal(h2, oh) and np.array_equal(m2, om)
+
+
+# ----------------------------------------------------------------------------- checkpoint
+
+def test_checkpoint_roundtrip(env, tmp_path):
+    ox, oy, cx, cy = env.synth.grid_scans(5, 40, 360, half_extent_m=8.0)
+    m = env.b2slam.Mapping(400, 300, 0.05, hit_weight=4.0)
+    m.update_batch(ox[:20], oy[:20], cx[:20], cy[:20])
+    path = str(tmp_path / "map.npz")
+    m.save(path)
+    m2 = env.b2slam.Mapping.load(path)
+    assert (m2.xw, m2.yw, m2.xyreso, m2.hit_weight) == (400, 300, 0.05, 4.0)
+    assert all(np.array_equal(a, b) for a, b in zip(m.counts(), m2.counts()))
+    assert np.array_equal(m.occupancy(), m2.occupancy())
+    pa = m.update_batch(ox[20:], oy[20:], cx[20:], cy[20:]).copy()      # resumed map evolves identically
+    pb = m2.update_batch(ox[20:], oy[20:], cx[20:], cy[20:]).copy()
+    assert np.array_equal(pa, pb) and all(np.array_equal(a, b) for a, b in zip(m.counts(), m2.counts()))

@@ -142,3 +142,41 @@ def test_cfg4_shape_sample_vs_oracle(env):
     finally:
         env.lib.lib().b2s_tune(b"icp_prune", 1)
     assert np.array_equal(it3, it[:256]) and np.array_equal(T3, T[:256])
+
+
+# ----------------------------------------------------------------------------- adjacent steps
+
+def test_pose_chain_parallel_prefix_vs_sequential_loop(env):
+    from b2slam import scan
+    from oracle import pyref
+    xy, _ = env.synth.room_sequence(9001, 2001, 360)
+    T, _ = env.icp.process_batch(xy[:-1], xy[1:])
+    traj = scan.compose_odometry_gpu((0.5, -0.25, 0.1), T)
+    st = (0.5, -0.25, 0.1)
+    want = [st]
+    for t in T:
+        st = pyref.compose_pose(st, t)
+        want.append(st)
+    np.testing.assert_allclose(traj, np.array(want), rtol=0, atol=1e-10)
+    assert np.allclose(traj, scan.compose_odometry((0.5, -0.25, 0.1), T), rtol=0, atol=1e-10)
+    one = scan.compose_odometry_gpu((1.0, 2.0, 3.0), np.zeros((0, 3, 3)))
+    assert one.shape == (1, 3) and np.array_equal(one[0], [1.0, 2.0, 3.0])
+
+
+def test_virtual_scan_vs_reference_loop(env):
+    import math
+    from b2slam import scan
+    from oracle import pyref
+    rng = np.random.Generator(np.random.PCG64(17))
+    # obstacle cells of a 129 x 129 map at 0.155 m (course_agv_gazebo/config/map.yaml), walls + clutter
+    cells = np.argwhere((rng.random((129, 129)) < 0.03) | (np.arange(129)[:, None] % 128 == 0) | (np.arange(129)[None, :] % 128 == 0))
+    obstacle = np.vstack((cells[:, 0] * 0.155 - 10.0, cells[:, 1] * 0.155 - 10.0))
+    beams = 120
+    inc = 2 * math.pi / (beams - 1)
+    for pose in ((0.0, 0.0, 0.0), (3.2, -4.1, 1.3), (-7.7, 8.8, -2.9)):
+        got = scan.virtual_scan(obstacle, pose, -math.pi, inc, beams)
+        want = pyref.virtual_scan(obstacle, pose, -math.pi, inc, beams)
+        # same bins, same minima; CUDA's hypot differs from libm's by at most a couple of ulp
+        np.testing.assert_allclose(got, want, rtol=1e-14, atol=0)
+    empty = scan.virtual_scan(np.zeros((2, 0)), (0, 0, 0), -math.pi, inc, beams)
+    assert (empty == 100.0).all()
