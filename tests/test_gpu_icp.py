@@ -180,3 +180,41 @@ def test_virtual_scan_vs_reference_loop(env):
         np.testing.assert_allclose(got, want, rtol=1e-14, atol=0)
     empty = scan.virtual_scan(np.zeros((2, 0)), (0, 0, 0), -math.pi, inc, beams)
     assert (empty == 100.0).all()
+
+
+# ----------------------------------------------------------------------------- randomised sweep
+
+def test_random_icp_shapes_vs_oracle(env):
+    """Seeded fuzz over cloud sizes (down to one point), duplicated targets, collinear and far-offset clouds,
+    both search modes: identical iteration counts, T within 1e-9 (relative to the cloud scale)."""
+    rng = np.random.Generator(np.random.PCG64(777))
+    for trial in range(30):
+        n = int(rng.choice([1, 2, 3, 5, 16, 17, 31, 33, 64, 100, 127, 250]))
+        m = int(rng.choice([1, 2, 4, 15, 16, 17, 32, 48, 100, 129, 300]))
+        pairs = int(rng.integers(1, 5))
+        scale = float(rng.choice([0.5, 5.0, 40.0]))
+        tar = rng.normal(0, scale, (pairs, 2, m))
+        if trial % 3 == 0:                      # collinear wall
+            tar[:, 1, :] = 0.3 * tar[:, 0, :] + 1.0
+        if m > 3 and trial % 4 == 0:            # duplicated targets: lowest index must win
+            tar[:, :, m // 2] = tar[:, :, 0]
+            tar[:, :, m - 1] = tar[:, :, 0]
+        pick = rng.integers(0, m, (pairs, n))
+        src = np.take_along_axis(tar, np.broadcast_to(pick[:, None, :], (pairs, 2, n)), axis=2)
+        th = rng.uniform(-0.1, 0.1)
+        c, s = np.cos(th), np.sin(th)
+        src = np.stack([c * src[:, 0] - s * src[:, 1] + rng.uniform(-0.2, 0.2),
+                        s * src[:, 0] + c * src[:, 1] + rng.uniform(-0.2, 0.2)], axis=1)
+        src = src + rng.normal(0, 0.01 * scale, src.shape)
+        tar = np.ascontiguousarray(tar.astype(np.float32))
+        src = np.ascontiguousarray(src.astype(np.float32))
+        want_T, want_it = env.corc.icp_batch(tar, src, 30, 1e-3)
+        for prune in (1, 0):
+            assert env.lib.lib().b2s_tune(b"icp_prune", prune) == 0
+            try:
+                T, it = env.icp.process_batch(tar, src)
+            finally:
+                env.lib.lib().b2s_tune(b"icp_prune", 1)
+            assert np.array_equal(it, want_it), "trial %d n %d m %d prune %d" % (trial, n, m, prune)
+            np.testing.assert_allclose(T, want_T, rtol=0, atol=1e-9 * max(1.0, scale),
+                                       err_msg="trial %d n %d m %d prune %d" % (trial, n, m, prune))
