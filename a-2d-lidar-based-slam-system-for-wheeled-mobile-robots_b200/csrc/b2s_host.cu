@@ -37,6 +37,7 @@ int sm_count()
 extern int g_grid_variant;
 extern int g_icp_src_per_thread;
 extern int g_icp_prune;
+extern int g_icp_block;
 
 // Growable device / pinned-host staging buffer.
 struct Buf {
@@ -139,6 +140,11 @@ extern "C" int b2s_tune(const char *key, int value)
     if (strcmp(key, "grid_variant") == 0) {
         B2S_REQUIRE((value >= 1 && value <= 4) || value == 99, "b2s_tune: grid_variant must be 1..4");
         g_grid_variant = value;
+        return B2S_OK;
+    }
+    if (strcmp(key, "icp_block") == 0) {
+        B2S_REQUIRE(value == 0 || value == 16 || value == 32, "b2s_tune: icp_block must be 0, 16 or 32");
+        g_icp_block = value;
         return B2S_OK;
     }
     if (strcmp(key, "icp_prune") == 0) {

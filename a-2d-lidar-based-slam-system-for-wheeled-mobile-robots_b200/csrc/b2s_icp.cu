@@ -90,9 +90,9 @@ __device__ __forceinline__ void cta_rigid_fit(const double (&ax)[R], const doubl
     extra = v[8];
 }
 
-constexpr int NN_BLK = 16;  // targets per pruning block
+// Targets per pruning block: 16 is fastest at 360 beams, 32 at 1080 (measured); chosen per launch.
 
-template <typename TIn, int R, bool PRUNE>
+template <typename TIn, int R, bool PRUNE, int NN_BLK>
 __global__ void icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__restrict__ src_xy, int n,
                                  int m, int max_iter, double tol, double *__restrict__ T_out,
                                  int32_t *__restrict__ iters_out, int use_bulk)
@@ -385,8 +385,9 @@ rigid_fit_kernel(const double *__restrict__ src_xy, const double *__restrict__ t
 
 int g_icp_src_per_thread = 0;  // 0: choose per problem size; 2..4 force (tuning hook)
 int g_icp_prune = 1;           // 1: exact search with block pruning (default); 0: plain brute force
+int g_icp_block = 0;           // 0: 16 targets per pruning block up to 600 targets, 32 above; 16 / 32 force
 
-template <typename TIn, int R, bool PRUNE>
+template <typename TIn, int R, bool PRUNE, int NN_BLK>
 static int launch_icp_rp(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_src, int n_tar, int max_iter,
                         double tol, double *T_out, int32_t *iters_out, void *stream)
 {
@@ -399,14 +400,14 @@ static int launch_icp_rp(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_
     B2S_REQUIRE(smem <= 227 * 1024, "b2s_icp_batch: n_tar too large for shared memory");
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        B2S_CUDA(cudaFuncSetAttribute(icp_batch_kernel<TIn, R, PRUNE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        B2S_CUDA(cudaFuncSetAttribute(icp_batch_kernel<TIn, R, PRUNE, NN_BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
         configured = smem;
     }
     // bulk copy needs 16-byte aligned source and size: every pair's target block must qualify
     const size_t pair_bytes = (size_t)2 * n_tar * sizeof(TIn);
     const int use_bulk = ((uintptr_t)tar_xy % 16 == 0) && (pair_bytes % 16 == 0);
-    icp_batch_kernel<TIn, R, PRUNE><<<pairs, threads, smem, (cudaStream_t)stream>>>(
+    icp_batch_kernel<TIn, R, PRUNE, NN_BLK><<<pairs, threads, smem, (cudaStream_t)stream>>>(
         tar_xy, src_xy, n_src, n_tar, max_iter, tol, T_out, iters_out, use_bulk);
     B2S_CUDA(cudaGetLastError());
     return B2S_OK;
@@ -416,11 +417,15 @@ template <typename TIn, int R>
 static int launch_icp_r(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_src, int n_tar, int max_iter,
                         double tol, double *T_out, int32_t *iters_out, void *stream)
 {
-    // the block bounds live in the staging area: [ceil(m/16)][4] doubles must fit in 2*m*sizeof(TIn)
-    const bool fits = (size_t)((n_tar + NN_BLK - 1) / NN_BLK) * 32 <= (size_t)2 * n_tar * sizeof(TIn);
-    if (g_icp_prune && fits)
-        return launch_icp_rp<TIn, R, true>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream);
-    return launch_icp_rp<TIn, R, false>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream);
+    // the block bounds live in the staging area: [ceil(m/blk)][4] doubles must fit in 2*m*sizeof(TIn)
+    const int blk = (g_icp_block == 16 || g_icp_block == 32) ? g_icp_block : (n_tar <= 600 ? 16 : 32);
+    const bool fits = (size_t)((n_tar + blk - 1) / blk) * 32 <= (size_t)2 * n_tar * sizeof(TIn);
+    if (g_icp_prune && fits) {
+        if (blk == 16)
+            return launch_icp_rp<TIn, R, true, 16>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream);
+        return launch_icp_rp<TIn, R, true, 32>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream);
+    }
+    return launch_icp_rp<TIn, R, false, 16>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream);
 }
 
 template <typename TIn>

@@ -358,10 +358,10 @@ def bench_grid(args, rank, world, torch, devapi, bdist, synth):
                                    "scan streams sharded by rank; count deltas merged by one peer-memory kernel "
                                    "(reduce-scatter + finalize + all-gather over NVLink)" if p2p is not None else
                                    "scan streams sharded by rank, int32 count deltas all-reduced (NCCL)")},
-        "dtype": "int32 counts / f64 cell+error arithmetic",
+        "dtype": "int32 counts (f64 cell / error arithmetic)",
         "roofline": {"bound": "hbm", "kernel": "grid_raycast (+ fold of the transposed scratch plane)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": ray_avg_ms,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu, profiles/r1/grid_traffic.json)",
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": ray_avg_ms,
                      "cell_visits_per_s": visits / (ray_avg_ms * 1e-3)},
         "e2e": {"value": world * K * N * e2e_steps / e2e_s, "unit": "beams/s",
                 "h2d_bytes_per_step": 8 * K * N + 8 * K, "d2h_bytes_per_step": G * G,
