@@ -51,6 +51,11 @@ SIGNATURES = {
     "b2s_virtual_scan_host": (_i32, [_vp, _vp, _i32, _dbl, _dbl, _dbl, _dbl, _dbl, _i32, _dbl, _vp]),
     "b2s_grid_allreduce": (_i32, [_vp, _vp, _sz, _vp, _vp]),
     "b2s_grid_merge_p2p": (_i32, [_vp, _vp, _vp, _i32, _sz, _sz, _vp, _vp, _dbl, _dbl, _dbl, _vp]),
+    "b2s_grid_merge_p2p_tiles": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _dbl, _dbl,
+                                        _dbl, _vp]),
+    "b2s_grid_workspace_dirty": (_vp, [_vp]),
+    "b2s_grid_tile_count": (_i32, [_i32, _i32, ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
+    "b2s_grid_clear_dirty": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp]),
     "b2s_device_alloc": (_i32, [_pp, _sz]),
     "b2s_device_free": (_i32, [_vp]),
     "b2s_ipc_export": (_i32, [_vp, _vp]),

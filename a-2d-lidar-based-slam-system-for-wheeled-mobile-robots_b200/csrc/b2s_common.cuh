@@ -34,6 +34,15 @@ inline int cuda_fail(cudaError_t e, const char *what)
 
 int sm_count();
 
+// Dirty-tile bookkeeping of the ray-cast workspace: one byte per 64 x 64-cell tile of the grid.
+constexpr int GRID_TILE = 64;
+constexpr int GRID_WS_HEADER = 64;
+inline __host__ __device__ int grid_tiles(int w) { return (w + GRID_TILE - 1) / GRID_TILE; }
+inline size_t grid_dirty_bytes(int xw, int yw)
+{
+    return (((size_t)grid_tiles(xw) * grid_tiles(yw)) + 255) & ~(size_t)255;
+}
+
 int grid_raycast_signed(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m, double off_x,
                         double off_y, const float *ox, const float *oy, const float *cx, const float *cy,
                         int scans, int beams, int32_t *counters, void *workspace, int sign, void *stream);

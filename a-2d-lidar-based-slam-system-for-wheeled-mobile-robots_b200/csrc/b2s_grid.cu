@@ -316,10 +316,12 @@ grid_raycast_v3(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int xw, i
 // then folds the touched bounding box of the scratch plane into `miss` and re-zeroes it.
 // Integer adds commute, so the result is bit-identical.
 
-struct GridWorkspace {      // lives at the front of the caller-provided workspace
-    int bbox[4];            // atomicMax of (-xmin, xmax, -ymin, ymax) over y-major beams; reset to very negative
+struct GridWorkspace {      // lives at the front of the caller-provided workspace (GRID_WS_HEADER bytes)
+    int bbox[4];            // atomicMax of (-xmin, xmax, -ymin, ymax) over warps with y-major beams; reset to very negative
     int pad[12];
 };
+static_assert(sizeof(GridWorkspace) == GRID_WS_HEADER, "workspace header size");
+// layout of the workspace: [GridWorkspace][dirty map: 1 byte per 64x64 tile, padded to 256 B][scratch plane [yw][xw]]
 
 // One warp-step.  Everything that addresses memory is kept DOUBLED (key2 = 2*cell + plane bit) so the
 // run key, the plane selector and the byte offset (key2 * 2, minus the plane bit folded into the
@@ -416,8 +418,8 @@ __device__ __forceinline__ void load_beam(const ScanInput &in, long long i, int 
 template <int SIGN, bool FUSED>
 __global__ void __launch_bounds__(256, 8)
 grid_raycast_v4(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int32_t *__restrict__ scratch_t,
-                GridWorkspace *__restrict__ ws, int xw, int yw, double cells_per_m, double off_x, double off_y,
-                const ScanInput in, long long total, int beams, int32_t *counters)
+                GridWorkspace *__restrict__ ws, uint8_t *__restrict__ dirty, int xw, int yw, double cells_per_m,
+                double off_x, double off_y, const ScanInput in, long long total, int beams, int32_t *counters)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31;
@@ -441,12 +443,13 @@ grid_raycast_v4(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int32_t *
     if (live && (unsigned)b.hx < (unsigned)xw && (unsigned)b.hy < (unsigned)yw)
         atomicAdd(hit + (b.hx * yw + b.hy), SIGN);
 
-    // bounding box of what the y-major beams of this warp can touch in the scratch plane
-    const bool steep_live = live && b.steep;
-    if (__any_sync(0xffffffffu, steep_live)) {
+    // Bounding box (clipped to the grid) of everything this warp can touch.  It marks the 64 x 64-cell
+    // tiles the warp dirties (sparse zeroing / merging of the planes downstream) and, when the warp
+    // holds y-major beams, bounds the part of the transposed scratch plane that has to be folded back.
+    {
         const int very_neg = (int)0x80808080;
         int nx0 = very_neg, x1 = very_neg, ny0 = very_neg, y1 = very_neg;
-        if (steep_live) {
+        if (live) {
             nx0 = -max(0, min(b.sx, b.hx));
             x1 = min(xw - 1, max(b.sx, b.hx));
             ny0 = -max(0, min(b.sy, b.hy));
@@ -459,12 +462,15 @@ grid_raycast_v4(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int32_t *
             ny0 = max(ny0, __shfl_xor_sync(0xffffffffu, ny0, o));
             y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
         }
-        if (lane == 0) {
+        if (__any_sync(0xffffffffu, live && b.steep) && lane == 0) {
             atomicMax(&ws->bbox[0], nx0);
             atomicMax(&ws->bbox[1], x1);
             atomicMax(&ws->bbox[2], ny0);
             atomicMax(&ws->bbox[3], y1);
         }
+        const int tx0 = (-nx0) / GRID_TILE, tx1 = x1 / GRID_TILE, ty0 = (-ny0) / GRID_TILE, ty1 = y1 / GRID_TILE;
+        const int ny = ty1 - ty0 + 1, cnt = (tx1 - tx0 + 1) * ny, tiles_y = grid_tiles(yw);
+        for (int k = lane; k < cnt; k += 32) dirty[(tx0 + k / ny) * tiles_y + ty0 + k % ny] = 1;
     }
 
     const int wmaj = b.steep ? yw : xw;
@@ -692,7 +698,7 @@ extern "C" int b2s_grid_raycast(int32_t *hit, int32_t *miss, int xw, int yw, dou
 extern "C" size_t b2s_grid_workspace_bytes(int xw, int yw)
 {
     if (xw <= 0 || yw <= 0) return 0;
-    return sizeof(GridWorkspace) + (size_t)xw * yw * sizeof(int32_t);
+    return GRID_WS_HEADER + grid_dirty_bytes(xw, yw) + (size_t)xw * yw * sizeof(int32_t);
 }
 
 extern "C" int b2s_grid_workspace_init(void *workspace, int xw, int yw, void *stream)
@@ -700,8 +706,9 @@ extern "C" int b2s_grid_workspace_init(void *workspace, int xw, int yw, void *st
     B2S_REQUIRE(workspace && xw > 0 && yw > 0, "b2s_grid_workspace_init: bad arguments");
     B2S_REQUIRE((uintptr_t)workspace % 16 == 0, "b2s_grid_workspace_init: workspace must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    B2S_CUDA(cudaMemsetAsync(workspace, 0x80, sizeof(GridWorkspace), st));
-    B2S_CUDA(cudaMemsetAsync((char *)workspace + sizeof(GridWorkspace), 0, (size_t)xw * yw * sizeof(int32_t), st));
+    B2S_CUDA(cudaMemsetAsync(workspace, 0x80, GRID_WS_HEADER, st));
+    B2S_CUDA(cudaMemsetAsync((char *)workspace + GRID_WS_HEADER, 0,
+                             grid_dirty_bytes(xw, yw) + (size_t)xw * yw * sizeof(int32_t), st));
     return B2S_OK;
 }
 
@@ -724,10 +731,12 @@ static int raycast_v4_launch(int32_t *hit, int32_t *miss, int xw, int yw, double
     B2S_REQUIRE(blocks < (1ll << 31), "b2s_grid_raycast_ws: too many beams for one launch");
     cudaStream_t st = (cudaStream_t)stream;
     GridWorkspace *ws = (GridWorkspace *)workspace;
-    int32_t *scratch_t = (int32_t *)((char *)workspace + sizeof(GridWorkspace));
-#define B2S_V4(SG, FU)                                                                                           \
-    grid_raycast_v4<SG, FU><<<(unsigned)blocks, threads, 0, st>>>(hit, miss, scratch_t, ws, xw, yw, cells_per_m, \
-                                                                   off_x, off_y, in, total, beams, counters)
+    uint8_t *dirty = (uint8_t *)workspace + GRID_WS_HEADER;
+    int32_t *scratch_t = (int32_t *)((char *)workspace + GRID_WS_HEADER + grid_dirty_bytes(xw, yw));
+#define B2S_V4(SG, FU)                                                                                        \
+    grid_raycast_v4<SG, FU><<<(unsigned)blocks, threads, 0, st>>>(hit, miss, scratch_t, ws, dirty, xw, yw,    \
+                                                                   cells_per_m, off_x, off_y, in, total, beams, \
+                                                                   counters)
     if (sign >= 0) {
         if (fused) B2S_V4(1, true); else B2S_V4(1, false);
     } else {
@@ -738,7 +747,7 @@ static int raycast_v4_launch(int32_t *hit, int32_t *miss, int xw, int yw, double
     dim3 fgrid((xw + 31) / 32, (yw + 31) / 32);
     grid_fold_kernel<<<fgrid, 256, 0, st>>>(miss, scratch_t, ws, xw, yw);
     B2S_CUDA(cudaGetLastError());
-    B2S_CUDA(cudaMemsetAsync(ws, 0x80, sizeof(GridWorkspace), st));
+    B2S_CUDA(cudaMemsetAsync(ws, 0x80, GRID_WS_HEADER, st));
     return B2S_OK;
 }
 
@@ -785,6 +794,53 @@ extern "C" int b2s_grid_raycast_ws(int32_t *hit, int32_t *miss, int xw, int yw, 
                                 counters, stream);
     return grid_raycast_signed(hit, miss, xw, yw, cells_per_m, off_x, off_y, ox, oy, cx, cy, scans, beams,
                                counters, workspace, +1, stream);
+}
+
+namespace b2s {
+// Zero the tiles of `hit` / `miss` whose dirty byte is set, then clear the byte: brings a pair of delta
+// planes back to all-zero at a cost proportional to what the last ray-casts touched.
+__global__ void __launch_bounds__(256)
+grid_clear_dirty_kernel(int32_t *__restrict__ hit, int32_t *__restrict__ miss, uint8_t *__restrict__ dirty, int xw,
+                        int yw)
+{
+    const int tiles_y = grid_tiles(yw);
+    const int tile = blockIdx.x;
+    if (!dirty[tile]) return;
+    const int x0 = (tile / tiles_y) * GRID_TILE, y0 = (tile % tiles_y) * GRID_TILE;
+    for (int k = threadIdx.x; k < GRID_TILE * GRID_TILE; k += blockDim.x) {
+        const int x = x0 + k / GRID_TILE, y = y0 + k % GRID_TILE;
+        if (x < xw && y < yw) {
+            const size_t at = (size_t)x * yw + y;
+            hit[at] = 0;
+            miss[at] = 0;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) dirty[tile] = 0;
+}
+}  // namespace b2s
+
+extern "C" void *b2s_grid_workspace_dirty(void *workspace)
+{
+    return workspace ? (void *)((char *)workspace + GRID_WS_HEADER) : nullptr;
+}
+
+extern "C" int b2s_grid_tile_count(int xw, int yw, int *tiles_x, int *tiles_y)
+{
+    B2S_REQUIRE(xw > 0 && yw > 0, "b2s_grid_tile_count: grid size");
+    if (tiles_x) *tiles_x = grid_tiles(xw);
+    if (tiles_y) *tiles_y = grid_tiles(yw);
+    return B2S_OK;
+}
+
+extern "C" int b2s_grid_clear_dirty(int32_t *hit, int32_t *miss, int xw, int yw, void *workspace, void *stream)
+{
+    B2S_REQUIRE(hit && miss && workspace && xw > 0 && yw > 0, "b2s_grid_clear_dirty: bad arguments");
+    const int tiles = grid_tiles(xw) * grid_tiles(yw);
+    grid_clear_dirty_kernel<<<tiles, 256, 0, (cudaStream_t)stream>>>(hit, miss, (uint8_t *)workspace + GRID_WS_HEADER,
+                                                                    xw, yw);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
 }
 
 extern "C" int b2s_grid_validate(const float *ox, const float *oy, const float *cx, const float *cy,

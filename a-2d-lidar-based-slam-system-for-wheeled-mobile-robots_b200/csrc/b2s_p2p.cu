@@ -103,9 +103,84 @@ grid_merge_p2p_kernel(PeerPlanes pp, int nranks_rt, long long cell_lo, long long
     }
 }
 
+// Tile-sparse form of the merge.  The ray-cast marks the 64 x 64-cell tiles it touches in a dirty map
+// (one byte per tile, inside its workspace); the maps of all ranks are gathered first (that gather is
+// also the fence that orders this kernel after every rank's ray-cast).  A CTA takes one tile of the
+// rank's shard of tiles: if no rank dirtied it, nothing is read or written -- counts and occupancy are
+// unchanged; otherwise only the ranks that did are read.  Cost follows the touched area, not the grid.
+// The rank's shard of the global counts is stored tile-major: [tile - tile_lo][64][64].
+__global__ void __launch_bounds__(256)
+grid_merge_tiles_kernel(PeerPlanes pp, const uint8_t *__restrict__ all_dirty, int nranks, int ntiles, int tile_lo,
+                        int tile_count, int xw, int yw, int32_t *__restrict__ g_hit, int32_t *__restrict__ g_miss,
+                        double w_hit, double w_miss, double thresh)
+{
+    const int tiles_y = grid_tiles(yw);
+    for (int t = blockIdx.x; t < tile_count; t += gridDim.x) {
+        const int tile = tile_lo + t;
+        unsigned who = 0;
+        for (int r = 0; r < nranks; ++r) who |= (all_dirty[(size_t)r * ntiles + tile] ? 1u : 0u) << r;
+        if (!who) continue;
+        const int x0 = (tile / tiles_y) * GRID_TILE, y0 = (tile % tiles_y) * GRID_TILE;
+        int32_t *gh = g_hit + (size_t)t * GRID_TILE * GRID_TILE, *gm = g_miss + (size_t)t * GRID_TILE * GRID_TILE;
+        // 256 threads = 16 rows x 16 quads of 4 cells per pass; 4 passes cover the 64 rows
+        const int qx = threadIdx.x >> 4, qy = (threadIdx.x & 15) * 4;
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass) {
+            const int rx = qx + 16 * pass;
+            const int x = x0 + rx, y = y0 + qy;
+            if (x >= xw || y >= yw) continue;  // yw is a multiple of 4 here (checked by the launcher)
+            const size_t cell = (size_t)x * yw + y;
+            int4 h = *reinterpret_cast<const int4 *>(gh + rx * GRID_TILE + qy);
+            int4 m = *reinterpret_cast<const int4 *>(gm + rx * GRID_TILE + qy);
+            for (int r = 0; r < nranks; ++r)
+                if (who & (1u << r)) {
+                    add4(h, ld_stream(pp.hit[r] + cell));
+                    add4(m, ld_stream(pp.miss[r] + cell));
+                }
+            *reinterpret_cast<int4 *>(gh + rx * GRID_TILE + qy) = h;
+            *reinterpret_cast<int4 *>(gm + rx * GRID_TILE + qy) = m;
+            const uint32_t occ = occupancy4(h, m, w_hit, w_miss, thresh);
+            for (int r = 0; r < nranks; ++r) *reinterpret_cast<uint32_t *>(pp.pmap[r] + cell) = occ;
+        }
+    }
+}
+
 }  // namespace b2s
 
 using namespace b2s;
+
+extern "C" int b2s_grid_merge_p2p_tiles(const int32_t *const *delta_hit, const int32_t *const *delta_miss,
+                                        int8_t *const *pmap, const uint8_t *all_dirty, int nranks, int xw, int yw,
+                                        int tile_lo, int tile_hi, int32_t *global_hit_shard,
+                                        int32_t *global_miss_shard, double w_hit, double w_miss, double thresh,
+                                        void *stream)
+{
+    B2S_REQUIRE(delta_hit && delta_miss && pmap && all_dirty && global_hit_shard && global_miss_shard,
+                "b2s_grid_merge_p2p_tiles: null pointer");
+    B2S_REQUIRE(nranks >= 1 && nranks <= MAX_RANKS, "b2s_grid_merge_p2p_tiles: 1..16 ranks");
+    B2S_REQUIRE(xw > 0 && yw > 0 && yw % 4 == 0, "b2s_grid_merge_p2p_tiles: yw must be a multiple of 4");
+    const int ntiles = grid_tiles(xw) * grid_tiles(yw);
+    B2S_REQUIRE(tile_lo >= 0 && tile_lo <= tile_hi && tile_hi <= ntiles, "b2s_grid_merge_p2p_tiles: tile range");
+    PeerPlanes pp;
+    for (int r = 0; r < nranks; ++r) {
+        B2S_REQUIRE(delta_hit[r] && delta_miss[r] && pmap[r], "b2s_grid_merge_p2p_tiles: null plane");
+        B2S_REQUIRE((uintptr_t)delta_hit[r] % 16 == 0 && (uintptr_t)delta_miss[r] % 16 == 0 && (uintptr_t)pmap[r] % 4 == 0,
+                    "b2s_grid_merge_p2p_tiles: planes must be 16-byte aligned");
+        pp.hit[r] = delta_hit[r];
+        pp.miss[r] = delta_miss[r];
+        pp.pmap[r] = pmap[r];
+    }
+    const int count = tile_hi - tile_lo;
+    if (count == 0) return B2S_OK;
+    int blocks = count;
+    const int cap = sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    grid_merge_tiles_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pp, all_dirty, nranks, ntiles, tile_lo, count, xw,
+                                                                     yw, global_hit_shard, global_miss_shard, w_hit,
+                                                                     w_miss, thresh);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
 
 extern "C" int b2s_grid_merge_p2p(const int32_t *const *delta_hit, const int32_t *const *delta_miss,
                                   int8_t *const *pmap, int nranks, size_t cell_lo, size_t cell_hi,

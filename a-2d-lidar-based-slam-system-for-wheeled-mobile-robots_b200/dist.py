@@ -144,22 +144,32 @@ class ShardedMappingP2P(object):
     all-reduces on the same stream fence the kernel against the peers' ray-casts and map writes.
     """
 
-    def __init__(self, xw, yw, xyreso, hit_weight=20.0, miss_weight=0.01, occ_threshold=10.0):
+    def __init__(self, xw, yw, xyreso, hit_weight=20.0, miss_weight=0.01, occ_threshold=10.0, sparse=True):
         import ctypes
         from b2slam import _lib, devapi
         self._lib, self._dev, self._ct = _lib, devapi, ctypes
+        # sparse: tile-level dirty tracking -- zeroing and merging cost follows the touched area
+        self.sparse = bool(sparse) and int(yw) % 4 == 0
         self.xw, self.yw = int(xw), int(yw)
         self.cells = self.xw * self.yw
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.scale = devapi.grid_scale(self.xw, self.yw, float(xyreso))
         self.weights = (float(hit_weight), float(miss_weight), float(occ_threshold))
-        blocks = self.cells // 4096
-        if blocks * 4096 != self.cells:
-            raise ValueError("ShardedMappingP2P needs xw*yw to be a multiple of 4096 cells")
-        lo, hi = shard_bounds(blocks, self.rank, self.world)
-        self.cell_lo, self.cell_hi = lo * 4096, hi * 4096
         L = _lib.lib()
+        if self.sparse:
+            tx, ty = ctypes.c_int(0), ctypes.c_int(0)
+            _lib.check(L.b2s_grid_tile_count(self.xw, self.yw, ctypes.byref(tx), ctypes.byref(ty)))
+            self.tiles_x, self.tiles_y = tx.value, ty.value
+            self.ntiles = self.tiles_x * self.tiles_y
+            self.tile_lo, self.tile_hi = shard_bounds(self.ntiles, self.rank, self.world)
+            self.cell_lo, self.cell_hi = 0, (self.tile_hi - self.tile_lo) * 4096   # tile-major shard storage
+        else:
+            blocks = self.cells // 4096
+            if blocks * 4096 != self.cells:
+                raise ValueError("the dense peer-memory merge needs xw*yw to be a multiple of 4096 cells")
+            lo, hi = shard_bounds(blocks, self.rank, self.world)
+            self.cell_lo, self.cell_hi = lo * 4096, hi * 4096
         self._own = []
         ptrs = []
         for nbytes in (self.cells * 4, self.cells * 4, self.cells):
@@ -200,6 +210,10 @@ class ShardedMappingP2P(object):
         self.g_hit = torch.zeros(max(n, 4096), dtype=torch.int32, device="cuda")
         self.g_miss = torch.zeros(max(n, 4096), dtype=torch.int32, device="cuda")
         self.workspace = devapi.new_workspace(self.xw, self.yw)
+        if self.sparse:
+            dptr = L.b2s_grid_workspace_dirty(ctypes.c_void_p(self.workspace.data_ptr()))
+            self.dirty = devapi.tensor_from_ptr(dptr, (self.ntiles,), torch.uint8)
+            self.all_dirty = torch.zeros(self.world * self.ntiles, dtype=torch.uint8, device="cuda")
         self.pmap_host = torch.empty((self.xw, self.yw), dtype=torch.int8).pin_memory()
         self._token = torch.zeros(1, dtype=torch.int32, device="cuda")
         self._in = None
@@ -213,20 +227,35 @@ class ShardedMappingP2P(object):
     def update_device(self, ox, oy, cx, cy, events=None):
         """Scans already on the device (float32 CUDA tensors).  Leaves the merged map in pmap_dev.
         `events`: optional (start, stop) torch.cuda.Event pair recorded around the ray-cast."""
-        self.d_hit.zero_()
-        self.d_miss.zero_()
+        L = self._lib.lib()
+        stream = torch.cuda.current_stream().cuda_stream
+        if self.sparse:   # only the tiles the previous call dirtied are non-zero: re-zero those, clear the map
+            self._lib.check(L.b2s_grid_clear_dirty(self.d_hit.data_ptr(), self.d_miss.data_ptr(), self.xw, self.yw,
+                                                   self.workspace.data_ptr(), stream))
+        else:
+            self.d_hit.zero_()
+            self.d_miss.zero_()
         S, Hx, Hy = self.scale
         if events:
             events[0].record()
         self._dev.grid_raycast(self.d_hit, self.d_miss, S, Hx, Hy, ox, oy, cx, cy, workspace=self.workspace)
         if events:
             events[1].record()
-        self._fence()
         w_hit, w_miss, thr = self.weights
-        self._lib.check(self._lib.lib().b2s_grid_merge_p2p(
-            self._hit_ptrs, self._miss_ptrs, self._pmap_ptrs, self.world, self.cell_lo, self.cell_hi,
-            self.g_hit.data_ptr(), self.g_miss.data_ptr(), w_hit, w_miss, thr,
-            torch.cuda.current_stream().cuda_stream))
+        if self.sparse:
+            if self.world > 1:   # the gather of the dirty maps is also the fence after every rank's ray-cast
+                dist.all_gather_into_tensor(self.all_dirty, self.dirty)
+            else:
+                self.all_dirty.copy_(self.dirty)
+            self._lib.check(L.b2s_grid_merge_p2p_tiles(
+                self._hit_ptrs, self._miss_ptrs, self._pmap_ptrs, self.all_dirty.data_ptr(), self.world, self.xw,
+                self.yw, self.tile_lo, self.tile_hi, self.g_hit.data_ptr(), self.g_miss.data_ptr(), w_hit, w_miss,
+                thr, stream))
+        else:
+            self._fence()
+            self._lib.check(L.b2s_grid_merge_p2p(
+                self._hit_ptrs, self._miss_ptrs, self._pmap_ptrs, self.world, self.cell_lo, self.cell_hi,
+                self.g_hit.data_ptr(), self.g_miss.data_ptr(), w_hit, w_miss, thr, stream))
         self._fence()
 
     def update_batch(self, ox, oy, cx, cy):
@@ -253,8 +282,15 @@ class ShardedMappingP2P(object):
         else:
             parts_h[0], parts_m[0] = mine
         import numpy as np
-        return (np.concatenate(parts_h).reshape(self.xw, self.yw),
-                np.concatenate(parts_m).reshape(self.xw, self.yw))
+        if not self.sparse:
+            return (np.concatenate(parts_h).reshape(self.xw, self.yw),
+                    np.concatenate(parts_m).reshape(self.xw, self.yw))
+        out = []
+        for parts in (parts_h, parts_m):   # tile-major shards -> [x][y] plane
+            tiles = np.concatenate(parts).reshape(self.tiles_x, self.tiles_y, 64, 64)
+            full = tiles.transpose(0, 2, 1, 3).reshape(self.tiles_x * 64, self.tiles_y * 64)
+            out.append(np.ascontiguousarray(full[:self.xw, :self.yw]))
+        return out[0], out[1]
 
     def close(self):
         torch.cuda.synchronize()

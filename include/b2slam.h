@@ -171,6 +171,22 @@ int b2s_grid_merge_p2p(const int32_t *const *delta_hit, const int32_t *const *de
                        int32_t *global_hit_shard, int32_t *global_miss_shard, double w_hit,
                        double w_miss, double thresh, void *stream);
 
+/* Tile-sparse form of the same merge.  b2s_grid_raycast_ws / _ranges mark every 64 x 64-cell tile they
+ * touch in a dirty map inside the workspace (b2s_grid_workspace_dirty: one byte per tile, row-major over
+ * b2s_grid_tile_count).  all_dirty [nranks][tiles] holds every rank's map (gather them first; the gather
+ * doubles as the fence after the ray-casts).  This rank merges tiles [tile_lo, tile_hi): untouched tiles
+ * cost nothing, touched ones read only the ranks that touched them.  The shard of global counts is
+ * tile-major int32 [tile_hi - tile_lo][64][64].  b2s_grid_clear_dirty re-zeroes a pair of delta planes
+ * (only their dirty tiles) and clears the map. */
+int b2s_grid_merge_p2p_tiles(const int32_t *const *delta_hit, const int32_t *const *delta_miss,
+                             int8_t *const *pmap, const uint8_t *all_dirty, int nranks, int xw, int yw,
+                             int tile_lo, int tile_hi, int32_t *global_hit_shard,
+                             int32_t *global_miss_shard, double w_hit, double w_miss, double thresh,
+                             void *stream);
+void *b2s_grid_workspace_dirty(void *workspace);
+int b2s_grid_tile_count(int xw, int yw, int *tiles_x, int *tiles_y);
+int b2s_grid_clear_dirty(int32_t *hit, int32_t *miss, int xw, int yw, void *workspace, void *stream);
+
 /* cudaMalloc'ed (IPC-exportable) device memory and CUDA IPC handles (64 bytes) for the peer mapping. */
 int b2s_device_alloc(void **out, size_t bytes);
 int b2s_device_free(void *p);

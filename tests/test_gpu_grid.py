@@ -185,7 +185,8 @@ def test_cfg3_counts_bit_exact_vs_oracle(env):
         env.dev.grid_raycast(hit, miss, S, Hx, Hy, *devt, counters=cnt, workspace=ws)
         if ws is not None:  # the workspace comes back clean and is reusable
             torch.cuda.synchronize()
-            assert int(ws[16:].abs().sum().item()) == 0 and ws[:4].tolist() == [-2139062144] * 4
+            assert int(ws[-G * G:].abs().sum().item()) == 0 and ws[:4].tolist() == [-2139062144] * 4
+            assert int(ws[16:-G * G].sum().item()) > 0      # the dirty-tile map stays set until it is consumed
             env.dev.grid_raycast(hit, miss, S, Hx, Hy, *devt, workspace=ws)
             hit //= 2
             miss //= 2

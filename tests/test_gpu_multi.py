@@ -30,13 +30,15 @@ for rnd in range(2):
     ox, oy, cx, cy = (np.concatenate([p[k] for p in parts]) for k in range(4))
     pm = sm.update_batch(ox, oy, cx, cy)
 hit, miss = sm.counts()
-p2p = bdist.ShardedMappingP2P(G, G, 0.05)
-for rnd in range(2):
-    parts = [synth.grid_scans(5001 + s + 100 * rnd, 24, 1080, half_extent_m=40.0) for s in range(lo, hi)]
-    ox, oy, cx, cy = (np.concatenate([p[k] for p in parts]) for k in range(4))
-    pm2 = p2p.update_batch(ox, oy, cx, cy).copy()
-hit2, miss2 = p2p.counts()
-p2p.close()
+res = {}
+for tag, sparse in (("2", True), ("3", False)):       # tile-sparse and dense forms of the fused merge
+    p2p = bdist.ShardedMappingP2P(G, G, 0.05, sparse=sparse)
+    for rnd in range(2):
+        parts = [synth.grid_scans(5001 + s + 100 * rnd, 24, 1080, half_extent_m=40.0) for s in range(lo, hi)]
+        ox, oy, cx, cy = (np.concatenate([p[k] for p in parts]) for k in range(4))
+        res["pm" + tag] = p2p.update_batch(ox, oy, cx, cy).copy()
+    res["hit" + tag], res["miss" + tag] = p2p.counts()
+    p2p.close()
 xy, _ = synth.room_sequence(9001, 41, 360)
 plo, phi = bdist.sequence_pair_bounds(41, rank, world)
 tar = torch.from_numpy(np.ascontiguousarray(xy[plo:phi])).cuda()
@@ -46,7 +48,7 @@ counts = [b - a for a, b in (bdist.sequence_pair_bounds(41, q, world) for q in r
 allT = bdist.gather_transforms(T, counts)
 torch.cuda.synchronize()
 np.savez(os.path.join(os.environ["B2S_OUT"], "rank%d.npz" % rank), hit=hit, miss=miss, pm=pm, T=allT.cpu().numpy(),
-         hit2=hit2, miss2=miss2, pm2=pm2)
+         **res)
 bdist.barrier()
 torch.distributed.destroy_process_group()
 '''
@@ -78,8 +80,9 @@ def test_two_gpu_grid_merge_and_icp_sharding(tmp_path):
         assert np.array_equal(z["hit"], oh) and np.array_equal(z["miss"], om)   # bit-identical to one pass
         assert np.array_equal(z["pm"], corc.grid_finalize(oh, om)[1])
         # fused peer-memory merge: same counts (sharded across ranks), same map on every rank
-        assert np.array_equal(z["hit2"], oh) and np.array_equal(z["miss2"], om)
-        assert np.array_equal(z["pm2"], corc.grid_finalize(oh, om)[1])
+        for tag in ("2", "3"):
+            assert np.array_equal(z["hit" + tag], oh) and np.array_equal(z["miss" + tag], om), tag
+            assert np.array_equal(z["pm" + tag], corc.grid_finalize(oh, om)[1]), tag
         np.testing.assert_allclose(z["T"], want_T, rtol=0, atol=1e-9)
 
 
@@ -88,15 +91,27 @@ def test_p2p_merge_single_rank_degenerates_to_finalize():
     import b2slam.dist as bdist
     import b2slam.synth as synth
     from oracle import corc
-    G = 1024
-    sm = bdist.ShardedMappingP2P(G, G, 0.05)
-    oh = np.zeros((G, G), dtype=np.int32)
-    om = np.zeros((G, G), dtype=np.int32)
-    for seed in (1, 2):
-        ox, oy, cx, cy = synth.grid_scans(seed, 40, 360, half_extent_m=15.0)
-        pm = sm.update_batch(ox, oy, cx, cy).copy()
-        corc.grid_raycast(oh, om, 20.0, 25.6, 25.6, ox, oy, cx, cy)
-    h, m = sm.counts()
-    assert np.array_equal(h, oh) and np.array_equal(m, om)
-    assert np.array_equal(pm, corc.grid_finalize(oh, om)[1])
-    sm.close()
+    for (xw, yw, sparse) in ((1024, 1024, True), (1024, 1024, False), (1000, 780, True)):
+        sm = bdist.ShardedMappingP2P(xw, yw, 0.05, sparse=sparse)
+        S, Hx, Hy = 20.0, xw * 0.05 / 2.0, yw * 0.05 / 2.0
+        oh = np.zeros((xw, yw), dtype=np.int32)
+        om = np.zeros((xw, yw), dtype=np.int32)
+        for seed in (1, 2, 3):
+            ox, oy, cx, cy = synth.grid_scans(seed, 40, 360, half_extent_m=15.0)
+            pm = sm.update_batch(ox, oy, cx, cy).copy()
+            corc.grid_raycast(oh, om, S, Hx, Hy, ox, oy, cx, cy)
+        h, m = sm.counts()
+        assert np.array_equal(h, oh) and np.array_equal(m, om), (xw, yw, sparse)
+        assert np.array_equal(pm, corc.grid_finalize(oh, om)[1]), (xw, yw, sparse)
+        # the delta planes hold only the last call's scans, and the dirty map covers every touched cell
+        if sparse:
+            dh, dm = sm.d_hit.cpu().numpy(), sm.d_miss.cpu().numpy()
+            lh = np.zeros((xw, yw), dtype=np.int32)
+            lm = np.zeros((xw, yw), dtype=np.int32)
+            corc.grid_raycast(lh, lm, S, Hx, Hy, ox, oy, cx, cy)
+            assert np.array_equal(dh, lh) and np.array_equal(dm, lm)
+            dirty = sm.dirty.cpu().numpy().reshape(sm.tiles_x, sm.tiles_y).astype(bool)
+            touched = (lh != 0) | (lm != 0)
+            tx, ty = np.nonzero(touched)
+            assert dirty[tx // 64, ty // 64].all()
+        sm.close()
