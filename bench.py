@@ -343,6 +343,14 @@ def bench_grid(args, rank, world, torch, devapi, bdist, synth):
 
     peak, peak_src = measured_peaks()
     achieved = algo_bytes / (ray_avg_ms * 1e-3) / 1e9
+    traffic = None  # DRAM bytes per launch from the committed ncu capture of this exact workload, if there is one
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1", "grid_traffic.json")) as fh:
+            cap = json.load(fh)
+        if cap.get("scans") == K and G == 4096 and N == 1080:
+            traffic = cap["dram__bytes_read.sum"] + cap["dram__bytes_write.sum"]
+    except Exception:
+        pass
     if p2p is not None:
         p2p.close()
     res = {
