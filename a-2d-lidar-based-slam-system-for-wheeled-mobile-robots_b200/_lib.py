@@ -75,6 +75,8 @@ SIGNATURES = {
     "b2s_mapping_destroy": (_i32, [_vp]),
     "b2s_mapping_reset": (_i32, [_vp]),
     "b2s_mapping_update": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "b2s_mapping_update_incremental": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32,
+                                              ctypes.POINTER(_i32)]),
     "b2s_mapping_update_ranges": (_i32, [_vp, _vp, _vp, _vp, _dbl, _i32, _i32, _vp]),
     "b2s_mapping_read": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "b2s_mapping_write": (_i32, [_vp, _vp, _vp]),

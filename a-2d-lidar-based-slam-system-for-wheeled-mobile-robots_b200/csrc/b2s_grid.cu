@@ -820,6 +820,53 @@ grid_clear_dirty_kernel(int32_t *__restrict__ hit, int32_t *__restrict__ miss, u
 }
 }  // namespace b2s
 
+namespace b2s {
+// Finalize only the dirty tiles: refresh their cells in the full device map and pack them (4096 bytes per
+// tile, row-major 64 x 64) into `packed` so the host can patch its copy with a transfer proportional to
+// what changed.  counter / tile_ids: number of dirty tiles and their indices (slots beyond cap are dropped;
+// the caller then falls back to the full map).
+__global__ void __launch_bounds__(256)
+grid_finalize_dirty_kernel(const int32_t *__restrict__ hit, const int32_t *__restrict__ miss, int xw, int yw,
+                           double w_hit, double w_miss, double thresh, const uint8_t *__restrict__ dirty,
+                           int8_t *__restrict__ pmap, int8_t *__restrict__ packed, int32_t *__restrict__ tile_ids,
+                           int32_t *__restrict__ counter, int cap)
+{
+    __shared__ int slot_s;
+    const int tile = blockIdx.x;
+    if (!dirty[tile]) return;
+    if (threadIdx.x == 0) slot_s = atomicAdd(counter, 1);
+    __syncthreads();
+    const int slot = slot_s;
+    if (slot < cap && threadIdx.x == 0) tile_ids[slot] = tile;
+    const int tiles_y = grid_tiles(yw);
+    const int x0 = (tile / tiles_y) * GRID_TILE, y0 = (tile % tiles_y) * GRID_TILE;
+    for (int k = threadIdx.x; k < GRID_TILE * GRID_TILE; k += blockDim.x) {
+        const int x = x0 + k / GRID_TILE, y = y0 + k % GRID_TILE;
+        int8_t v = 0;
+        if (x < xw && y < yw) {
+            const size_t at = (size_t)x * yw + y;
+            const int h = hit[at], m = miss[at];
+            const double sc = __dadd_rn(__dmul_rn(w_miss, (double)m), __dmul_rn(w_hit, (double)h));
+            v = (h == 0 && m == 0) ? 50 : (sc > thresh ? 100 : 0);
+            pmap[at] = v;
+        }
+        if (slot < cap) packed[(size_t)slot * GRID_TILE * GRID_TILE + k] = v;
+    }
+}
+
+int grid_finalize_dirty(const int32_t *hit, const int32_t *miss, int xw, int yw, double w_hit, double w_miss,
+                        double thresh, void *workspace, int8_t *pmap, int8_t *packed, int32_t *tile_ids,
+                        int32_t *counter, int cap, void *stream)
+{
+    const int tiles = grid_tiles(xw) * grid_tiles(yw);
+    grid_finalize_dirty_kernel<<<tiles, 256, 0, (cudaStream_t)stream>>>(
+        hit, miss, xw, yw, w_hit, w_miss, thresh, (const uint8_t *)workspace + GRID_WS_HEADER, pmap, packed, tile_ids,
+        counter, cap);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+}  // namespace b2s
+
 extern "C" void *b2s_grid_workspace_dirty(void *workspace)
 {
     return workspace ? (void *)((char *)workspace + GRID_WS_HEADER) : nullptr;

@@ -104,7 +104,10 @@ struct b2s_mapping {
     int32_t *hit, *miss;
     int32_t *counters;
     void *workspace;
-    Buf d_in, d_datamap, d_pmap;
+    Buf d_in, d_datamap, d_pmap, d_packed;
+    bool pmap_valid;  // d_pmap holds the occupancy of the current counts
+    int8_t *h_packed;  // pinned staging for the dirty tiles
+    int32_t *h_ids;
 };
 
 extern "C" int b2s_version(void) { return 100; }
@@ -356,6 +359,9 @@ extern "C" int b2s_mapping_create(b2s_mapping **out, int xw, int yw, double xyre
     m->thresh = thresh;
     m->hit = m->miss = m->counters = nullptr;
     m->workspace = nullptr;
+    m->pmap_valid = false;
+    m->h_packed = nullptr;
+    m->h_ids = nullptr;
     m->stream = m->copy_stream = nullptr;
     for (int k = 0; k < 8; ++k) m->chunk_ready[k] = nullptr;
     m->inputs_free = nullptr;
@@ -391,6 +397,9 @@ extern "C" int b2s_mapping_destroy(b2s_mapping *m)
     if (m->miss) cudaFree(m->miss);
     if (m->counters) cudaFree(m->counters);
     if (m->workspace) cudaFree(m->workspace);
+    if (m->h_packed) cudaFreeHost(m->h_packed);
+    if (m->h_ids) cudaFreeHost(m->h_ids);
+    m->d_packed.release();
     m->d_in.release(); m->d_datamap.release(); m->d_pmap.release();
     for (int k = 0; k < 8; ++k)
         if (m->chunk_ready[k]) cudaEventDestroy(m->chunk_ready[k]);
@@ -409,6 +418,7 @@ extern "C" int b2s_mapping_reset(b2s_mapping *m)
     B2S_CUDA(cudaMemsetAsync(m->hit, 0, plane, m->stream));
     B2S_CUDA(cudaMemsetAsync(m->miss, 0, plane, m->stream));
     B2S_CUDA(cudaStreamSynchronize(m->stream));
+    m->pmap_valid = false;
     return B2S_OK;
 }
 
@@ -428,7 +438,11 @@ struct HostBatch {
 //   * beams that int() would raise on ([MAP]:33-36) are skipped and counted by the kernels, so applying
 //     a chunk before the verdict on the whole batch is known is safe: a rejected batch is taken back
 //     out with the sign -1 kernel (integer adds: exact inverse)
-int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beams, int8_t *pmap_out)
+constexpr int PACK_CAP = 1024;  // dirty tiles shipped individually; beyond that the whole map is cheaper
+
+int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beams, int8_t *pmap_out,
+                        bool incremental = false, int32_t *tiles_out = nullptr, int tiles_cap = 0,
+                        int *tiles_count = nullptr)
 {
     DeviceGuard g(m->device);
     const size_t total = (size_t)scans * beams;
@@ -468,8 +482,10 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
             d_c = (float *)(base + 2 * a_pts);
             d_d = (float *)(base + 2 * a_pts + a_ctr);
         }
-        // counters[0..3]: the ray-cast kernel's own (B2S_CNT_*); counters[4], [5]: NaN / inf seen by the screening
+        // counters[0..3]: the ray-cast kernel's own (B2S_CNT_*); counters[4]: dirty-tile count of this call
         B2S_CUDA(cudaMemsetAsync(m->counters, 0, 2 * B2S_CNT_WORDS * sizeof(int32_t), m->stream));
+        // the dirty-tile map describes THIS call
+        B2S_CUDA(cudaMemsetAsync((char *)m->workspace + GRID_WS_HEADER, 0, grid_dirty_bytes(m->xw, m->yw), m->stream));
         nchunk = (int)((total + (1u << 21) - 1) >> 21);  // ~2M beams per chunk
         if (nchunk > 8) nchunk = 8;
         if (nchunk > scans) nchunk = scans;
@@ -494,16 +510,62 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
             if ((rc = launch(k, +1, m->counters))) return rc;
         }
     }
-    int32_t cnt[B2S_CNT_WORDS] = {0, 0, 0, 0};
-    if (total > 0)
-        B2S_CUDA(cudaMemcpyAsync(cnt, m->counters, sizeof(cnt), cudaMemcpyDeviceToHost, m->stream));
+    int32_t cnt[2 * B2S_CNT_WORDS] = {0, 0, 0, 0, 0, 0, 0, 0};
     const size_t cells = (size_t)m->xw * m->yw;
-    if (pmap_out) {
+    const size_t tile_bytes = (size_t)GRID_TILE * GRID_TILE;
+    // Incremental read-back: when the host already holds the previous map and this call touched few tiles,
+    // finalize and ship only those tiles (a single scan dirties ~20 of the 4096 tiles of a 4096^2 map).
+    bool patched = false;
+    if (tiles_count) *tiles_count = -1;
+    if (pmap_out && incremental && m->pmap_valid && total > 0) {
+        if ((rc = m->d_pmap.reserve(cells))) return rc;
+        if ((rc = m->d_packed.reserve(PACK_CAP * tile_bytes + PACK_CAP * sizeof(int32_t)))) return rc;
+        if (!m->h_packed) {
+            B2S_CUDA(cudaMallocHost((void **)&m->h_packed, PACK_CAP * tile_bytes));
+            B2S_CUDA(cudaMallocHost((void **)&m->h_ids, PACK_CAP * sizeof(int32_t)));
+        }
+        int8_t *d_packed = (int8_t *)m->d_packed.p;
+        int32_t *d_ids = (int32_t *)((char *)m->d_packed.p + PACK_CAP * tile_bytes);
+        rc = grid_finalize_dirty(m->hit, m->miss, m->xw, m->yw, m->w_hit, m->w_miss, m->thresh, m->workspace,
+                                 (int8_t *)m->d_pmap.p, d_packed, d_ids, m->counters + B2S_CNT_WORDS, PACK_CAP, m->stream);
+        if (rc) return rc;
+        B2S_CUDA(cudaMemcpyAsync(cnt, m->counters, sizeof(cnt), cudaMemcpyDeviceToHost, m->stream));
+        B2S_CUDA(cudaStreamSynchronize(m->stream));
+        const int nd = cnt[B2S_CNT_WORDS];
+        const bool bad = cnt[B2S_CNT_NONFINITE] || cnt[B2S_CNT_OVERFLOW] || cnt[B2S_CNT_TOO_LONG] > 0;
+        if (!bad && nd <= PACK_CAP) {
+            if (nd > 0) {
+                B2S_CUDA(cudaMemcpyAsync(m->h_packed, d_packed, (size_t)nd * tile_bytes, cudaMemcpyDeviceToHost, m->stream));
+                B2S_CUDA(cudaMemcpyAsync(m->h_ids, d_ids, (size_t)nd * sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+                B2S_CUDA(cudaStreamSynchronize(m->stream));
+            }
+            const int tiles_y = grid_tiles(m->yw);
+            for (int k = 0; k < nd; ++k) {
+                const int tile = m->h_ids[k];
+                const int x0 = (tile / tiles_y) * GRID_TILE, y0 = (tile % tiles_y) * GRID_TILE;
+                const int nx = (m->xw - x0 < GRID_TILE) ? m->xw - x0 : GRID_TILE;
+                const int ny = (m->yw - y0 < GRID_TILE) ? m->yw - y0 : GRID_TILE;
+                for (int r = 0; r < nx; ++r)
+                    memcpy(pmap_out + (size_t)(x0 + r) * m->yw + y0, m->h_packed + (size_t)k * tile_bytes + (size_t)r * GRID_TILE,
+                           (size_t)ny);
+                if (tiles_out && k < tiles_cap) tiles_out[k] = tile;
+            }
+            if (tiles_count) *tiles_count = (tiles_out && nd > tiles_cap) ? -1 : nd;
+            patched = true;
+        }
+        if (bad) m->pmap_valid = false;  // handled (and rolled back) below with a full refresh
+    } else if (total > 0) {
+        B2S_CUDA(cudaMemcpyAsync(cnt, m->counters, sizeof(cnt), cudaMemcpyDeviceToHost, m->stream));
+    }
+    if (pmap_out && !patched) {
         if ((rc = m->d_pmap.reserve(cells))) return rc;
         rc = b2s_grid_finalize(m->hit, m->miss, m->xw, m->yw, m->w_hit, m->w_miss, m->thresh, nullptr,
                                (int8_t *)m->d_pmap.p, m->stream);
         if (rc) return rc;
         B2S_CUDA(cudaMemcpyAsync(pmap_out, m->d_pmap.p, cells, cudaMemcpyDeviceToHost, m->stream));
+        m->pmap_valid = true;
+    } else if (!pmap_out) {
+        m->pmap_valid = false;  // counts moved on without the device map
     }
     B2S_CUDA(cudaStreamSynchronize(m->stream));
     const int saw_nan = cnt[B2S_CNT_NONFINITE], saw_inf = cnt[B2S_CNT_OVERFLOW];
@@ -538,6 +600,17 @@ extern "C" int b2s_mapping_update(b2s_mapping *m, const float *ox, const float *
     B2S_REQUIRE((size_t)scans * beams == 0 || (ox && oy && cx && cy), "b2s_mapping_update: null pointer");
     HostBatch hb = {false, ox, oy, cx, cy, nullptr, nullptr, nullptr, 0.0};
     return mapping_update_impl(m, hb, scans, beams, pmap_out);
+}
+
+extern "C" int b2s_mapping_update_incremental(b2s_mapping *m, const float *ox, const float *oy, const float *cx,
+                                              const float *cy, int scans, int beams, int8_t *pmap_inout,
+                                              int32_t *tiles_out, int tiles_cap, int *tiles_count)
+{
+    B2S_REQUIRE(m && pmap_inout, "b2s_mapping_update_incremental: null pointer");
+    B2S_REQUIRE(scans >= 0 && beams >= 0 && tiles_cap >= 0, "b2s_mapping_update_incremental: negative count");
+    B2S_REQUIRE((size_t)scans * beams == 0 || (ox && oy && cx && cy), "b2s_mapping_update_incremental: null pointer");
+    HostBatch hb = {false, ox, oy, cx, cy, nullptr, nullptr, nullptr, 0.0};
+    return mapping_update_impl(m, hb, scans, beams, pmap_inout, true, tiles_out, tiles_cap, tiles_count);
 }
 
 extern "C" int b2s_mapping_update_ranges(b2s_mapping *m, const float *ranges, const double *pose4,
@@ -582,6 +655,7 @@ extern "C" int b2s_mapping_write(b2s_mapping *m, const int32_t *hit, const int32
     B2S_CUDA(cudaMemcpyAsync(m->hit, hit, plane, cudaMemcpyHostToDevice, m->stream));
     B2S_CUDA(cudaMemcpyAsync(m->miss, miss, plane, cudaMemcpyHostToDevice, m->stream));
     B2S_CUDA(cudaStreamSynchronize(m->stream));
+    m->pmap_valid = false;
     return B2S_OK;
 }
 

@@ -43,6 +43,8 @@ class Mapping(object):
         self._h = h
         self._pmap8 = _lib.pinned_empty((self.xw, self.yw), np.int8)  # page-locked result buffer
         self._pmap8.fill(50)  # [MAP]:14 unknown = 50
+        self._pmap64 = None            # float64 mirror handed out by update(), patched tile by tile
+        self._tiles = np.empty(1024, dtype=np.int32)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -52,9 +54,11 @@ class Mapping(object):
 
     @property
     def pmap(self):
-        """[MAP]:14 occupancy as the reference's float64 (xw, yw) array in {0, 50, 100}; a snapshot
-        of the last update (the reference hands out its live array)."""
-        return self._pmap8.astype(np.float64)
+        """[MAP]:14 occupancy as the reference's float64 (xw, yw) array in {0, 50, 100}: the live array
+        update() maintains (like the reference's), rebuilt here if a batched call moved past it."""
+        if self._pmap64 is None:
+            self._pmap64 = self._pmap8.astype(np.float64)
+        return self._pmap64
 
     # ------------------------------------------------------------------ reference methods
 
@@ -65,12 +69,36 @@ class Mapping(object):
         Raises ValueError / OverflowError on NaN / inf where the reference's int() does
         (infinite ox alone is skipped, [MAP]:30) -- but before any beam is applied.
         """
-        ox = np.asarray(ox, dtype=np.float64).reshape(1, -1)
-        oy = np.asarray(oy, dtype=np.float64).reshape(1, -1)
-        cx = np.asarray(center_x, dtype=np.float64).reshape(-1)[:1]
-        cy = np.asarray(center_y, dtype=np.float64).reshape(-1)[:1]
-        self.update_batch(ox, oy, cx, cy)
-        return self.pmap
+        ox = np.ascontiguousarray(np.asarray(ox, dtype=np.float32).reshape(1, -1))
+        oy = np.ascontiguousarray(np.asarray(oy, dtype=np.float32).reshape(1, -1))
+        cx = np.asarray(center_x, dtype=np.float32).reshape(-1)[:1].copy()
+        cy = np.asarray(center_y, dtype=np.float32).reshape(-1)[:1].copy()
+        if ox.shape != oy.shape:
+            raise ValueError("ox and oy differ in length: %s vs %s" % (ox.shape, oy.shape))
+        # incremental read-back: only the 64 x 64-cell tiles this scan touched cross PCIe and are patched
+        # into the host maps, so the call costs the same on a 4096^2 map as on the reference's 200^2
+        count = ctypes.c_int(-1)
+        rc = self._L.b2s_mapping_update_incremental(
+            self._h, _lib.ptr(ox), _lib.ptr(oy), _lib.ptr(cx), _lib.ptr(cy), 1, ox.shape[1], _lib.ptr(self._pmap8),
+            _lib.ptr(self._tiles), self._tiles.shape[0], ctypes.byref(count))
+        self._raise_nonfinite(rc)
+        _lib.check(rc)
+        if self._pmap64 is None:
+            self._pmap64 = self._pmap8.astype(np.float64)
+        elif count.value < 0:
+            self._pmap64[...] = self._pmap8          # whole map rewritten: refresh the live array in place
+        else:
+            tiles_y = (self.yw + 63) // 64
+            for t in self._tiles[:count.value]:
+                x0, y0 = (int(t) // tiles_y) * 64, (int(t) % tiles_y) * 64
+                self._pmap64[x0:x0 + 64, y0:y0 + 64] = self._pmap8[x0:x0 + 64, y0:y0 + 64]
+        return self._pmap64
+
+    def _raise_nonfinite(self, rc):
+        if rc == _lib.ERR_NONFINITE:
+            if "NaN" in self._L.b2s_last_error().decode():
+                raise ValueError("cannot convert float NaN to integer")
+            raise OverflowError("cannot convert float infinity to integer")
 
     # ------------------------------------------------------------------ batched entry points
 
@@ -88,12 +116,10 @@ class Mapping(object):
             raise ValueError("expected ox, oy (K,N) and cx, cy (K,), got %s %s %s %s"
                              % (ox.shape, oy.shape, cx.shape, cy.shape))
         out = self._pmap8 if want_pmap else None
+        self._pmap64 = None
         rc = self._L.b2s_mapping_update(self._h, _lib.ptr(ox), _lib.ptr(oy), _lib.ptr(cx),
                                         _lib.ptr(cy), ox.shape[0], ox.shape[1], _lib.ptr(out))
-        if rc == _lib.ERR_NONFINITE:
-            if "NaN" in self._L.b2s_last_error().decode():
-                raise ValueError("cannot convert float NaN to integer")
-            raise OverflowError("cannot convert float infinity to integer")
+        self._raise_nonfinite(rc)
         _lib.check(rc)
         return self._pmap8 if want_pmap else None
 
@@ -117,13 +143,11 @@ class Mapping(object):
             self._beam_cs = scan.beam_table(angle_min, angle_max, ranges.shape[1])
             self._beam_key = key
         out = self._pmap8 if want_pmap else None
+        self._pmap64 = None
         rc = self._L.b2s_mapping_update_ranges(self._h, _lib.ptr(ranges), _lib.ptr(pose4), _lib.ptr(self._beam_cs),
                                                float(clamp_inf_to or 0.0), ranges.shape[0], ranges.shape[1],
                                                _lib.ptr(out))
-        if rc == _lib.ERR_NONFINITE:
-            if "NaN" in self._L.b2s_last_error().decode():
-                raise ValueError("cannot convert float NaN to integer")
-            raise OverflowError("cannot convert float infinity to integer")
+        self._raise_nonfinite(rc)
         _lib.check(rc)
         return self._pmap8 if want_pmap else None
 
@@ -172,10 +196,12 @@ class Mapping(object):
         miss = np.ascontiguousarray(miss, dtype=np.int32).reshape(self.xw, self.yw)
         _lib.check(self._L.b2s_mapping_write(self._h, _lib.ptr(hit), _lib.ptr(miss)))
         _lib.check(self._L.b2s_mapping_read(self._h, None, None, None, _lib.ptr(self._pmap8)))
+        self._pmap64 = None
 
     def reset(self):
         _lib.check(self._L.b2s_mapping_reset(self._h))
         self._pmap8.fill(50)
+        self._pmap64 = None
 
     def device_planes(self):
         """(hit_ptr, miss_ptr, stream_ptr) integers for layer-1 calls and collectives."""

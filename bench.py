@@ -99,7 +99,7 @@ class ClockSampler(object):
                             self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop.wait(0.01)
+            self._stop.wait(0.002)
 
     def stop(self):
         self._stop.set()
@@ -458,6 +458,38 @@ def bench_icp(args, rank, world, torch, devapi, bdist, synth):
     }
 
 
+def drop_in_latency(torch, synth):
+    """Single-call latency of the reference-signature methods (what a ROS node sees per scan)."""
+    import b2slam
+    out = {}
+    tar, src, _ = synth.icp_pairs(7001, 1, 360)                       # cfg 1: the W7 pair
+    t3, s3 = synth.homogeneous(tar[0].astype(np.float64)), synth.homogeneous(src[0].astype(np.float64))
+    icp = b2slam.ICP(max_iter=10, tolerance=0.0)                      # W7 icp.launch:10-11
+    for _ in range(5):
+        icp.process(t3, s3)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        icp.process(t3, s3)
+    out["ICP.process cfg1 (360 beams, max_iter 10, tolerance 0) ms"] = (time.perf_counter() - t0) / 50 * 1e3
+    ox, oy, cx, cy = synth.grid_scans(12001, 64, 1080, half_extent_m=8.0)
+    for shape, reso in (((200, 200), 0.1), ((4096, 4096), 0.05)):
+        m = b2slam.Mapping(shape[0], shape[1], reso)
+        for k in range(4):
+            m.update(ox[k].astype(np.float64), oy[k].astype(np.float64), float(cx[k]), float(cy[k]))
+        t0 = time.perf_counter()
+        for k in range(4, 36):
+            m.update(ox[k].astype(np.float64), oy[k].astype(np.float64), float(cx[k]), float(cy[k]))
+        out["Mapping.update one 1080-beam scan, %dx%d map (float64 pmap returned) ms" % shape] = \
+            (time.perf_counter() - t0) / 32 * 1e3
+        t0 = time.perf_counter()
+        for k in range(36, 64):
+            m.update_batch(ox[k:k + 1], oy[k:k + 1], cx[k:k + 1], cy[k:k + 1], want_pmap=False)
+        out["Mapping.update_batch one scan, %dx%d map (no map read-back) ms" % shape] = \
+            (time.perf_counter() - t0) / 28 * 1e3
+    torch.cuda.synchronize()
+    return out
+
+
 def cpu_baselines(args, synth):
     cores = host_cores()
     ctx = mp.get_context("fork")
@@ -525,6 +557,9 @@ def main():
         bdist.barrier()
 
     cpu = {}
+    latency = None
+    if rank == 0 and world == 1 and args.only == "both":
+        latency = drop_in_latency(torch, synth)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baselines(args, synth)
     bdist.barrier()
@@ -540,6 +575,8 @@ def main():
             "gpu_launches": sum(r["gpu_launches"] for r in results.values()), "clocks": prim["clocks"],
             "cpu_baseline": cpu.get(order[0]),
         }
+        if latency:
+            line["drop_in_latency_ms"] = latency
         if len(order) > 1:
             sec = results[order[1]]
             sec["cpu_baseline"] = cpu.get(order[1])

@@ -230,6 +230,15 @@ int b2s_mapping_reset(b2s_mapping *map);
  * not NULL it receives the refreshed occupancy [xw][yw]. */
 int b2s_mapping_update(b2s_mapping *map, const float *ox, const float *oy, const float *cx,
                        const float *cy, int scans, int beams, int8_t *pmap_out);
+/* Mapping.update with an incremental read-back: pmap_inout must still hold the map written by the previous
+ * call on this object (any of the update calls with a map pointer); only the 64 x 64-cell tiles this batch
+ * touched are finalized, copied and patched into it, so a single scan on a large map costs microseconds
+ * instead of a full-map transfer.  tiles_out / tiles_count (optional) report the patched tile indices
+ * (row-major over b2s_grid_tile_count); *tiles_count = -1 means the whole map was rewritten (first call,
+ * after reset / write, too many tiles, or more than tiles_cap). */
+int b2s_mapping_update_incremental(b2s_mapping *map, const float *ox, const float *oy, const float *cx,
+                                   const float *cy, int scans, int beams, int8_t *pmap_inout,
+                                   int32_t *tiles_out, int tiles_cap, int *tiles_count);
 /* The same for raw scans (fused ingestion, see b2s_grid_raycast_ranges): ranges [scans][beams], pose4
  * [scans][4], beam_cs [beams][2] on the host. */
 int b2s_mapping_update_ranges(b2s_mapping *map, const float *ranges, const double *pose4,

@@ -406,3 +406,37 @@ def test_random_grids_all_variants_vs_oracle(env):
         m = env.b2slam.Mapping(xw, yw, reso)
         pm = m.update_batch(ox, oy, cx, cy)
         assert np.array_equal(pm, env.corc.grid_finalize(oh, om)[1])
+
+
+def test_single_scan_updates_patch_only_touched_tiles(env):
+    """Mapping.update on a large map: incremental read-back must give exactly the full map, call after call,
+    also when mixed with batched calls, errors and resets."""
+    G = 2048
+    ox, oy, cx, cy = env.synth.grid_scans(909, 30, 1080, half_extent_m=40.0)
+    m = env.b2slam.Mapping(G, G, 0.05)
+    oh = np.zeros((G, G), dtype=np.int32)
+    om = np.zeros((G, G), dtype=np.int32)
+    S, Hx, Hy = env.dev.grid_scale(G, G, 0.05)
+    live = None
+    for k in range(12):
+        pm = m.update(ox[k].astype(np.float64), oy[k].astype(np.float64), float(cx[k]), float(cy[k]))
+        env.corc.grid_raycast(oh, om, S, Hx, Hy, ox[k][None], oy[k][None], cx[k:k + 1], cy[k:k + 1])
+        assert np.array_equal(pm, env.corc.grid_finalize(oh, om)[1].astype(np.float64)), k
+        if live is None:
+            live = pm
+        else:
+            assert pm is live                  # the reference hands out its live array; so does update()
+        if k == 5:                             # a rejected scan in between changes nothing
+            with pytest.raises(ValueError):
+                m.update(np.array([1.0, np.nan]), np.array([0.0, 0.0]), 0.0, 0.0)
+        if k == 8:                             # a batched call in between: the mirror is rebuilt lazily
+            m.update_batch(ox[20:25], oy[20:25], cx[20:25], cy[20:25])
+            env.corc.grid_raycast(oh, om, S, Hx, Hy, ox[20:25], oy[20:25], cx[20:25], cy[20:25])
+            live = None
+    assert np.array_equal(m.occupancy(), env.corc.grid_finalize(oh, om)[1])
+    m.reset()
+    pm = m.update(ox[0].astype(np.float64), oy[0].astype(np.float64), float(cx[0]), float(cy[0]))
+    oh[:] = 0
+    om[:] = 0
+    env.corc.grid_raycast(oh, om, S, Hx, Hy, ox[0][None], oy[0][None], cx[0:1], cy[0:1])
+    assert np.array_equal(pm, env.corc.grid_finalize(oh, om)[1].astype(np.float64))
