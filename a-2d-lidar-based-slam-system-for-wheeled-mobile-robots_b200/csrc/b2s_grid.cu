@@ -213,7 +213,7 @@ grid_raycast_v2(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int xw, i
 //     (phase A); once every lane has started the guard disappears (phase B)
 //   * run length = clz of the reversed head mask, RED predicated instead of branched
 
-template <bool GUARD_START, int NORED>
+template <bool GUARD_START>
 __device__ __forceinline__ void march_step(int t, int delay, double slope, double &acc, unsigned &cmaj, int &minor,
                                            unsigned smaj, int smin, int inc, unsigned wmin, int t_em,
                                            unsigned em_len, int dead_key, unsigned lane, unsigned lane_bit,
@@ -237,10 +237,9 @@ __device__ __forceinline__ void march_step(int t, int delay, double slope, doubl
     // lanes after this one up to the next head carry the same cell: run = distance to that head
     const unsigned ahead = ((__brev(heads) << lane) << 1) | lane_bit;
     const int run = __clz(ahead) + 1;
-    if (head && emit && (NORED == 0 || run == 77)) atomicAdd(miss + key, run);
+    if (head && emit) atomicAdd(miss + key, run);
 }
 
-template <int NORED>
 __global__ void __launch_bounds__(256)
 grid_raycast_v3(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int xw, int yw,
                 double cells_per_m, double off_x, double off_y, const float *__restrict__ ox,
@@ -296,11 +295,11 @@ grid_raycast_v3(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int xw, i
 
     int t = 0;
     for (; t < dmax; ++t)
-        march_step<true, NORED>(t, delay, slope, acc, cmaj, minor, smaj, smin, inc, wmin, t_em, em_len, dead_key, lane,
+        march_step<true>(t, delay, slope, acc, cmaj, minor, smaj, smin, inc, wmin, t_em, em_len, dead_key, lane,
                          lane_bit, miss);
 #pragma unroll 4
     for (; t <= tmax; ++t)
-        march_step<false, NORED>(t, delay, slope, acc, cmaj, minor, smaj, smin, inc, wmin, t_em, em_len, dead_key, lane,
+        march_step<false>(t, delay, slope, acc, cmaj, minor, smaj, smin, inc, wmin, t_em, em_len, dead_key, lane,
                           lane_bit, miss);
 }
 
@@ -685,12 +684,9 @@ extern "C" int b2s_grid_raycast(int32_t *hit, int32_t *miss, int xw, int yw, dou
     else if (g_grid_variant == 2)
         grid_raycast_v2<<<(unsigned)blocks, threads, 0, st>>>(hit, miss, xw, yw, cells_per_m, off_x, off_y,
                                                               ox, oy, cx, cy, total, beams, counters);
-    else if (g_grid_variant == 3 || g_grid_variant == 4)
-        grid_raycast_v3<0><<<(unsigned)blocks, threads, 0, st>>>(hit, miss, xw, yw, cells_per_m, off_x, off_y,
-                                                                 ox, oy, cx, cy, total, beams, counters);
-    else  // 99: timing experiment only -- the march without its REDs (results are wrong by design)
-        grid_raycast_v3<1><<<(unsigned)blocks, threads, 0, st>>>(hit, miss, xw, yw, cells_per_m, off_x, off_y,
-                                                                 ox, oy, cx, cy, total, beams, counters);
+    else  // 3, and 4 without a workspace
+        grid_raycast_v3<<<(unsigned)blocks, threads, 0, st>>>(hit, miss, xw, yw, cells_per_m, off_x, off_y,
+                                                              ox, oy, cx, cy, total, beams, counters);
     B2S_CUDA(cudaGetLastError());
     return B2S_OK;
 }

@@ -141,7 +141,7 @@ extern "C" int b2s_tune(const char *key, int value)
 {
     B2S_REQUIRE(key, "b2s_tune: null key");
     if (strcmp(key, "grid_variant") == 0) {
-        B2S_REQUIRE((value >= 1 && value <= 4) || value == 99, "b2s_tune: grid_variant must be 1..4");
+        B2S_REQUIRE(value >= 1 && value <= 4, "b2s_tune: grid_variant must be 1..4");
         g_grid_variant = value;
         return B2S_OK;
     }
