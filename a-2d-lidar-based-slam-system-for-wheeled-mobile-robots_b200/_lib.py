@@ -29,6 +29,7 @@ SIGNATURES = {
     "b2s_last_error": (ctypes.c_char_p, []),
     "b2s_device_count": (_i32, [ctypes.POINTER(_i32)]),
     "b2s_tune": (_i32, [ctypes.c_char_p, _i32]),
+    "b2s_measure_fp64_peak": (_i32, [ctypes.POINTER(_dbl)]),
     "b2s_icp_batch_f32": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _dbl, _vp, _vp, _vp]),
     "b2s_icp_batch_f64": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _dbl, _vp, _vp, _vp]),
     "b2s_nearest_f64": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _vp]),

@@ -176,3 +176,46 @@ extern "C" int b2s_virtual_scan_host(const double *obs_x, const double *obs_y, i
     if (e != cudaSuccess) return cuda_fail(e, "b2s_virtual_scan_host");
     return rc;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Same-run FP64 issue peak (bench.py quotes the ICP kernel against it): 8 independent DFMA chains per thread.
+namespace b2s {
+__global__ void __launch_bounds__(256)
+fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (double)(threadIdx.x + k);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fma(v[k], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+    if (s == 123.456) out[0] = s;  // never true; keeps the chains alive
+}
+}  // namespace b2s
+
+extern "C" int b2s_measure_fp64_peak(double *tflops_out)
+{
+    B2S_REQUIRE(tflops_out, "b2s_measure_fp64_peak: null pointer");
+    double *d = nullptr;
+    B2S_CUDA(cudaMalloc((void **)&d, 8));
+    cudaEvent_t e0, e1;
+    B2S_CUDA(cudaEventCreate(&e0));
+    B2S_CUDA(cudaEventCreate(&e1));
+    const int blocks = sm_count() * 8, iters = 4096;
+    fp64_peak_kernel<<<blocks, 256>>>(d, iters, 0.999999, 1e-9);  // warm-up
+    B2S_CUDA(cudaEventRecord(e0));
+    fp64_peak_kernel<<<blocks, 256>>>(d, iters, 0.999999, 1e-9);
+    B2S_CUDA(cudaEventRecord(e1));
+    B2S_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    B2S_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *tflops_out = 2.0 * 8.0 * iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return B2S_OK;
+}

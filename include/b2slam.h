@@ -55,6 +55,9 @@ int b2s_device_count(int *count);
  * aggregated runs, 3 = lean loop, 4 = transposed scratch plane, the default).  Not part of the
  * reference surface. */
 int b2s_tune(const char *key, int value);
+/* Same-run FP64 FMA issue peak of the current device in TFLOP/s (8 independent DFMA chains per thread);
+ * bench.py quotes the ICP kernel against it.  Not part of the reference surface. */
+int b2s_measure_fp64_peak(double *tflops_out);
 
 /* ===================================================================== layer 1: device */
 

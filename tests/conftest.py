@@ -11,6 +11,19 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def _ensure_built():
+    """The .so files are build artefacts (git-ignored): build them once if a fresh checkout has none."""
+    import subprocess
+    pkg = os.path.join(ROOT, "a-2d-lidar-based-slam-system-for-wheeled-mobile-robots_b200")
+    if not os.path.isfile(os.path.join(pkg, "libb2slam.so")):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(pkg, "csrc")])
+    if not os.path.isfile(os.path.join(ROOT, "oracle", "_build", "liboracle.so")):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+
+
+_ensure_built()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
