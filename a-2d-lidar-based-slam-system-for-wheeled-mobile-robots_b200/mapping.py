@@ -57,8 +57,15 @@ class Mapping(object):
         """[MAP]:14 occupancy as the reference's float64 (xw, yw) array in {0, 50, 100}: the live array
         update() maintains (like the reference's), rebuilt here if a batched call moved past it."""
         if self._pmap64 is None:
-            self._pmap64 = self._pmap8.astype(np.float64)
+            self._pmap64 = self._host_map().astype(np.float64)
         return self._pmap64
+
+    def _host_map(self):
+        """The int8 host copy of the occupancy, made consistent with a reset that nobody read back."""
+        if getattr(self, "_host_map_blank", False):
+            self._pmap8.fill(50)
+            self._host_map_blank = False
+        return self._pmap8
 
     # ------------------------------------------------------------------ reference methods
 
@@ -83,6 +90,7 @@ class Mapping(object):
             _lib.ptr(self._tiles), self._tiles.shape[0], ctypes.byref(count))
         self._raise_nonfinite(rc)
         _lib.check(rc)
+        self._host_map_blank = False         # after a reset the C side rewrites the whole host map
         if self._pmap64 is None:
             self._pmap64 = self._pmap8.astype(np.float64)
         elif count.value < 0:
@@ -121,6 +129,8 @@ class Mapping(object):
                                         _lib.ptr(cy), ox.shape[0], ox.shape[1], _lib.ptr(out))
         self._raise_nonfinite(rc)
         _lib.check(rc)
+        if want_pmap:
+            self._host_map_blank = False
         return self._pmap8 if want_pmap else None
 
     def update_scans(self, ranges, poses, angle_min, angle_max, clamp_inf_to=30.0, want_pmap=True):
@@ -149,6 +159,8 @@ class Mapping(object):
                                                _lib.ptr(out))
         self._raise_nonfinite(rc)
         _lib.check(rc)
+        if want_pmap:
+            self._host_map_blank = False
         return self._pmap8 if want_pmap else None
 
     def counts(self):
@@ -196,11 +208,12 @@ class Mapping(object):
         miss = np.ascontiguousarray(miss, dtype=np.int32).reshape(self.xw, self.yw)
         _lib.check(self._L.b2s_mapping_write(self._h, _lib.ptr(hit), _lib.ptr(miss)))
         _lib.check(self._L.b2s_mapping_read(self._h, None, None, None, _lib.ptr(self._pmap8)))
+        self._host_map_blank = False
         self._pmap64 = None
 
     def reset(self):
         _lib.check(self._L.b2s_mapping_reset(self._h))
-        self._pmap8.fill(50)
+        self._host_map_blank = True      # the 16 MB host copy is re-filled only if somebody looks at it
         self._pmap64 = None
 
     def device_planes(self):

@@ -103,7 +103,7 @@ def test_mapping_edge_cases(env):
     hit, miss = m.counts()
     assert hit.sum() == 0 and miss.sum() == 100 and int((pm == 0).sum()) == 100 and (pm != 100).all()
     m.reset()
-    assert (m.counts()[1] == 0).all() and (m.pmap == 50).all()
+    assert (m.counts()[1] == 0).all() and (m.pmap == 50).all() and (m.occupancy() == 50).all()
 
 
 def test_rejected_batch_is_rolled_back_exactly(env):
