@@ -38,6 +38,7 @@ extern int g_grid_variant;
 extern int g_icp_src_per_thread;
 extern int g_icp_prune;
 extern int g_icp_block;
+int g_h2d_chunks = 0;  // 0: automatic; 1..8 force the pipeline depth of the host-buffer calls (tuning hook)
 
 // Growable device / pinned-host staging buffer.
 struct Buf {
@@ -145,6 +146,11 @@ extern "C" int b2s_tune(const char *key, int value)
         g_grid_variant = value;
         return B2S_OK;
     }
+    if (strcmp(key, "h2d_chunks") == 0) {
+        B2S_REQUIRE(value >= 0 && value <= 8, "b2s_tune: h2d_chunks must be 0..8");
+        g_h2d_chunks = value;
+        return B2S_OK;
+    }
     if (strcmp(key, "icp_block") == 0) {
         B2S_REQUIRE(value == 0 || value == 16 || value == 32, "b2s_tune: icp_block must be 0, 16 or 32");
         g_icp_block = value;
@@ -248,8 +254,9 @@ extern "C" int b2s_icp_process(b2s_icp *c, const void *tar_xy, const void *src_x
     if ((rc = c->d_T.reserve((size_t)pairs * 9 * sizeof(double)))) return rc;
     if ((rc = c->d_iters.reserve((size_t)pairs * sizeof(int32_t)))) return rc;
     // Pipeline: up to 8 chunks of pairs; chunk k+1 crosses PCIe on the copy stream while chunk k is solved.
-    int nchunk = (int)((tb + sb + (8u << 20) - 1) / (8u << 20));  // ~8 MB of points per chunk
+    int nchunk = (int)((tb + sb + (16u << 20) - 1) / (16u << 20));  // ~16 MB of points per chunk (measured best)
     if (nchunk > 8) nchunk = 8;
+    if (g_h2d_chunks > 0) nchunk = g_h2d_chunks;
     if (nchunk > pairs) nchunk = pairs;
     if (nchunk < 1) nchunk = 1;
     const size_t tpair = (size_t)2 * n_tar * el, spair = (size_t)2 * n_src * el;
@@ -488,6 +495,7 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
         B2S_CUDA(cudaMemsetAsync((char *)m->workspace + GRID_WS_HEADER, 0, grid_dirty_bytes(m->xw, m->yw), m->stream));
         nchunk = (int)((total + (1u << 21) - 1) >> 21);  // ~2M beams per chunk
         if (nchunk > 8) nchunk = 8;
+        if (g_h2d_chunks > 0) nchunk = g_h2d_chunks;
         if (nchunk > scans) nchunk = scans;
         if (nchunk < 1) nchunk = 1;
         for (int k = 0; k <= nchunk; ++k) lo[k] = (int)((long long)scans * k / nchunk);

@@ -52,8 +52,9 @@ const char *b2s_status_string(int status);
 const char *b2s_last_error(void); /* thread-local, valid until the next call on this thread */
 int b2s_device_count(int *count);
 /* Kernel-variant switch for benchmarking (key "grid_variant": 1 = one RED per visit, 2 = warp-
- * aggregated runs, 3 = lean loop, 4 = transposed scratch plane, the default).  Not part of the
- * reference surface. */
+ * aggregated runs, 3 = lean loop, 4 = transposed scratch plane, the default; "icp_prune" 0/1,
+ * "icp_block" 0/16/32, "icp_src_per_thread" 0/2/3/4, "h2d_chunks" 0..8).  Not part of the reference
+ * surface; process-global, set it before the calls it should affect. */
 int b2s_tune(const char *key, int value);
 /* Same-run FP64 FMA issue peak of the current device in TFLOP/s (8 independent DFMA chains per thread);
  * bench.py quotes the ICP kernel against it.  Not part of the reference surface. */
