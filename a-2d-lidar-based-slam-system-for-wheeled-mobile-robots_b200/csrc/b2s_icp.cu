@@ -398,12 +398,10 @@ static int launch_icp_rp(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_
     const size_t smem = 16 + SCRATCH_DOUBLES * sizeof(double) + (size_t)n_tar * sizeof(double2) +
                         (size_t)n_tar * 2 * sizeof(TIn);
     B2S_REQUIRE(smem <= 227 * 1024, "b2s_icp_batch: n_tar too large for shared memory");
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    // opt-in above 48 KB; the attribute is per device and per function, and setting it is cheap
+    if (smem > 48 * 1024)
         B2S_CUDA(cudaFuncSetAttribute(icp_batch_kernel<TIn, R, PRUNE, NN_BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-        configured = smem;
-    }
     // bulk copy needs 16-byte aligned source and size: every pair's target block must qualify
     const size_t pair_bytes = (size_t)2 * n_tar * sizeof(TIn);
     const int use_bulk = ((uintptr_t)tar_xy % 16 == 0) && (pair_bytes % 16 == 0);

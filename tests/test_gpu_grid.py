@@ -440,3 +440,29 @@ def test_single_scan_updates_patch_only_touched_tiles(env):
     om[:] = 0
     env.corc.grid_raycast(oh, om, S, Hx, Hy, ox[0][None], oy[0][None], cx[0:1], cy[0:1])
     assert np.array_equal(pm, env.corc.grid_finalize(oh, om)[1].astype(np.float64))
+
+
+def test_layer1_validate_flags(env):
+    """b2s_grid_validate: NaN -> flags[0], inf in oy / sensor position -> flags[1], inf in ox alone is legal."""
+    L = env.lib.lib()
+    ox, oy, cx, cy = env.synth.grid_scans(1, 4, 100, half_extent_m=5.0)
+
+    def run(ox, oy, cx, cy):
+        dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (ox, oy, cx, cy)]
+        flags = torch.zeros(2, dtype=torch.int32, device="cuda")
+        env.lib.check(L.b2s_grid_validate(dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), dev[3].data_ptr(),
+                                          ox.shape[0], ox.shape[1], flags.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream))
+        return flags.tolist()
+
+    assert run(ox, oy, cx, cy) == [0, 0]
+    a = ox.copy(); a[1, 5] = np.inf
+    assert run(a, oy, cx, cy) == [0, 0]
+    b = oy.copy(); b[1, 5] = np.inf
+    assert run(a, b, cx, cy) == [0, 0]          # the beam is skipped before oy is looked at ([MAP]:30)
+    b = oy.copy(); b[2, 7] = np.inf
+    assert run(ox, b, cx, cy) == [0, 1]
+    a = ox.copy(); a[3, 99] = np.nan
+    assert run(a, oy, cx, cy) == [1, 0]
+    c = cx.copy(); c[0] = -np.inf
+    assert run(ox, oy, c, cy) == [0, 1]

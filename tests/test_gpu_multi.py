@@ -39,6 +39,24 @@ for tag, sparse in (("2", True), ("3", False)):       # tile-sparse and dense fo
         res["pm" + tag] = p2p.update_batch(ox, oy, cx, cy).copy()
     res["hit" + tag], res["miss" + tag] = p2p.counts()
     p2p.close()
+# the library's own NCCL plumbing (dlopen'ed libnccl): communicator from a broadcast unique id, in-place all-reduce
+import ctypes
+from b2slam import _lib
+L = _lib.lib()
+uid = ctypes.create_string_buffer(128)
+if rank == 0:
+    _lib.check(L.b2s_nccl_unique_id(uid))
+box = [uid.raw]
+torch.distributed.broadcast_object_list(box, src=0)
+comm = ctypes.c_void_p()
+_lib.check(L.b2s_nccl_comm_init(ctypes.byref(comm), world, rank, ctypes.create_string_buffer(box[0], 128)))
+ah = torch.full((64, 64), rank + 1, dtype=torch.int32, device="cuda")
+am = torch.full((64, 64), 10 * (rank + 1), dtype=torch.int32, device="cuda")
+_lib.check(L.b2s_grid_allreduce(ah.data_ptr(), am.data_ptr(), ah.numel(), comm, torch.cuda.current_stream().cuda_stream))
+torch.cuda.synchronize()
+res["nccl_hit"] = ah.cpu().numpy()
+res["nccl_miss"] = am.cpu().numpy()
+_lib.check(L.b2s_nccl_comm_destroy(comm))
 xy, _ = synth.room_sequence(9001, 41, 360)
 plo, phi = bdist.sequence_pair_bounds(41, rank, world)
 tar = torch.from_numpy(np.ascontiguousarray(xy[plo:phi])).cuda()
@@ -84,6 +102,7 @@ def test_two_gpu_grid_merge_and_icp_sharding(tmp_path):
             assert np.array_equal(z["hit" + tag], oh) and np.array_equal(z["miss" + tag], om), tag
             assert np.array_equal(z["pm" + tag], corc.grid_finalize(oh, om)[1]), tag
         np.testing.assert_allclose(z["T"], want_T, rtol=0, atol=1e-9)
+        assert (z["nccl_hit"] == sum(range(1, world + 1))).all() and (z["nccl_miss"] == 10 * sum(range(1, world + 1))).all()
 
 
 def test_p2p_merge_single_rank_degenerates_to_finalize():
