@@ -152,12 +152,12 @@ extern "C" int b2s_tune(const char *key, int value)
         return B2S_OK;
     }
     if (strcmp(key, "icp_block") == 0) {
-        B2S_REQUIRE(value == 0 || value == 16 || value == 32, "b2s_tune: icp_block must be 0, 16 or 32");
+        B2S_REQUIRE(value == 0 || value == 8 || value == 16 || value == 32, "b2s_tune: icp_block must be 0, 8, 16 or 32");
         g_icp_block = value;
         return B2S_OK;
     }
     if (strcmp(key, "icp_prune") == 0) {
-        B2S_REQUIRE(value == 0 || value == 1, "b2s_tune: icp_prune must be 0 or 1");
+        B2S_REQUIRE(value >= 0 && value <= 3, "b2s_tune: icp_prune must be 0..3");
         g_icp_prune = value;
         return B2S_OK;
     }

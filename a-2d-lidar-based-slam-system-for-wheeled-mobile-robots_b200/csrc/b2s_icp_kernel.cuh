@@ -1,0 +1,513 @@
+// Batched 2-D point-to-point ICP: one CTA per scan pair, whole iteration loop on chip.
+//
+// Replaces ICP.process ([ICP]:38-88), findNearest ([ICP]:90-114), getTransform ([ICP]:149-179).
+//
+// Per pair the kernel reads 2*(N+M) coordinates once (target rows staged into shared memory
+// with a 1-D bulk async copy + mbarrier), then runs up to max_iter iterations of
+//   brute-force nearest neighbour  (N*M distance evaluations, strict '<', ascending j so the
+//                                   lowest index wins ties exactly like the reference loop)
+//   centroid + 2x2 cross-covariance (two-pass, as the reference centres before multiplying)
+//   closed-form proper rotation     (theta = atan2(W10-W01, W00+W11) == U.Vt with the W9 fix)
+//   src <- T.src, mean-error stop rule
+// and the final re-fit of the original source onto the moved source ([ICP]:81).
+//
+// Numerics: everything is float64, like the reference.  B200 (sm_100a) issues FP64 at half the
+// FP32 rate, and an FP32 search would need a second-best tracker plus a float64 re-check of
+// near ties to keep correspondences identical, which costs about the same issue slots; see
+// DESIGN.md "ICP numerics".  Source points live in registers (SRC_PER_THREAD per thread) for
+// the whole solve; targets live in shared memory as double2 and are read as warp broadcasts.
+#pragma once
+#include "b2s_common.cuh"
+
+#include <math.h>
+
+namespace b2s {
+
+constexpr int FIT_SUMS = 9;
+constexpr int NN_CHAINS = 4;
+constexpr int SUM_PAD = 10;                          // doubles per warp slot (9 sums, padded for 16-byte loads)
+constexpr int SCRATCH_DOUBLES = 2 * 32 * SUM_PAD;    // two buffers (alternating calls) x 32 warps
+
+// Sum of 8 values over the warp with 9 shuffles instead of 40: at offsets 16, 8, 4 every lane hands the half of
+// its values it is not responsible for to its partner and keeps the other half, so the value count halves while
+// the lane count doubles; two plain butterfly steps finish.  Afterwards lane l holds the warp total of value
+// (l >> 2) & 7.  Fixed order, hence run-to-run identical.
+__device__ __forceinline__ double warp_sum8_transposed(const double (&v)[8], int lane)
+{
+    const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
+    double a[4], b[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double send = up16 ? v[i] : v[i + 4], keep = up16 ? v[i + 4] : v[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double send = up8 ? a[i] : a[i + 2], keep = up8 ? a[i + 2] : a[i];
+        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const double send = up4 ? b[0] : b[1], keep = up4 ? b[1] : b[0];
+    double c = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    return c;
+}
+
+// Sum FIT_SUMS doubles over the CTA; every thread returns the same totals (warps added in index order).
+// ONE barrier per call: consecutive calls alternate between two scratch buffers (`phase`), so the next call's
+// writes cannot overtake this call's reads.
+__device__ __forceinline__ void cta_sum9(double (&v)[FIT_SUMS], double *scratch, int &phase)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x + 31) >> 5;
+    double *buf = scratch + phase * (32 * SUM_PAD);
+    phase ^= 1;
+    const double v8[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
+    const double t = warp_sum8_transposed(v8, lane);
+    const double last = warp_sum(v[8]);
+    if ((lane & 3) == 0) buf[warp * SUM_PAD + ((lane >> 2) & 7)] = t;
+    if (lane == 1) buf[warp * SUM_PAD + 8] = last;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < FIT_SUMS; ++k) v[k] = 0.0;
+    for (int w = 0; w < nwarps; ++w) {
+        const double2 *row = reinterpret_cast<const double2 *>(buf + w * SUM_PAD);
+        const double2 p0 = row[0], p1 = row[1], p2 = row[2], p3 = row[3], p4 = row[4];
+        v[0] += p0.x; v[1] += p0.y; v[2] += p1.x; v[3] += p1.y; v[4] += p2.x;
+        v[5] += p2.y; v[6] += p3.x; v[7] += p3.y; v[8] += p4.x;
+    }
+}
+
+// Closed-form Kabsch for row-matched sets given centred sums; returns T (row-major 2x3 part).
+__device__ __forceinline__ void rotation_from_w(double w00, double w01, double w10, double w11,
+                                                double cax, double cay, double cbx, double cby,
+                                                double (&T)[6])
+{
+    const double cc = w00 + w11, ss = w10 - w01;
+    const double h = hypot(cc, ss);
+    double c = 1.0, s = 0.0;
+    if (h > 0.0) {
+        c = cc / h;
+        s = ss / h;
+    }
+    T[0] = c;
+    T[1] = -s;
+    T[2] = cbx - (c * cax - s * cay);
+    T[3] = s;
+    T[4] = c;
+    T[5] = cby - (s * cax + c * cay);
+}
+
+// getTransform ([ICP]:149-179) over the CTA for points held in registers: a[r] -> b[r].
+//
+// The reference centres both sets on their means and then forms W = BB^T.AA, which needs two
+// reductions.  Here every coordinate is taken relative to a FIXED per-pair shift close to the
+// centroids (sa, sb: the centroids of the original source / of the target scan), the first and
+// second moments are reduced together in ONE block reduction, and the exact identity
+//     sum (b-cb)(a-ca)^T = sum (b-sb)(a-sa)^T - n (cb-sb)(ca-sa)^T
+// removes the offset.  Because |c - s| is of the order of the scan-to-scan motion while the spread
+// of a scan is metres, the subtracted term is ~1e-3 of W and costs no accuracy (the parity tests hold
+// the result to 1e-9 of the reference).  `extra` rides along in the same reduction (the distance sum).
+template <int R>
+__device__ __forceinline__ void cta_rigid_fit(const double (&ax)[R], const double (&ay)[R],
+                                              const double (&bx)[R], const double (&by)[R], int count,
+                                              int n, double sax, double say, double sbx, double sby,
+                                              double &extra, double *scratch, int &phase, double (&T)[6])
+{
+    double v[FIT_SUMS];
+#pragma unroll
+    for (int k = 0; k < FIT_SUMS; ++k) v[k] = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+        if (r < count) {
+            const double px = ax[r] - sax, py = ay[r] - say;
+            const double qx = bx[r] - sbx, qy = by[r] - sby;
+            v[0] += px;
+            v[1] += py;
+            v[2] += qx;
+            v[3] += qy;
+            v[4] = fma(qx, px, v[4]);  // W = BB^T . AA  ([ICP]:160)
+            v[5] = fma(qx, py, v[5]);
+            v[6] = fma(qy, px, v[6]);
+            v[7] = fma(qy, py, v[7]);
+        }
+    v[8] = extra;
+    cta_sum9(v, scratch, phase);
+    const double inv = 1.0 / (double)n;
+    const double mpx = v[0] * inv, mpy = v[1] * inv, mqx = v[2] * inv, mqy = v[3] * inv;
+    const double w00 = v[4] - v[2] * mpx, w01 = v[5] - v[2] * mpy;
+    const double w10 = v[6] - v[3] * mpx, w11 = v[7] - v[3] * mpy;
+    (void)mqx;
+    (void)mqy;
+    rotation_from_w(w00, w01, w10, w11, sax + mpx, say + mpy, sbx + mqx, sby + mqy, T);
+    extra = v[8];
+}
+
+// Targets per pruning block: 16 is fastest at 360 beams, 32 at 1080 (measured); chosen per launch.
+
+template <typename TIn, int R, int PRUNE, int NN_BLK>
+__global__ void icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__restrict__ src_xy, int n,
+                                 int m, int max_iter, double tol, double *__restrict__ T_out,
+                                 int32_t *__restrict__ iters_out, int use_bulk)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: [mbarrier 16 B][scratch][tar double2 * m][staging TIn * 2m]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    double *scratch = reinterpret_cast<double *>(smem_raw + 16);
+    double2 *tar = reinterpret_cast<double2 *>(smem_raw + 16 + SCRATCH_DOUBLES * sizeof(double));
+    TIn *stage = reinterpret_cast<TIn *>(tar + m);
+
+    const int pair = blockIdx.x;
+    const int tid = threadIdx.x;
+    const TIn *tar_g = tar_xy + (size_t)pair * 2 * m;
+    const TIn *src_g = src_xy + (size_t)pair * 2 * n;
+
+    // ---- stage the target scan: global -> shared via the bulk-copy engine when alignment allows
+    if (use_bulk) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytes = 2u * (uint32_t)m * (uint32_t)sizeof(TIn);
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(stage, tar_g, bytes, bar);
+        }
+    } else {
+        for (int j = tid; j < 2 * m; j += blockDim.x) stage[j] = tar_g[j];
+    }
+
+    // ---- this thread's source points (registers for the whole solve); overlaps the copy
+    double ox_[R], oy_[R];  // original
+    double sx[R], sy[R];    // moved
+    int count = 0;
+    double first[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = tid + r * blockDim.x;
+        ox_[r] = oy_[r] = 0.0;
+        if (i < n) {
+            ox_[r] = (double)src_g[i];
+            oy_[r] = (double)src_g[n + i];
+            count = r + 1;
+            first[0] += ox_[r];
+            first[1] += oy_[r];
+        }
+        sx[r] = ox_[r];
+        sy[r] = oy_[r];
+    }
+
+    if (use_bulk) mbar_wait(bar, 0);
+    else __syncthreads();
+    for (int j = tid; j < m; j += blockDim.x) {
+        const double2 t = make_double2((double)stage[j], (double)stage[m + j]);
+        tar[j] = t;
+        first[2] += t.x;
+        first[3] += t.y;
+    }
+    // fixed shifts for the one-pass fits: centroid of the original source, centroid of the target scan
+    block_sum<4>(first, scratch);  // its barriers also publish tar[]
+    int phase = 0;
+    // (any fixed value is a valid shift; a scan with NaN / inf points, which are never matched, falls back to 0)
+    auto shift = [](double sum, int cnt) { const double c = sum / (double)cnt; return (fabs(c) < INFINITY) ? c : 0.0; };
+    const double sax = shift(first[0], n), say = shift(first[1], n);
+    const double sbx = shift(first[2], m), sby = shift(first[3], m);
+
+    // ---- pruning bounds: the target scan is cut into blocks of NN_BLK consecutive points, each with the
+    // centre of its bounding box and a radius that covers it (inflated by 1e-9 so rounding can only make
+    // the test below more conservative).  The staging area is free again and holds them: [nblk][4] doubles.
+    const int nblk = (m + NN_BLK - 1) / NN_BLK;
+    double4 *bnd = reinterpret_cast<double4 *>(stage);
+    if (PRUNE) {
+        for (int b = tid; b < nblk; b += blockDim.x) {
+            const int j0 = b * NN_BLK, j1 = min(m, j0 + NN_BLK);
+            double x0 = tar[j0].x, x1 = x0, y0 = tar[j0].y, y1 = y0;
+            for (int j = j0 + 1; j < j1; ++j) {
+                x0 = fmin(x0, tar[j].x); x1 = fmax(x1, tar[j].x);
+                y0 = fmin(y0, tar[j].y); y1 = fmax(y1, tar[j].y);
+            }
+            const double cx = 0.5 * (x0 + x1), cy = 0.5 * (y0 + y1);
+            double rad2 = 0.0;
+            bool finite = true;
+            for (int j = j0; j < j1; ++j) {
+                const double dx = tar[j].x - cx, dy = tar[j].y - cy;
+                const double d2 = fma(dy, dy, dx * dx);
+                finite = finite && (d2 == d2) && (d2 < INFINITY);
+                rad2 = fmax(rad2, d2);
+            }
+            // a block with a NaN / inf point gets an infinite radius: it is never skipped
+            const double rad = finite ? sqrt(rad2) * 1.000000001 + 1e-300 : INFINITY;
+            bnd[b] = make_double4(cx, cy, rad, 0.0);
+        }
+        __syncthreads();
+    }
+
+    // previous match of every source point; seeds the pruning bound (first pass: the target with the
+    // proportional index, which is the same beam when both scans have the same beam count)
+    int arg[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const long long i = tid + r * blockDim.x;
+        arg[r] = (int)min((long long)(m - 1), i * m / n);
+    }
+
+    double prev_err = 0.0;
+    int iters = 0;
+    for (int it = 0; it < max_iter; ++it) {
+        // ---- nearest neighbour ([ICP]:99-106)
+        double best[R];
+        if (!PRUNE) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                best[r] = INFINITY;
+                arg[r] = 0;
+            }
+#pragma unroll 4
+            for (int j = 0; j < m; ++j) {
+                const double2 t = tar[j];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const double dx = sx[r] - t.x, dy = sy[r] - t.y;
+                    const double d2 = fma(dy, dy, dx * dx);
+                    if (d2 < best[r]) {
+                        best[r] = d2;
+                        arg[r] = j;
+                    }
+                }
+            }
+        } else {
+            // Exact search with pruning.  ANY target gives an upper bound ub on the nearest distance; a block
+            // whose every point is provably farther than sqrt(ub) cannot contain the nearest point nor tie
+            // with it, so it is skipped.  Blocks are visited in ascending order and their points compared
+            // with the same strict '<', so the winner (lowest index among equals) is the brute-force one.
+            // The 32 lanes of a warp hold 32 consecutive source points for a given r, so they agree on almost
+            // all blocks; a block is evaluated by the whole warp as soon as one lane needs it.
+            //
+            // PRUNE == 2 puts a warp-level test in front: the 32 source points of the warp lie within g of a
+            // common centre w (g = max over lanes of |p - w| + sqrt(ub), rounded UP to float and reduced with one
+            // REDUX), so a block whose centre is farther than radius + g from w is skipped for every lane by the
+            // triangle inequality.  Lane b tests block b, i.e. 32 blocks per instruction sequence instead of one,
+            // and only the surviving few blocks reach the per-lane test.  NaN / inf anywhere makes the comparison
+            // false, i.e. nothing is skipped.
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const bool real = r < count;
+                const double px = sx[r], py = sy[r];
+                const double2 g = tar[arg[r]];
+                const double gx = px - g.x, gy = py - g.y;
+                const double ub = fma(gy, gy, gx * gx);
+                const double su = sqrt(ub) * 1.000000001;  // NaN stays NaN: then nothing is skipped
+                // NN_CHAINS independent running minima (target j feeds chain j % NN_CHAINS) shorten the serial
+                // compare-select dependency; they are merged below with the lower index winning ties, which is
+                // what one ascending strict '<' scan gives.
+                double bst[NN_CHAINS];
+                int bj[NN_CHAINS];
+#pragma unroll
+                for (int q = 0; q < NN_CHAINS; ++q) {
+                    bst[q] = INFINITY;
+                    bj[q] = 0;
+                }
+                auto visit = [&](int b) {
+                    const int j0 = b * NN_BLK;
+                    if (j0 + NN_BLK <= m) {
+#pragma unroll
+                        for (int jj = 0; jj < NN_BLK; ++jj) {
+                            const double2 t = tar[j0 + jj];
+                            const double dx = px - t.x, dy = py - t.y;
+                            const double d2 = fma(dy, dy, dx * dx);
+                            if (d2 < bst[jj % NN_CHAINS]) {
+                                bst[jj % NN_CHAINS] = d2;
+                                bj[jj % NN_CHAINS] = j0 + jj;
+                            }
+                        }
+                    } else {
+                        for (int j = j0; j < m; ++j) {
+                            const double2 t = tar[j];
+                            const double dx = px - t.x, dy = py - t.y;
+                            const double d2 = fma(dy, dy, dx * dx);
+                            if (d2 < bst[0] || (d2 == bst[0] && j < bj[0])) {
+                                bst[0] = d2;
+                                bj[0] = j;
+                            }
+                        }
+                    }
+                };
+                auto lane_skips = [&](int b) -> bool {
+                    const double4 c = bnd[b];
+                    const double cxd = px - c.x, cyd = py - c.y;
+                    const double dc2 = fma(cyd, cyd, cxd * cxd);
+                    const double reach = c.z + su;
+                    return !real || (dc2 > reach * reach);
+                };
+                if (PRUNE >= 2) {
+                    // common centre: the middle lane's point (any point works; the bound is computed from the actual points)
+                    const int mid = __popc(__ballot_sync(0xffffffffu, real)) >> 1;  // real lanes are the low ones
+                    const double wx = __shfl_sync(0xffffffffu, px, mid), wy = __shfl_sync(0xffffffffu, py, mid);
+                    const double ex = px - wx, ey = py - wy;
+                    const double el = sqrt(fma(ey, ey, ex * ex)) + su;
+                    const float ef = real ? __double2float_ru(el) * 1.000001f : 0.0f;  // NaN bits compare above all
+                    const double gmax = (double)__uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(ef)));
+                    const int lane = tid & 31;
+                    for (int base = 0; base < nblk; base += 32) {
+                        bool keep = false;
+                        if (base + lane < nblk) {
+                            const double4 c = bnd[base + lane];
+                            const double cxd = wx - c.x, cyd = wy - c.y;
+                            const double dc2 = fma(cyd, cyd, cxd * cxd);
+                            const double reach = c.z + gmax;
+                            keep = !(dc2 > reach * reach);
+                        }
+                        unsigned todo = __ballot_sync(0xffffffffu, keep);
+                        while (todo) {
+                            const int b = base + __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            if (PRUNE == 2 && __all_sync(0xffffffffu, lane_skips(b))) continue;  // PRUNE 3: warp test only
+                            visit(b);
+                        }
+                    }
+                } else {
+                    for (int b = 0; b < nblk; ++b) {
+                        if (__all_sync(0xffffffffu, lane_skips(b))) continue;
+                        visit(b);
+                    }
+                }
+#pragma unroll
+                for (int q = 1; q < NN_CHAINS; ++q)
+                    if (bst[q] < bst[0] || (bst[q] == bst[0] && bj[q] < bj[0])) {
+                        bst[0] = bst[q];
+                        bj[0] = bj[q];
+                    }
+                best[r] = bst[0];
+                arg[r] = bj[0];
+            }
+        }
+        // ---- matched targets, distances ([ICP]:69,75)
+        double bx[R], by[R];
+        double dsum = 0.0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (PRUNE && r >= count) arg[r] = 0;  // idle slot: keep the index in range
+            const double2 t = tar[arg[r]];
+            bx[r] = t.x;
+            by[r] = t.y;
+            if (r < count) dsum += (best[r] == INFINITY) ? 0.0 : sqrt(best[r]);
+        }
+        double T[6];
+        cta_rigid_fit<R>(sx, sy, bx, by, count, n, sax, say, sbx, sby, dsum, scratch, phase, T);
+        // ---- src <- T . src ([ICP]:71)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double x = sx[r], y = sy[r];
+            sx[r] = T[0] * x + T[1] * y + T[2];
+            sy[r] = T[3] * x + T[4] * y + T[5];
+        }
+        ++iters;
+        const double err = dsum / (double)n;
+        if (fabs(prev_err - err) < tol) break;  // [ICP]:76, uniform across the CTA
+        prev_err = err;
+    }
+
+    double T[6];
+    double unused = 0.0;
+    cta_rigid_fit<R>(ox_, oy_, sx, sy, count, n, sax, say, sax, say, unused, scratch, phase, T);  // [ICP]:81
+    if (tid == 0) {
+        double *o = T_out + (size_t)pair * 9;
+        o[0] = T[0]; o[1] = T[1]; o[2] = T[2];
+        o[3] = T[3]; o[4] = T[4]; o[5] = T[5];
+        o[6] = 0.0;  o[7] = 0.0;  o[8] = 1.0;
+        if (iters_out) iters_out[pair] = iters;
+    }
+}
+
+extern int g_icp_src_per_thread;
+extern int g_icp_prune;
+extern int g_icp_block;
+
+template <typename TIn, int R, int PRUNE, int NN_BLK>
+static int launch_icp_rp(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_src, int n_tar, int max_iter,
+                        double tol, double *T_out, int32_t *iters_out, void *stream)
+{
+    int threads = (n_src + R - 1) / R;
+    threads = ((threads + 31) / 32) * 32;
+    if (threads < 64) threads = 64;
+    B2S_REQUIRE(threads <= 1024, "b2s_icp_batch: too many source points per scan");
+    const size_t smem = 16 + SCRATCH_DOUBLES * sizeof(double) + (size_t)n_tar * sizeof(double2) +
+                        (size_t)n_tar * 2 * sizeof(TIn);
+    B2S_REQUIRE(smem <= 227 * 1024, "b2s_icp_batch: n_tar too large for shared memory");
+    // opt-in above 48 KB; the attribute is per device and per function, and setting it is cheap
+    if (smem > 48 * 1024)
+        B2S_CUDA(cudaFuncSetAttribute(icp_batch_kernel<TIn, R, PRUNE, NN_BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    // bulk copy needs 16-byte aligned source and size: every pair's target block must qualify
+    const size_t pair_bytes = (size_t)2 * n_tar * sizeof(TIn);
+    const int use_bulk = ((uintptr_t)tar_xy % 16 == 0) && (pair_bytes % 16 == 0);
+    icp_batch_kernel<TIn, R, PRUNE, NN_BLK><<<pairs, threads, smem, (cudaStream_t)stream>>>(
+        tar_xy, src_xy, n_src, n_tar, max_iter, tol, T_out, iters_out, use_bulk);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+
+template <typename TIn, int R>
+static int launch_icp_r(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_src, int n_tar, int max_iter,
+                        double tol, double *T_out, int32_t *iters_out, void *stream)
+{
+    // the block bounds live in the staging area: [ceil(m/blk)][4] doubles must fit in 2*m*sizeof(TIn)
+    const int blk = (g_icp_block == 8 || g_icp_block == 16 || g_icp_block == 32) ? g_icp_block
+                    : (g_icp_prune >= 2 ? (n_tar <= 600 ? 8 : 16) : (n_tar <= 600 ? 16 : 32));  // measured best per mode
+    const bool fits = (size_t)((n_tar + blk - 1) / blk) * 32 <= (size_t)2 * n_tar * sizeof(TIn);
+#define B2S_ICP_GO(P, B) \
+    return launch_icp_rp<TIn, R, P, B>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream)
+    if (g_icp_prune && fits) {
+        if (g_icp_prune == 3) {
+            if (blk == 8) B2S_ICP_GO(3, 8);
+            if (blk == 16) B2S_ICP_GO(3, 16);
+            B2S_ICP_GO(3, 32);
+        }
+        if (g_icp_prune == 2) {
+            if (blk == 8) B2S_ICP_GO(2, 8);
+            if (blk == 16) B2S_ICP_GO(2, 16);
+            B2S_ICP_GO(2, 32);
+        }
+        if (blk == 8) B2S_ICP_GO(1, 16);
+        if (blk == 16) B2S_ICP_GO(1, 16);
+        B2S_ICP_GO(1, 32);
+    }
+    B2S_ICP_GO(0, 16);
+#undef B2S_ICP_GO
+}
+
+template <typename TIn>
+static int launch_icp(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_src, int n_tar,
+                      int max_iter, double tol, double *T_out, int32_t *iters_out, void *stream)
+{
+    B2S_REQUIRE(pairs >= 0 && n_src > 0 && n_tar > 0 && max_iter >= 0, "b2s_icp_batch: bad sizes");
+    if (pairs == 0) return B2S_OK;
+    B2S_REQUIRE(tar_xy && src_xy && T_out, "b2s_icp_batch: null pointer");
+    B2S_REQUIRE(tol == tol, "b2s_icp_batch: NaN tolerance");
+    B2S_REQUIRE(n_src <= 4096, "b2s_icp_batch: n_src above 4096 points per scan is not supported");
+    int r = g_icp_src_per_thread;
+    if (r == 0) {
+        // Work is proportional to the register slots (threads x points per thread, idle ones included).  Three
+        // points per thread is the measured optimum on B200 (360 and 1080 beams) and is taken unless it wastes more
+        // than 10 % over the leanest choice; then 4, then 2.
+        int slots[5] = {0, 0, 0, 0, 0}, least = 1 << 30;
+        for (int c = 2; c <= 4; ++c) {
+            int threads = ((((n_src + c - 1) / c) + 31) / 32) * 32;
+            if (threads < 64) threads = 64;
+            slots[c] = threads <= 1024 ? threads * c : (1 << 30);
+            if (slots[c] < least) least = slots[c];
+        }
+        const int order[3] = {3, 4, 2};
+        for (int k = 0; k < 3 && r == 0; ++k)
+            if (slots[order[k]] < (1 << 30) && (long long)slots[order[k]] * 10 <= (long long)least * 11) r = order[k];
+        if (r == 0) r = 4;
+    }
+    switch (r) {
+    case 2: return launch_icp_r<TIn, 2>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream);
+    case 3: return launch_icp_r<TIn, 3>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream);
+    default: return launch_icp_r<TIn, 4>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream);
+    }
+}
+
+}  // namespace b2s

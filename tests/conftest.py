@@ -16,7 +16,7 @@ def _ensure_built():
     import subprocess
     pkg = os.path.join(ROOT, "a-2d-lidar-based-slam-system-for-wheeled-mobile-robots_b200")
     if not os.path.isfile(os.path.join(pkg, "libb2slam.so")):
-        subprocess.check_call(["make", "-s", "-C", os.path.join(pkg, "csrc")])
+        subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(pkg, "csrc")])
     if not os.path.isfile(os.path.join(ROOT, "oracle", "_build", "liboracle.so")):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
 

@@ -136,12 +136,44 @@ def test_cfg4_shape_sample_vs_oracle(env):
     np.testing.assert_allclose(T[pick], want_T, rtol=0, atol=T_ATOL)
     T2, it2 = env.icp.process_batch(tar[1000:1100], src[1000:1100])     # batch position must not matter
     assert np.array_equal(it2, it[1000:1100]) and np.array_equal(T2, T[1000:1100])
-    assert env.lib.lib().b2s_tune(b"icp_prune", 0) == 0                  # pruned == brute force, bit for bit
+    # every search mode (0 brute force, 1 per-lane block pruning, 2 warp-level + per-lane, 3 warp-level only) and
+    # every pruning block size gives the brute-force answer bit for bit
+    tune = env.lib.lib().b2s_tune
     try:
-        T3, it3 = env.icp.process_batch(tar[:256], src[:256])
+        for prune, block in ((0, 0), (1, 16), (1, 32), (2, 8), (2, 16), (2, 32), (3, 8), (3, 16)):
+            assert tune(b"icp_prune", prune) == 0 and tune(b"icp_block", block) == 0
+            T3, it3 = env.icp.process_batch(tar[:256], src[:256])
+            assert np.array_equal(it3, it[:256]) and np.array_equal(T3, T[:256]), (prune, block)
     finally:
-        env.lib.lib().b2s_tune(b"icp_prune", 1)
-    assert np.array_equal(it3, it[:256]) and np.array_equal(T3, T[:256])
+        tune(b"icp_prune", 2)
+        tune(b"icp_block", 0)
+
+
+def test_non_finite_target_points_are_never_matched(env):
+    """[ICP]:99-106: a NaN / inf distance never satisfies `dist < min_dist`, so such targets are ignored and the
+    solve stays finite; the pruned searches must not skip anything because of them (same bits as brute force)."""
+    tar, src, _ = env.synth.icp_pairs(4242, 6, 360)
+    tar = tar.copy()
+    tar[0, 0, 5] = np.nan
+    tar[1, 1, 200] = np.inf
+    tar[2, :, 17] = np.nan
+    tar[3, 0, 0] = -np.inf
+    tar[4, :, 100:140] = np.nan
+    want_T, want_it = env.corc.icp_batch(tar, src, 30, 1e-3)
+    assert np.isfinite(want_T).all()
+    tune = env.lib.lib().b2s_tune
+    got = {}
+    try:
+        for prune in (0, 1, 2, 3):
+            assert tune(b"icp_prune", prune) == 0
+            got[prune] = env.icp.process_batch(tar, src)
+    finally:
+        tune(b"icp_prune", 2)
+    for prune in (0, 1, 2, 3):
+        T, it = got[prune]
+        assert np.array_equal(it, want_it), prune
+        np.testing.assert_allclose(T, want_T, rtol=0, atol=T_ATOL)
+        assert np.array_equal(T, got[0][0])
 
 
 # ----------------------------------------------------------------------------- adjacent steps (SURVEY 8f-2, 8f-4)
@@ -186,7 +218,7 @@ def test_virtual_scan_vs_reference_loop(env):
 
 def test_random_icp_shapes_vs_oracle(env):
     """Seeded fuzz over cloud sizes (down to one point), duplicated targets, collinear and far-offset clouds,
-    both search modes: identical iteration counts, T within 1e-9 (relative to the cloud scale)."""
+    all search modes and pruning block sizes: identical iteration counts, T within 1e-9 (relative to the cloud scale)."""
     rng = np.random.Generator(np.random.PCG64(777))
     for trial in range(30):
         n = int(rng.choice([1, 2, 3, 5, 16, 17, 31, 33, 64, 100, 127, 250]))
@@ -209,12 +241,14 @@ def test_random_icp_shapes_vs_oracle(env):
         tar = np.ascontiguousarray(tar.astype(np.float32))
         src = np.ascontiguousarray(src.astype(np.float32))
         want_T, want_it = env.corc.icp_batch(tar, src, 30, 1e-3)
-        for prune in (1, 0):
+        for prune in (3, 2, 1, 0):
             assert env.lib.lib().b2s_tune(b"icp_prune", prune) == 0
+            assert env.lib.lib().b2s_tune(b"icp_block", (0, 8, 16, 32)[trial % 4]) == 0
             try:
                 T, it = env.icp.process_batch(tar, src)
             finally:
-                env.lib.lib().b2s_tune(b"icp_prune", 1)
+                env.lib.lib().b2s_tune(b"icp_prune", 2)
+                env.lib.lib().b2s_tune(b"icp_block", 0)
             assert np.array_equal(it, want_it), "trial %d n %d m %d prune %d" % (trial, n, m, prune)
             np.testing.assert_allclose(T, want_T, rtol=0, atol=1e-9 * max(1.0, scale),
                                        err_msg="trial %d n %d m %d prune %d" % (trial, n, m, prune))
