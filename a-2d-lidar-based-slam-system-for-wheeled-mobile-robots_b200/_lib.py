@@ -70,6 +70,7 @@ SIGNATURES = {
     "b2s_icp_create": (_i32, [_pp, _i32]),
     "b2s_icp_destroy": (_i32, [_vp]),
     "b2s_icp_process": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _dbl, _vp, _vp]),
+    "b2s_icp_process_sequence": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _dbl, _vp, _vp]),
     "b2s_icp_find_nearest": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _vp]),
     "b2s_icp_get_transform": (_i32, [_vp, _vp, _vp, _i32, _vp]),
     "b2s_mapping_create": (_i32, [_pp, _i32, _i32, _dbl, _dbl, _dbl, _dbl, _i32]),
@@ -79,6 +80,7 @@ SIGNATURES = {
     "b2s_mapping_update_incremental": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32,
                                               ctypes.POINTER(_i32)]),
     "b2s_mapping_update_ranges": (_i32, [_vp, _vp, _vp, _vp, _dbl, _i32, _i32, _vp]),
+    "b2s_mapping_update_scans": (_i32, [_vp, _vp, _vp, _vp, _dbl, _i32, _i32, _vp]),
     "b2s_mapping_read": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "b2s_mapping_write": (_i32, [_vp, _vp, _vp]),
     "b2s_mapping_planes": (_i32, [_vp, _pp, _pp, _pp]),

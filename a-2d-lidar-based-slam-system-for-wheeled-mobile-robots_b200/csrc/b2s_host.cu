@@ -5,7 +5,9 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <new>
 
@@ -84,6 +86,63 @@ struct DeviceGuard {
     }
 };
 
+// Timeline of one host-buffer call, printed to stderr when B2S_TRACE is set in the environment: CUDA events on
+// the copy and compute streams (ms since the call started on the device) and host timestamps (ms since entry).
+// Diagnostic only; with the variable unset it costs one getenv per call.
+struct Trace {
+    struct Mark {
+        const char *what;
+        int k;
+        cudaEvent_t ev;
+        double host_ms;
+    };
+    bool on = false;
+    int n = 0;
+    Mark marks[96];
+    cudaEvent_t t0 = nullptr;
+    timespec h0;
+    explicit Trace(cudaStream_t s)
+    {
+        on = getenv("B2S_TRACE") != nullptr;
+        if (!on) return;
+        clock_gettime(CLOCK_MONOTONIC, &h0);
+        if (cudaEventCreate(&t0) != cudaSuccess || cudaEventRecord(t0, s) != cudaSuccess) on = false;
+    }
+    double host_now() const
+    {
+        timespec t;
+        clock_gettime(CLOCK_MONOTONIC, &t);
+        return (t.tv_sec - h0.tv_sec) * 1e3 + (t.tv_nsec - h0.tv_nsec) * 1e-6;
+    }
+    void mark(const char *what, int k, cudaStream_t s)  // s == nullptr: host-only mark
+    {
+        if (!on || n >= 96) return;
+        Mark &m = marks[n];
+        m.what = what;
+        m.k = k;
+        m.ev = nullptr;
+        m.host_ms = host_now();
+        if (s && (cudaEventCreate(&m.ev) != cudaSuccess || cudaEventRecord(m.ev, s) != cudaSuccess)) m.ev = nullptr;
+        ++n;
+    }
+    ~Trace()
+    {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        fprintf(stderr, "[b2s trace] %-28s %10s %10s\n", "mark", "device ms", "host ms");
+        for (int i = 0; i < n; ++i) {
+            float ms = -1.0f;
+            if (marks[i].ev) {
+                cudaEventElapsedTime(&ms, t0, marks[i].ev);
+                cudaEventDestroy(marks[i].ev);
+            }
+            fprintf(stderr, "[b2s trace] %-24s %3d %10.3f %10.3f\n", marks[i].what, marks[i].k, ms, marks[i].host_ms);
+        }
+        fprintf(stderr, "[b2s trace] %-28s %10s %10.3f\n", "return", "", host_now());
+        cudaEventDestroy(t0);
+    }
+};
+
 }  // namespace b2s
 
 using namespace b2s;
@@ -106,6 +165,7 @@ struct b2s_mapping {
     int32_t *counters;
     void *workspace;
     Buf d_in, d_datamap, d_pmap, d_packed;
+    Buf h_pose;  // pinned [scans][4] pose table of the call in flight (b2s_mapping_update_scans)
     bool pmap_valid;  // d_pmap holds the occupancy of the current counts
     int8_t *h_packed;  // pinned staging for the dirty tiles
     int32_t *h_ids;
@@ -246,6 +306,7 @@ extern "C" int b2s_icp_process(b2s_icp *c, const void *tar_xy, const void *src_x
     if (pairs == 0) return B2S_OK;
     B2S_REQUIRE(tar_xy && src_xy && T_out, "b2s_icp_process: null pointer");
     DeviceGuard g(c->device);
+    Trace tr(c->stream);
     const size_t el = is_f64 ? 8 : 4;
     const size_t tb = (size_t)pairs * 2 * n_tar * el, sb = (size_t)pairs * 2 * n_src * el;
     int rc;
@@ -268,6 +329,7 @@ extern "C" int b2s_icp_process(b2s_icp *c, const void *tar_xy, const void *src_x
         B2S_CUDA(cudaMemcpyAsync((char *)c->d_src.p + p0 * spair, (const char *)src_xy + p0 * spair, (p1 - p0) * spair,
                                  cudaMemcpyHostToDevice, c->copy_stream));
         B2S_CUDA(cudaEventRecord(c->chunk_ready[k], c->copy_stream));
+        tr.mark("h2d chunk done", k, c->copy_stream);
     }
     for (int k = 0; k < nchunk; ++k) {
         const size_t p0 = (size_t)pairs * k / nchunk, p1 = (size_t)pairs * (k + 1) / nchunk;
@@ -281,12 +343,72 @@ extern "C" int b2s_icp_process(b2s_icp *c, const void *tar_xy, const void *src_x
             rc = b2s_icp_batch_f32((const float *)((char *)c->d_tar.p + p0 * tpair), (const float *)((char *)c->d_src.p + p0 * spair),
                                    (int)(p1 - p0), n_src, n_tar, max_iter, tol, dT, dI, c->stream);
         if (rc) return rc;
+        tr.mark("icp chunk done", k, c->stream);
     }
     B2S_CUDA(cudaMemcpyAsync(T_out, c->d_T.p, (size_t)pairs * 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (iters_out)
         B2S_CUDA(cudaMemcpyAsync(iters_out, c->d_iters.p, (size_t)pairs * sizeof(int32_t), cudaMemcpyDeviceToHost,
                                  c->stream));
+    tr.mark("results d2h done", 0, c->stream);
     B2S_CUDA(cudaStreamSynchronize(c->stream));
+    tr.mark("synchronized", 0, nullptr);
+    return B2S_OK;
+}
+
+// LiDAR odometry over a scan sequence ([LOC9]:159-168, [SLAM]:109-113: the target of pair k is scan k, the source
+// is scan k + 1).  Every scan crosses PCIe ONCE (the pair form ships each scan twice) and the kernel reads the
+// pairs in place: tar = scans, src = scans + one scan, same pair stride.
+extern "C" int b2s_icp_process_sequence(b2s_icp *c, const void *scans_xy, int is_f64, int scans, int n,
+                                        int max_iter, double tol, double *T_out, int32_t *iters_out)
+{
+    B2S_REQUIRE(c, "b2s_icp_process_sequence: null handle");
+    B2S_REQUIRE(scans >= 0 && n > 0 && max_iter >= 0, "b2s_icp_process_sequence: bad sizes");
+    if (scans <= 1) return B2S_OK;
+    B2S_REQUIRE(scans_xy && T_out, "b2s_icp_process_sequence: null pointer");
+    DeviceGuard g(c->device);
+    Trace tr(c->stream);
+    const size_t el = is_f64 ? 8 : 4, scan_bytes = (size_t)2 * n * el;
+    const int pairs = scans - 1;
+    int rc;
+    if ((rc = c->d_tar.reserve((size_t)scans * scan_bytes))) return rc;
+    if ((rc = c->d_T.reserve((size_t)pairs * 9 * sizeof(double)))) return rc;
+    if ((rc = c->d_iters.reserve((size_t)pairs * sizeof(int32_t)))) return rc;
+    int nchunk = (int)(((size_t)scans * scan_bytes + (8u << 20) - 1) / (8u << 20));  // ~8 MB of points per chunk
+    if (nchunk > 8) nchunk = 8;
+    if (g_h2d_chunks > 0) nchunk = g_h2d_chunks;
+    if (nchunk > pairs) nchunk = pairs;
+    if (nchunk < 1) nchunk = 1;
+    // chunk k solves pairs [p0, p1) and therefore needs scans [p0, p1]; scan p0 arrived with the previous chunk
+    for (int k = 0; k < nchunk; ++k) {
+        const size_t p0 = (size_t)pairs * k / nchunk, p1 = (size_t)pairs * (k + 1) / nchunk;
+        const size_t s0 = k == 0 ? 0 : p0 + 1, s1 = p1 + 1;
+        B2S_CUDA(cudaMemcpyAsync((char *)c->d_tar.p + s0 * scan_bytes, (const char *)scans_xy + s0 * scan_bytes,
+                                 (s1 - s0) * scan_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        B2S_CUDA(cudaEventRecord(c->chunk_ready[k], c->copy_stream));
+        tr.mark("h2d chunk done", k, c->copy_stream);
+    }
+    for (int k = 0; k < nchunk; ++k) {
+        const size_t p0 = (size_t)pairs * k / nchunk, p1 = (size_t)pairs * (k + 1) / nchunk;
+        B2S_CUDA(cudaStreamWaitEvent(c->stream, c->chunk_ready[k], 0));
+        const char *tar = (const char *)c->d_tar.p + p0 * scan_bytes;
+        double *dT = (double *)c->d_T.p + p0 * 9;
+        int32_t *dI = (int32_t *)c->d_iters.p + p0;
+        if (is_f64)
+            rc = b2s_icp_batch_f64((const double *)tar, (const double *)(tar + scan_bytes), (int)(p1 - p0), n, n, max_iter, tol,
+                                   dT, dI, c->stream);
+        else
+            rc = b2s_icp_batch_f32((const float *)tar, (const float *)(tar + scan_bytes), (int)(p1 - p0), n, n, max_iter, tol,
+                                   dT, dI, c->stream);
+        if (rc) return rc;
+        tr.mark("icp chunk done", k, c->stream);
+    }
+    B2S_CUDA(cudaMemcpyAsync(T_out, c->d_T.p, (size_t)pairs * 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (iters_out)
+        B2S_CUDA(cudaMemcpyAsync(iters_out, c->d_iters.p, (size_t)pairs * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                 c->stream));
+    tr.mark("results d2h done", 0, c->stream);
+    B2S_CUDA(cudaStreamSynchronize(c->stream));
+    tr.mark("synchronized", 0, nullptr);
     return B2S_OK;
 }
 
@@ -408,6 +530,7 @@ extern "C" int b2s_mapping_destroy(b2s_mapping *m)
     if (m->h_ids) cudaFreeHost(m->h_ids);
     m->d_packed.release();
     m->d_in.release(); m->d_datamap.release(); m->d_pmap.release();
+    m->h_pose.release();
     for (int k = 0; k < 8; ++k)
         if (m->chunk_ready[k]) cudaEventDestroy(m->chunk_ready[k]);
     if (m->inputs_free) cudaEventDestroy(m->inputs_free);
@@ -435,8 +558,9 @@ struct HostBatch {
     bool fused;
     const float *ox, *oy, *cx, *cy;  // endpoints form
     const float *ranges;             // fused form
-    const double *pose4, *beam_cs;
+    const double *pose4, *beam_cs;   // pose4 [scans][4] = x, y, cos yaw, sin yaw ...
     double clamp;
+    const double *poses3;            // ... or poses3 [scans][3] = x, y, yaw: the table is built here, chunk by chunk
 };
 
 // Mapping.update for a batch, all-or-nothing like a Python exception raised before the loop.
@@ -452,6 +576,7 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
                         int *tiles_count = nullptr)
 {
     DeviceGuard g(m->device);
+    Trace tr(m->stream);
     const size_t total = (size_t)scans * beams;
     int rc;
     int nchunk = 0;
@@ -499,12 +624,29 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
         if (nchunk > scans) nchunk = scans;
         if (nchunk < 1) nchunk = 1;
         for (int k = 0; k <= nchunk; ++k) lo[k] = (int)((long long)scans * k / nchunk);
+        const double *pose4 = hb.pose4;
+        double *table = nullptr;
+        if (hb.fused && hb.poses3) {
+            m->h_pose.pinned = true;
+            if ((rc = m->h_pose.reserve((size_t)scans * 4 * sizeof(double)))) return rc;
+            pose4 = table = (double *)m->h_pose.p;
+        }
+        // per chunk: [pose table] -> copies on the copy stream -> ray-cast on the compute stream once they landed.
+        // The host runs ahead of the device, so the table of chunk k+1 (u2T's math.cos / math.sin, [SLAM]:130-137:
+        // the same libm calls) is computed while chunk k crosses PCIe and is ray-cast.
         for (int k = 0; k < nchunk; ++k) {
             const size_t s0 = (size_t)lo[k], ns = (size_t)(lo[k + 1] - lo[k]);
             cudaStream_t cs = m->copy_stream;
             if (hb.fused) {
+                if (table)
+                    for (size_t s = s0; s < s0 + ns; ++s) {
+                        table[4 * s] = hb.poses3[3 * s];
+                        table[4 * s + 1] = hb.poses3[3 * s + 1];
+                        table[4 * s + 2] = cos(hb.poses3[3 * s + 2]);
+                        table[4 * s + 3] = sin(hb.poses3[3 * s + 2]);
+                    }
                 B2S_CUDA(cudaMemcpyAsync(d_a + s0 * beams, hb.ranges + s0 * beams, ns * beams * sizeof(float), cudaMemcpyHostToDevice, cs));
-                B2S_CUDA(cudaMemcpyAsync(d_pose + 4 * s0, hb.pose4 + 4 * s0, ns * 4 * sizeof(double), cudaMemcpyHostToDevice, cs));
+                B2S_CUDA(cudaMemcpyAsync(d_pose + 4 * s0, pose4 + 4 * s0, ns * 4 * sizeof(double), cudaMemcpyHostToDevice, cs));
             } else {
                 B2S_CUDA(cudaMemcpyAsync(d_a + s0 * beams, hb.ox + s0 * beams, ns * beams * sizeof(float), cudaMemcpyHostToDevice, cs));
                 B2S_CUDA(cudaMemcpyAsync(d_b + s0 * beams, hb.oy + s0 * beams, ns * beams * sizeof(float), cudaMemcpyHostToDevice, cs));
@@ -512,10 +654,10 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
                 B2S_CUDA(cudaMemcpyAsync(d_d + s0, hb.cy + s0, ns * sizeof(float), cudaMemcpyHostToDevice, cs));
             }
             B2S_CUDA(cudaEventRecord(m->chunk_ready[k], cs));
-        }
-        for (int k = 0; k < nchunk; ++k) {
+            tr.mark("h2d chunk done", k, cs);
             B2S_CUDA(cudaStreamWaitEvent(m->stream, m->chunk_ready[k], 0));
             if ((rc = launch(k, +1, m->counters))) return rc;
+            tr.mark("ray-cast chunk done", k, m->stream);
         }
     }
     int32_t cnt[2 * B2S_CNT_WORDS] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -523,7 +665,7 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
     const size_t tile_bytes = (size_t)GRID_TILE * GRID_TILE;
     // Incremental read-back: when the host already holds the previous map and this call touched few tiles,
     // finalize and ship only those tiles (a single scan dirties ~20 of the 4096 tiles of a 4096^2 map).
-    bool patched = false;
+    bool patched = false, have_cnt = false;
     if (tiles_count) *tiles_count = -1;
     if (pmap_out && incremental && m->pmap_valid && total > 0) {
         if ((rc = m->d_pmap.reserve(cells))) return rc;
@@ -539,6 +681,7 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
         if (rc) return rc;
         B2S_CUDA(cudaMemcpyAsync(cnt, m->counters, sizeof(cnt), cudaMemcpyDeviceToHost, m->stream));
         B2S_CUDA(cudaStreamSynchronize(m->stream));
+        have_cnt = true;
         const int nd = cnt[B2S_CNT_WORDS];
         const bool bad = cnt[B2S_CNT_NONFINITE] || cnt[B2S_CNT_OVERFLOW] || cnt[B2S_CNT_TOO_LONG] > 0;
         if (!bad && nd <= PACK_CAP) {
@@ -562,20 +705,25 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
             patched = true;
         }
         if (bad) m->pmap_valid = false;  // handled (and rolled back) below with a full refresh
-    } else if (total > 0) {
-        B2S_CUDA(cudaMemcpyAsync(cnt, m->counters, sizeof(cnt), cudaMemcpyDeviceToHost, m->stream));
     }
+    const bool cnt_pending = !have_cnt && total > 0;
     if (pmap_out && !patched) {
         if ((rc = m->d_pmap.reserve(cells))) return rc;
         rc = b2s_grid_finalize(m->hit, m->miss, m->xw, m->yw, m->w_hit, m->w_miss, m->thresh, nullptr,
                                (int8_t *)m->d_pmap.p, m->stream);
         if (rc) return rc;
+        tr.mark("finalize done", 0, m->stream);
         B2S_CUDA(cudaMemcpyAsync(pmap_out, m->d_pmap.p, cells, cudaMemcpyDeviceToHost, m->stream));
+        tr.mark("map d2h done", 0, m->stream);
         m->pmap_valid = true;
     } else if (!pmap_out) {
         m->pmap_valid = false;  // counts moved on without the device map
     }
+    // (a pageable destination makes this copy synchronous, so it goes last: everything else is already queued)
+    if (cnt_pending) B2S_CUDA(cudaMemcpyAsync(cnt, m->counters, sizeof(cnt), cudaMemcpyDeviceToHost, m->stream));
+    tr.mark("all enqueued", 0, nullptr);
     B2S_CUDA(cudaStreamSynchronize(m->stream));
+    tr.mark("synchronized", 0, nullptr);
     const int saw_nan = cnt[B2S_CNT_NONFINITE], saw_inf = cnt[B2S_CNT_OVERFLOW];
     if (saw_nan || saw_inf || cnt[B2S_CNT_TOO_LONG] > 0) {
         for (int k = 0; k < nchunk; ++k)
@@ -606,7 +754,7 @@ extern "C" int b2s_mapping_update(b2s_mapping *m, const float *ox, const float *
     B2S_REQUIRE(m, "b2s_mapping_update: null handle");
     B2S_REQUIRE(scans >= 0 && beams >= 0, "b2s_mapping_update: negative count");
     B2S_REQUIRE((size_t)scans * beams == 0 || (ox && oy && cx && cy), "b2s_mapping_update: null pointer");
-    HostBatch hb = {false, ox, oy, cx, cy, nullptr, nullptr, nullptr, 0.0};
+    HostBatch hb = {false, ox, oy, cx, cy, nullptr, nullptr, nullptr, 0.0, nullptr};
     return mapping_update_impl(m, hb, scans, beams, pmap_out);
 }
 
@@ -617,7 +765,7 @@ extern "C" int b2s_mapping_update_incremental(b2s_mapping *m, const float *ox, c
     B2S_REQUIRE(m && pmap_inout, "b2s_mapping_update_incremental: null pointer");
     B2S_REQUIRE(scans >= 0 && beams >= 0 && tiles_cap >= 0, "b2s_mapping_update_incremental: negative count");
     B2S_REQUIRE((size_t)scans * beams == 0 || (ox && oy && cx && cy), "b2s_mapping_update_incremental: null pointer");
-    HostBatch hb = {false, ox, oy, cx, cy, nullptr, nullptr, nullptr, 0.0};
+    HostBatch hb = {false, ox, oy, cx, cy, nullptr, nullptr, nullptr, 0.0, nullptr};
     return mapping_update_impl(m, hb, scans, beams, pmap_inout, true, tiles_out, tiles_cap, tiles_count);
 }
 
@@ -628,7 +776,18 @@ extern "C" int b2s_mapping_update_ranges(b2s_mapping *m, const float *ranges, co
     B2S_REQUIRE(m, "b2s_mapping_update_ranges: null handle");
     B2S_REQUIRE(scans >= 0 && beams >= 0, "b2s_mapping_update_ranges: negative count");
     B2S_REQUIRE((size_t)scans * beams == 0 || (ranges && pose4 && beam_cs), "b2s_mapping_update_ranges: null pointer");
-    HostBatch hb = {true, nullptr, nullptr, nullptr, nullptr, ranges, pose4, beam_cs, clamp_inf_to};
+    HostBatch hb = {true, nullptr, nullptr, nullptr, nullptr, ranges, pose4, beam_cs, clamp_inf_to, nullptr};
+    return mapping_update_impl(m, hb, scans, beams, pmap_out);
+}
+
+extern "C" int b2s_mapping_update_scans(b2s_mapping *m, const float *ranges, const double *poses3,
+                                        const double *beam_cs, double clamp_inf_to, int scans, int beams,
+                                        int8_t *pmap_out)
+{
+    B2S_REQUIRE(m, "b2s_mapping_update_scans: null handle");
+    B2S_REQUIRE(scans >= 0 && beams >= 0, "b2s_mapping_update_scans: negative count");
+    B2S_REQUIRE((size_t)scans * beams == 0 || (ranges && poses3 && beam_cs), "b2s_mapping_update_scans: null pointer");
+    HostBatch hb = {true, nullptr, nullptr, nullptr, nullptr, ranges, nullptr, beam_cs, clamp_inf_to, poses3};
     return mapping_update_impl(m, hb, scans, beams, pmap_out);
 }
 

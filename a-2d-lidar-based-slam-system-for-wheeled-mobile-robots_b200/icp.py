@@ -120,3 +120,29 @@ class ICP(object):
             self.tolerance if tolerance is None else float(tolerance),
             _lib.ptr(T), _lib.ptr(iters)))
         return T.reshape(P, 3, 3), iters
+
+    def process_sequence(self, scans, max_iter=None, tolerance=None):
+        """LiDAR odometry over a scan stream, the loop of [LOC9]:159-168 / [SLAM]:109-113: pair k matches scan
+        k + 1 (source) onto scan k (target), i.e. process_batch(scans[:-1], scans[1:]) bit for bit, but every scan
+        crosses PCIe once instead of twice.
+
+        scans (K,2,N) float64 or float32.  Returns (T (K-1,3,3) float64, iterations (K-1,) int32).
+        """
+        scans = np.asarray(scans)
+        if scans.ndim != 3 or scans.shape[1] != 2:
+            raise ValueError("expected scans (K,2,N), got %s" % (scans.shape,))
+        f64 = scans.dtype != np.float32
+        scans = np.ascontiguousarray(scans, dtype=np.float64 if f64 else np.float32)
+        K, N = scans.shape[0], scans.shape[2]
+        P = max(K - 1, 0)
+        T = np.empty((P, 9))
+        iters = np.empty(P, dtype=np.int32)
+        if P > 0 and N == 0:
+            raise ValueError("empty scans")
+        if P > 0:
+            _lib.check(self._L.b2s_icp_process_sequence(
+                self._h, _lib.ptr(scans), 1 if f64 else 0, K, N,
+                self.max_iter if max_iter is None else int(max_iter),
+                self.tolerance if tolerance is None else float(tolerance),
+                _lib.ptr(T), _lib.ptr(iters)))
+        return T.reshape(P, 3, 3), iters

@@ -145,18 +145,20 @@ class Mapping(object):
         ranges = np.ascontiguousarray(ranges, dtype=np.float32)
         if ranges.ndim == 1:
             ranges = ranges.reshape(1, -1)
-        pose4 = scan.pose_table(poses)
-        if pose4.shape[0] != ranges.shape[0]:
-            raise ValueError("need one pose per scan, got %d poses for %d scans" % (pose4.shape[0], ranges.shape[0]))
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 3)
+        if poses.shape[0] != ranges.shape[0]:
+            raise ValueError("need one pose per scan, got %d poses for %d scans" % (poses.shape[0], ranges.shape[0]))
         key = (float(angle_min), float(angle_max), ranges.shape[1])
         if getattr(self, "_beam_key", None) != key:
             self._beam_cs = scan.beam_table(angle_min, angle_max, ranges.shape[1])
             self._beam_key = key
         out = self._pmap8 if want_pmap else None
         self._pmap64 = None
-        rc = self._L.b2s_mapping_update_ranges(self._h, _lib.ptr(ranges), _lib.ptr(pose4), _lib.ptr(self._beam_cs),
-                                               float(clamp_inf_to or 0.0), ranges.shape[0], ranges.shape[1],
-                                               _lib.ptr(out))
+        # cos / sin of the yaw (u2T, slam_ekf.py:130-137) are taken inside the call, chunk by chunk, while the
+        # previous chunk is on its way to the device
+        rc = self._L.b2s_mapping_update_scans(self._h, _lib.ptr(ranges), _lib.ptr(poses), _lib.ptr(self._beam_cs),
+                                              float(clamp_inf_to or 0.0), ranges.shape[0], ranges.shape[1],
+                                              _lib.ptr(out))
         self._raise_nonfinite(rc)
         _lib.check(rc)
         if want_pmap:

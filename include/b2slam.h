@@ -219,6 +219,11 @@ int b2s_icp_destroy(b2s_icp *icp);
 int b2s_icp_process(b2s_icp *icp, const void *tar_xy, const void *src_xy, int is_f64, int pairs,
                     int n_src, int n_tar, int max_iter, double tol, double *T_out,
                     int32_t *iters_out);
+/* ICP.process over the consecutive pairs of a scan stream: calc_odometry's loop, [LOC9]:159-168 / [SLAM]:109-113
+ * (target = scan k, source = scan k + 1).  scans_xy [scans][2][n]; T_out [scans-1][9], iters_out [scans-1] (may be
+ * NULL).  Same results as b2s_icp_process on the pairs, half the host-to-device bytes. */
+int b2s_icp_process_sequence(b2s_icp *icp, const void *scans_xy, int is_f64, int scans, int n, int max_iter,
+                             double tol, double *T_out, int32_t *iters_out);
 int b2s_icp_find_nearest(b2s_icp *icp, const double *src_xy, int n, const double *tar_xy, int m,
                          double *dist_out, int64_t *idx_out);
 int b2s_icp_get_transform(b2s_icp *icp, const double *src_xy, const double *tar_xy, int n,
@@ -248,6 +253,10 @@ int b2s_mapping_update_incremental(b2s_mapping *map, const float *ox, const floa
 int b2s_mapping_update_ranges(b2s_mapping *map, const float *ranges, const double *pose4,
                               const double *beam_cs, double clamp_inf_to, int scans, int beams,
                               int8_t *pmap_out);
+/* The same with raw poses: poses3 [scans][3] = x, y, yaw.  cos / sin of the yaw (u2T, [SLAM]:130-137: math.cos,
+ * math.sin) are evaluated with libm inside the call, one pipeline chunk ahead of the device. */
+int b2s_mapping_update_scans(b2s_mapping *m, const float *ranges, const double *poses3, const double *beam_cs,
+                             double clamp_inf_to, int scans, int beams, int8_t *pmap_out);
 /* Snapshot to host; any pointer may be NULL. */
 int b2s_mapping_read(b2s_mapping *map, int32_t *hit, int32_t *miss, float *datamap, int8_t *pmap);
 /* Overwrite the count planes from host arrays [xw][yw] (checkpoint restore; the reference has none). */

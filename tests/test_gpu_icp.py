@@ -125,6 +125,32 @@ def test_device_pointer_abi_and_sequence_chain(env):
     assert np.allclose(traj[-1], st, rtol=0, atol=1e-7)
 
 
+def test_sequence_form_equals_pair_form(env):
+    """process_sequence == process_batch on the consecutive pairs, bit for bit (float32 and float64 input),
+    including streams too short to hold a pair and chunk boundaries of the copy pipeline."""
+    xy, _ = env.synth.room_sequence(9001, 300, 360)
+    for arr in (xy, xy.astype(np.float64)):
+        T, it = env.icp.process_sequence(arr)
+        T2, it2 = env.icp.process_batch(arr[:-1], arr[1:])
+        assert T.shape == (299, 3, 3) and np.array_equal(T, T2) and np.array_equal(it, it2)
+    tune = env.lib.lib().b2s_tune
+    try:
+        for chunks in (1, 3, 8):
+            assert tune(b"h2d_chunks", chunks) == 0
+            T3, it3 = env.icp.process_sequence(xy[:50])
+            assert np.array_equal(T3, T2[:49]) and np.array_equal(it3, it2[:49])
+    finally:
+        tune(b"h2d_chunks", 0)
+    want_T, want_it = env.corc.icp_batch(xy[:8], xy[1:9], 30, 1e-3)
+    assert np.array_equal(it[:8], want_it)
+    np.testing.assert_allclose(T[:8], want_T, rtol=0, atol=T_ATOL)
+    for k in (0, 1):
+        Te, ite = env.icp.process_sequence(xy[:k])
+        assert Te.shape == (0, 3, 3) and ite.shape == (0,)
+    T1, _ = env.icp.process_sequence(xy[:2])
+    assert np.array_equal(T1[0], T2[0])
+
+
 def test_cfg4_shape_sample_vs_oracle(env):
     """cfg 4 shape (1080-beam independent pairs) at a size the oracle finishes in seconds, plus a
     size-independent check on a larger batch: every pair of a batch gives the result it gives alone."""
