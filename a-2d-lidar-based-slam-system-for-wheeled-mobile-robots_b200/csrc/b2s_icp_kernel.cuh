@@ -68,13 +68,27 @@ __device__ __forceinline__ void cta_sum9(double (&v)[FIT_SUMS], double *scratch,
     if ((lane & 3) == 0) buf[warp * SUM_PAD + ((lane >> 2) & 7)] = t;
     if (lane == 1) buf[warp * SUM_PAD + 8] = last;
     __syncthreads();
+    if (nwarps <= 4) {
+        // few warps: every thread adds the columns itself (nine independent chains, shortest latency; this sits
+        // on the critical path right after the barrier)
 #pragma unroll
-    for (int k = 0; k < FIT_SUMS; ++k) v[k] = 0.0;
-    for (int w = 0; w < nwarps; ++w) {
-        const double2 *row = reinterpret_cast<const double2 *>(buf + w * SUM_PAD);
-        const double2 p0 = row[0], p1 = row[1], p2 = row[2], p3 = row[3], p4 = row[4];
-        v[0] += p0.x; v[1] += p0.y; v[2] += p1.x; v[3] += p1.y; v[4] += p2.x;
-        v[5] += p2.y; v[6] += p3.x; v[7] += p3.y; v[8] += p4.x;
+        for (int k = 0; k < FIT_SUMS; ++k) v[k] = 0.0;
+        for (int w = 0; w < nwarps; ++w) {
+            const double2 *row = reinterpret_cast<const double2 *>(buf + w * SUM_PAD);
+            const double2 p0 = row[0], p1 = row[1], p2 = row[2], p3 = row[3], p4 = row[4];
+            v[0] += p0.x; v[1] += p0.y; v[2] += p1.x; v[3] += p1.y; v[4] += p2.x;
+            v[5] += p2.y; v[6] += p3.x; v[7] += p3.y; v[8] += p4.x;
+        }
+    } else {
+        // many warps: lane k adds up column k (1 load + 1 add per warp instead of 5 + 9), then the nine totals
+        // are broadcast.  Both forms add the warps in index order.
+        double acc = 0.0;
+        if (lane < FIT_SUMS) {
+#pragma unroll 4
+            for (int w = 0; w < nwarps; ++w) acc += buf[w * SUM_PAD + lane];
+        }
+#pragma unroll
+        for (int k = 0; k < FIT_SUMS; ++k) v[k] = __shfl_sync(0xffffffffu, acc, k);
     }
 }
 
@@ -145,8 +159,10 @@ __device__ __forceinline__ void cta_rigid_fit(const double (&ax)[R], const doubl
 
 // Targets per pruning block: 16 is fastest at 360 beams, 32 at 1080 (measured); chosen per launch.
 
+// Register cap: 80 per thread keeps 6 CTAs of 128 threads (360 beams) / 2 CTAs of 384 threads (1080 beams)
+// resident per SM; without it the allocation of some instances drifts above that step from build to build.
 template <typename TIn, int R, int PRUNE, int NN_BLK>
-__global__ void icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__restrict__ src_xy, int n,
+__global__ void __maxnreg__(R <= 3 ? 80 : 104) icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__restrict__ src_xy, int n,
                                  int m, int max_iter, double tol, double *__restrict__ T_out,
                                  int32_t *__restrict__ iters_out, int use_bulk)
 {
@@ -179,23 +195,20 @@ __global__ void icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__re
     }
 
     // ---- this thread's source points (registers for the whole solve); overlaps the copy
-    double ox_[R], oy_[R];  // original
-    double sx[R], sy[R];    // moved
+    double sx[R], sy[R];  // moved by every iteration; the originals are read again for the final fit
     int count = 0;
     double first[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int i = tid + r * blockDim.x;
-        ox_[r] = oy_[r] = 0.0;
+        sx[r] = sy[r] = 0.0;
         if (i < n) {
-            ox_[r] = (double)src_g[i];
-            oy_[r] = (double)src_g[n + i];
+            sx[r] = (double)src_g[i];
+            sy[r] = (double)src_g[n + i];
             count = r + 1;
-            first[0] += ox_[r];
-            first[1] += oy_[r];
+            first[0] += sx[r];
+            first[1] += sy[r];
         }
-        sx[r] = ox_[r];
-        sy[r] = oy_[r];
     }
 
     if (use_bulk) mbar_wait(bar, 0);
@@ -297,7 +310,11 @@ __global__ void icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__re
                 const double2 g = tar[arg[r]];
                 const double gx = px - g.x, gy = py - g.y;
                 const double ub = fma(gy, gy, gx * gx);
-                const double su = sqrt(ub) * 1.000000001;  // NaN stays NaN: then nothing is skipped
+                // sqrt(ub) rounded UP in float (two instructions instead of a double-precision square root); an
+                // upper bound is all the tests need.  NaN stays NaN, overflow gives inf: then nothing is skipped.
+                // The factor (> 1 + 2^-23) covers the rounding of the double-precision tests below.
+                const float suf = __fmul_ru(__fsqrt_ru(__double2float_ru(ub)), 1.0000002f);
+                const double su = (double)suf;
                 // NN_CHAINS independent running minima (target j feeds chain j % NN_CHAINS) shorten the serial
                 // compare-select dependency; they are merged below with the lower index winning ties, which is
                 // what one ascending strict '<' scan gives.
@@ -345,8 +362,8 @@ __global__ void icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__re
                     const int mid = __popc(__ballot_sync(0xffffffffu, real)) >> 1;  // real lanes are the low ones
                     const double wx = __shfl_sync(0xffffffffu, px, mid), wy = __shfl_sync(0xffffffffu, py, mid);
                     const double ex = px - wx, ey = py - wy;
-                    const double el = sqrt(fma(ey, ey, ex * ex)) + su;
-                    const float ef = real ? __double2float_ru(el) * 1.000001f : 0.0f;  // NaN bits compare above all
+                    const float ef = real ? __fadd_ru(__fsqrt_ru(__double2float_ru(fma(ey, ey, ex * ex))), suf) * 1.000001f
+                                          : 0.0f;  // every step rounds up; NaN bits compare above all
                     const double gmax = (double)__uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(ef)));
                     const int lane = tid & 31;
                     for (int base = 0; base < nblk; base += 32) {
@@ -410,6 +427,13 @@ __global__ void icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__re
 
     double T[6];
     double unused = 0.0;
+    double ox_[R], oy_[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = tid + r * blockDim.x;
+        ox_[r] = (i < n) ? (double)src_g[i] : 0.0;
+        oy_[r] = (i < n) ? (double)src_g[n + i] : 0.0;
+    }
     cta_rigid_fit<R>(ox_, oy_, sx, sy, count, n, sax, say, sax, say, unused, scratch, phase, T);  // [ICP]:81
     if (tid == 0) {
         double *o = T_out + (size_t)pair * 9;
