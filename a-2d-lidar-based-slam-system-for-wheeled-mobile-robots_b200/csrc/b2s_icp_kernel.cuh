@@ -98,11 +98,21 @@ __device__ __forceinline__ void rotation_from_w(double w00, double w01, double w
                                                 double (&T)[6])
 {
     const double cc = w00 + w11, ss = w10 - w01;
-    const double h = hypot(cc, ss);
+    // (c, s) = (cc, ss) / |(cc, ss)|.  Every thread of the CTA evaluates this after each reduction, so the common
+    // case takes one reciprocal square root (<= 2 ulp on c and s, far inside the 1e-9 the tests hold) instead of
+    // hypot + two divisions; sums outside the safely squarable range take the careful path.
+    const double h2 = fma(cc, cc, ss * ss);
     double c = 1.0, s = 0.0;
-    if (h > 0.0) {
-        c = cc / h;
-        s = ss / h;
+    if (h2 > 1e-280 && h2 < 1e280) {
+        const double inv = rsqrt(h2);
+        c = cc * inv;
+        s = ss * inv;
+    } else {
+        const double h = hypot(cc, ss);
+        if (h > 0.0) {
+            c = cc / h;
+            s = ss / h;
+        }
     }
     T[0] = c;
     T[1] = -s;
