@@ -217,6 +217,10 @@ class ShardedMappingP2P(object):
         self.pmap_host = torch.empty((self.xw, self.yw), dtype=torch.int8).pin_memory()
         self._token = torch.zeros(1, dtype=torch.int32, device="cuda")
         self._in = None
+        self._in_r = None
+        self._beam_key = None
+        self._copy_stream = None
+        self.h2d_chunks = 0   # 0: automatic pipeline depth of the host-buffer calls; > 0 forces it
         torch.cuda.synchronize()
         barrier()
 
@@ -224,23 +228,21 @@ class ShardedMappingP2P(object):
         if self.world > 1:
             dist.all_reduce(self._token)  # stream-ordered: completes only when every rank got here
 
-    def update_device(self, ox, oy, cx, cy, events=None):
-        """Scans already on the device (float32 CUDA tensors).  Leaves the merged map in pmap_dev.
-        `events`: optional (start, stop) torch.cuda.Event pair recorded around the ray-cast."""
+    def _begin(self):
+        """Bring the private delta planes back to zero (sparse: only the tiles the previous call dirtied)."""
         L = self._lib.lib()
         stream = torch.cuda.current_stream().cuda_stream
-        if self.sparse:   # only the tiles the previous call dirtied are non-zero: re-zero those, clear the map
+        if self.sparse:
             self._lib.check(L.b2s_grid_clear_dirty(self.d_hit.data_ptr(), self.d_miss.data_ptr(), self.xw, self.yw,
                                                    self.workspace.data_ptr(), stream))
         else:
             self.d_hit.zero_()
             self.d_miss.zero_()
-        S, Hx, Hy = self.scale
-        if events:
-            events[0].record()
-        self._dev.grid_raycast(self.d_hit, self.d_miss, S, Hx, Hy, ox, oy, cx, cy, workspace=self.workspace)
-        if events:
-            events[1].record()
+
+    def _merge(self):
+        """ONE peer-memory kernel per rank: reduce-scatter + accumulate + finalize + all-gather of the map."""
+        L = self._lib.lib()
+        stream = torch.cuda.current_stream().cuda_stream
         w_hit, w_miss, thr = self.weights
         if self.sparse:
             if self.world > 1:   # the gather of the dirty maps is also the fence after every rank's ray-cast
@@ -258,17 +260,83 @@ class ShardedMappingP2P(object):
                 self.g_hit.data_ptr(), self.g_miss.data_ptr(), w_hit, w_miss, thr, stream))
         self._fence()
 
+    def update_device(self, ox, oy, cx, cy, events=None):
+        """Scans already on the device (float32 CUDA tensors).  Leaves the merged map in pmap_dev.
+        `events`: optional (start, stop) torch.cuda.Event pair recorded around the ray-cast."""
+        self._begin()
+        S, Hx, Hy = self.scale
+        if events:
+            events[0].record()
+        self._dev.grid_raycast(self.d_hit, self.d_miss, S, Hx, Hy, ox, oy, cx, cy, workspace=self.workspace)
+        if events:
+            events[1].record()
+        self._merge()
+
+    def _pipeline(self, host, dev, scans, beams, raycast):
+        """Chunked H2D on a side stream overlapped with the ray-cast of the previous chunk (the host-buffer calls
+        of Mapping do the same inside the library), then the merge and the read-back of the map."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        nchunk = self.h2d_chunks or max(1, min(8, (scans * beams + (1 << 21) - 1) >> 21))   # ~2M beams per chunk
+        nchunk = max(1, min(nchunk, scans))
+        bounds = [scans * k // nchunk for k in range(nchunk + 1)]
+        self._copy_stream.wait_stream(main)   # the device input buffers are free once earlier work is done
+        ready = []
+        with torch.cuda.stream(self._copy_stream):
+            for k in range(nchunk):
+                lo, hi = bounds[k], bounds[k + 1]
+                for d, h in zip(dev, host):
+                    d[lo:hi].copy_(h[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+                ready.append(ev)
+        self._begin()
+        for k in range(nchunk):
+            main.wait_event(ready[k])
+            raycast(bounds[k], bounds[k + 1])
+        self._merge()
+        self.pmap_host.copy_(self.pmap_dev, non_blocking=True)
+        main.synchronize()
+        return self.pmap_host.numpy()
+
     def update_batch(self, ox, oy, cx, cy):
         """ox, oy (K,N), cx, cy (K,) float32 host arrays -> merged int8 occupancy (host, pinned)."""
         host = [torch.from_numpy(a) if not isinstance(a, torch.Tensor) else a for a in (ox, oy, cx, cy)]
         if self._in is None or self._in[0].shape != host[0].shape:
             self._in = [torch.empty(h.shape, dtype=torch.float32, device="cuda") for h in host]
-        for d, h in zip(self._in, host):
-            d.copy_(h, non_blocking=True)
-        self.update_device(*self._in)
-        self.pmap_host.copy_(self.pmap_dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return self.pmap_host.numpy()
+        d = self._in
+        S, Hx, Hy = self.scale
+
+        def raycast(lo, hi):
+            self._dev.grid_raycast(self.d_hit, self.d_miss, S, Hx, Hy, d[0][lo:hi], d[1][lo:hi], d[2][lo:hi], d[3][lo:hi],
+                                   workspace=self.workspace)
+        return self._pipeline(host, d, host[0].shape[0], host[0].shape[1], raycast)
+
+    def update_scans(self, ranges, poses, angle_min, angle_max, clamp_inf_to=30.0):
+        """Fused ingestion (Mapping.update_scans) for this rank's stream: ranges (K,N) float32 + poses (K,3) instead
+        of world-frame endpoints, half the bytes over PCIe.  Returns the merged int8 occupancy (host, pinned)."""
+        import numpy as np
+        from b2slam import scan
+        ranges = torch.from_numpy(np.ascontiguousarray(ranges, dtype=np.float32)) if not isinstance(ranges, torch.Tensor) else ranges
+        pose4 = torch.from_numpy(scan.pose_table(poses))
+        K, N = ranges.shape
+        if pose4.shape[0] != K:
+            raise ValueError("need one pose per scan, got %d poses for %d scans" % (pose4.shape[0], K))
+        key = (float(angle_min), float(angle_max), N)
+        if self._beam_key != key:
+            self._beam_cs = torch.from_numpy(scan.beam_table(angle_min, angle_max, N)).cuda()
+            self._beam_key = key
+        if self._in_r is None or self._in_r[0].shape != ranges.shape:
+            self._in_r = [torch.empty((K, N), dtype=torch.float32, device="cuda"),
+                          torch.empty((K, 4), dtype=torch.float64, device="cuda")]
+        d = self._in_r
+        S, Hx, Hy = self.scale
+
+        def raycast(lo, hi):
+            self._dev.grid_raycast_ranges(self.d_hit, self.d_miss, S, Hx, Hy, d[0][lo:hi], d[1][lo:hi], self._beam_cs,
+                                          clamp_inf_to, workspace=self.workspace)
+        return self._pipeline([ranges, pose4], d, K, N, raycast)
 
     def counts(self):
         """Full (hit, miss) planes assembled from the ranks' shards (for checks; not a hot path)."""

@@ -324,22 +324,30 @@ def bench_grid(args, rank, world, torch, devapi, bdist, synth):
 
     # ---- the same scans in raw form (ranges + poses) through the fused-ingestion call: half the H2D bytes
     fused = None
-    if world == 1:
+    if world == 1 or p2p is not None:
         import math
         ranges, poses = synth.grid_scan_ranges(12001 + rank, K, N)
         keep_r, h_ranges = pinned(ranges)
-        m.reset()
-        m.update_scans(h_ranges, poses, -math.pi, math.pi)
+        if world == 1:
+            def fused_step():
+                m.reset()
+                m.update_scans(h_ranges, poses, -math.pi, math.pi)
+            api = "Mapping.update_scans (b2s_mapping_update_scans)"
+        else:
+            def fused_step():
+                p2p.update_scans(keep_r, poses, -math.pi, math.pi)
+            api = "dist.ShardedMappingP2P.update_scans"
+        fused_step()
+        bdist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            m.reset()
-            m.update_scans(h_ranges, poses, -math.pi, math.pi)
+            fused_step()
         torch.cuda.synchronize()
-        fs = time.perf_counter() - t0
-        fused = {"value": K * N * e2e_steps / fs, "unit": "beams/s", "h2d_bytes_per_step": 4 * K * N + 32 * K,
-                 "d2h_bytes_per_step": G * G, "api": "Mapping.update_scans (b2s_mapping_update_scans)",
-                 "ms_per_step": fs / e2e_steps * 1e3}
+        fs = bdist.max_over_ranks(time.perf_counter() - t0)
+        bdist.barrier()
+        fused = {"value": world * K * N * e2e_steps / fs, "unit": "beams/s", "h2d_bytes_per_step": 4 * K * N + 32 * K,
+                 "d2h_bytes_per_step": G * G, "api": api, "ms_per_step": fs / e2e_steps * 1e3}
 
     peak, peak_src = measured_peaks()
     achieved = algo_bytes / (ray_avg_ms * 1e-3) / 1e9
@@ -466,8 +474,8 @@ def bench_icp(args, rank, world, torch, devapi, bdist, synth):
                      "fp64_peak_tflops_nominal": FP64_PEAK_TFLOPS,
                      "fp64_peak_tflops_measured_same_run": fp64_peak.value,
                      "fp64_note": "the pruned search executes a fraction of the brute-force evaluations, so the equivalent "
-                                  "rate may exceed the peak; executed-instruction utilisation is in profiles/r1 (ncu: "
-                                  "FP64 pipe 54 %, issue slots 67 %)"},
+                                  "rate may exceed the peak; executed-instruction utilisation is in profiles/r1/"
+                                  "icp_batch_warp_pruned_360_ncu_full.txt (ncu: FP64 pipe 52 %, issue slots 70 %)"},
         "e2e": {"value": world * P * e2e_steps / e2e_s, "unit": "pairs/s",
                 "h2d_bytes_per_step": int(h_seq.nbytes), "d2h_bytes_per_step": P * 76,
                 "api": "ICP.process_sequence (b2s_icp_process_sequence)", "ms_per_step": e2e_s / e2e_steps * 1e3},
@@ -542,7 +550,7 @@ def main():
     ap.add_argument("--icp-scans", type=int, default=ICP_SCANS)
     ap.add_argument("--grid-variant", type=int, default=0)
     ap.add_argument("--icp-r", type=int, default=0, help="force ICP source points per thread (tuning)")
-    ap.add_argument("--icp-prune", type=int, default=-1, help="0: brute-force NN, 1: pruned exact NN (tuning)")
+    ap.add_argument("--icp-prune", type=int, default=-1, help="0: brute-force NN, 1: per-lane block pruning, 2: warp-level + per-lane (default), 3: warp-level only (tuning)")
     ap.add_argument("--merge", default="p2p", choices=["p2p", "nccl"], help="multi-GPU grid merge")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only", default="both", choices=["both", "primary"])

@@ -133,4 +133,17 @@ def test_p2p_merge_single_rank_degenerates_to_finalize():
             touched = (lh != 0) | (lm != 0)
             tx, ty = np.nonzero(touched)
             assert dirty[tx // 64, ty // 64].all()
+        # fused ingestion and a forced pipeline depth on the same object: raw scans + poses, chunked copies
+        import math
+        from b2slam import scan
+        sm.h2d_chunks = 3
+        ranges, poses = synth.grid_scan_ranges(77, 40, 360, half_extent_m=15.0)
+        pm = sm.update_scans(ranges, poses, -math.pi, math.pi).copy()
+        corc.grid_raycast_ranges(oh, om, S, Hx, Hy, ranges, scan.pose_table(poses), scan.beam_table(-math.pi, math.pi, 360), 30.0)
+        ox, oy, cx, cy = synth.grid_scans(4, 40, 360, half_extent_m=15.0)
+        pm = sm.update_batch(ox, oy, cx, cy).copy()
+        corc.grid_raycast(oh, om, S, Hx, Hy, ox, oy, cx, cy)
+        h, m = sm.counts()
+        assert np.array_equal(h, oh) and np.array_equal(m, om), (xw, yw, sparse, "pipelined")
+        assert np.array_equal(pm, corc.grid_finalize(oh, om)[1]), (xw, yw, sparse, "pipelined")
         sm.close()
