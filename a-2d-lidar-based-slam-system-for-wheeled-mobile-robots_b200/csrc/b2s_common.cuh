@@ -45,14 +45,17 @@ inline size_t grid_dirty_bytes(int xw, int yw)
 
 int grid_raycast_signed(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m, double off_x,
                         double off_y, const float *ox, const float *oy, const float *cx, const float *cy,
-                        int scans, int beams, int32_t *counters, void *workspace, int sign, void *stream);
+                        int scans, int beams, int32_t *counters, void *workspace, int sign, void *stream,
+                        bool fold = true);
 int grid_finalize_dirty(const int32_t *hit, const int32_t *miss, int xw, int yw, double w_hit, double w_miss,
                         double thresh, void *workspace, int8_t *pmap, int8_t *packed, int32_t *tile_ids,
                         int32_t *counter, int cap, void *stream);
 int grid_raycast_ranges_signed(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m, double off_x,
                                double off_y, const float *ranges, const double *pose4, const double *beam_cs,
                                double clamp, int scans, int beams, int32_t *counters, void *workspace, int sign,
-                               void *stream);
+                               void *stream, bool fold = true);
+// fold = false leaves the y-major visits of this launch in the transposed scratch plane (and its bounding box in
+// the workspace header): a caller that ray-casts a batch as several launches folds once, with the last of them.
 
 // ---------------------------------------------------------------- warp / block reductions
 

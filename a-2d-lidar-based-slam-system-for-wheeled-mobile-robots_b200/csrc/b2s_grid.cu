@@ -713,7 +713,7 @@ namespace b2s {
 // rejected batch (sign -1).
 static int raycast_v4_launch(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m, double off_x,
                              double off_y, const ScanInput &in, bool fused, int scans, int beams, int32_t *counters,
-                             void *workspace, int sign, void *stream)
+                             void *workspace, int sign, void *stream, bool fold)
 {
     B2S_REQUIRE(hit && miss && workspace, "b2s_grid_raycast_ws: null pointer");
     B2S_REQUIRE(xw > 0 && yw > 0 && (long long)xw * yw < (1ll << 30), "b2s_grid_raycast_ws: grid size");
@@ -740,6 +740,7 @@ static int raycast_v4_launch(int32_t *hit, int32_t *miss, int xw, int yw, double
     }
 #undef B2S_V4
     B2S_CUDA(cudaGetLastError());
+    if (!fold) return B2S_OK;
     dim3 fgrid((xw + 31) / 32, (yw + 31) / 32);
     grid_fold_kernel<<<fgrid, 256, 0, st>>>(miss, scratch_t, ws, xw, yw);
     B2S_CUDA(cudaGetLastError());
@@ -749,25 +750,25 @@ static int raycast_v4_launch(int32_t *hit, int32_t *miss, int xw, int yw, double
 
 int grid_raycast_signed(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m, double off_x,
                         double off_y, const float *ox, const float *oy, const float *cx, const float *cy,
-                        int scans, int beams, int32_t *counters, void *workspace, int sign, void *stream)
+                        int scans, int beams, int32_t *counters, void *workspace, int sign, void *stream, bool fold)
 {
     B2S_REQUIRE(ox && oy && cx && cy, "b2s_grid_raycast_ws: null pointer");
     ScanInput in = {ox, oy, cx, cy, nullptr, nullptr, nullptr, 0.0};
     return raycast_v4_launch(hit, miss, xw, yw, cells_per_m, off_x, off_y, in, false, scans, beams, counters,
-                             workspace, sign, stream);
+                             workspace, sign, stream, fold);
 }
 
 int grid_raycast_ranges_signed(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m, double off_x,
                                double off_y, const float *ranges, const double *pose4, const double *beam_cs,
                                double clamp, int scans, int beams, int32_t *counters, void *workspace, int sign,
-                               void *stream)
+                               void *stream, bool fold)
 {
     B2S_REQUIRE(ranges && pose4 && beam_cs, "b2s_grid_raycast_ranges: null pointer");
     B2S_REQUIRE((uintptr_t)pose4 % 16 == 0 && (uintptr_t)beam_cs % 16 == 0,
                 "b2s_grid_raycast_ranges: pose and beam tables must be 16-byte aligned");
     ScanInput in = {nullptr, nullptr, nullptr, nullptr, ranges, pose4, beam_cs, clamp};
     return raycast_v4_launch(hit, miss, xw, yw, cells_per_m, off_x, off_y, in, true, scans, beams, counters,
-                             workspace, sign, stream);
+                             workspace, sign, stream, fold);
 }
 }  // namespace b2s
 

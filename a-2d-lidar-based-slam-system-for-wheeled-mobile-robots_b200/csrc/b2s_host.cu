@@ -40,7 +40,8 @@ extern int g_grid_variant;
 extern int g_icp_src_per_thread;
 extern int g_icp_prune;
 extern int g_icp_block;
-int g_h2d_chunks = 0;  // 0: automatic; 1..8 force the pipeline depth of the host-buffer calls (tuning hook)
+constexpr int MAX_CHUNKS = 16;
+int g_h2d_chunks = 0;  // 0: automatic; 1..MAX_CHUNKS force the pipeline depth of the host-buffer calls (tuning hook)
 
 // Growable device / pinned-host staging buffer.
 struct Buf {
@@ -150,7 +151,7 @@ using namespace b2s;
 struct b2s_icp {
     int device;
     cudaStream_t stream, copy_stream;
-    cudaEvent_t chunk_ready[8];
+    cudaEvent_t chunk_ready[MAX_CHUNKS];
     Buf d_tar, d_src, d_T, d_iters, d_aux;
 };
 
@@ -160,7 +161,7 @@ struct b2s_mapping {
     double xyreso, cells_per_m, off_x, off_y;
     double w_hit, w_miss, thresh;
     cudaStream_t stream, copy_stream;
-    cudaEvent_t chunk_ready[8], inputs_free;
+    cudaEvent_t chunk_ready[MAX_CHUNKS], inputs_free;
     int32_t *hit, *miss;
     int32_t *counters;
     void *workspace;
@@ -207,7 +208,7 @@ extern "C" int b2s_tune(const char *key, int value)
         return B2S_OK;
     }
     if (strcmp(key, "h2d_chunks") == 0) {
-        B2S_REQUIRE(value >= 0 && value <= 8, "b2s_tune: h2d_chunks must be 0..8");
+        B2S_REQUIRE(value >= 0 && value <= MAX_CHUNKS, "b2s_tune: h2d_chunks must be 0..16");
         g_h2d_chunks = value;
         return B2S_OK;
     }
@@ -269,10 +270,10 @@ extern "C" int b2s_icp_create(b2s_icp **out, int device)
     if (!c) return B2S_ERR_NOMEM;
     c->device = device;
     c->stream = c->copy_stream = nullptr;
-    for (int k = 0; k < 8; ++k) c->chunk_ready[k] = nullptr;
+    for (int k = 0; k < MAX_CHUNKS; ++k) c->chunk_ready[k] = nullptr;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
-    for (int k = 0; k < 8 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&c->chunk_ready[k], cudaEventDisableTiming);
+    for (int k = 0; k < MAX_CHUNKS && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&c->chunk_ready[k], cudaEventDisableTiming);
     if (e != cudaSuccess) {
         int rc = cuda_fail(e, "b2s_icp_create");
         b2s_icp_destroy(c);
@@ -289,7 +290,7 @@ extern "C" int b2s_icp_destroy(b2s_icp *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     c->d_tar.release(); c->d_src.release(); c->d_T.release(); c->d_iters.release(); c->d_aux.release();
-    for (int k = 0; k < 8; ++k)
+    for (int k = 0; k < MAX_CHUNKS; ++k)
         if (c->chunk_ready[k]) cudaEventDestroy(c->chunk_ready[k]);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -492,12 +493,12 @@ extern "C" int b2s_mapping_create(b2s_mapping **out, int xw, int yw, double xyre
     m->h_packed = nullptr;
     m->h_ids = nullptr;
     m->stream = m->copy_stream = nullptr;
-    for (int k = 0; k < 8; ++k) m->chunk_ready[k] = nullptr;
+    for (int k = 0; k < MAX_CHUNKS; ++k) m->chunk_ready[k] = nullptr;
     m->inputs_free = nullptr;
     const size_t plane = (size_t)xw * yw * sizeof(int32_t);
     cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
-    for (int k = 0; k < 8 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&m->chunk_ready[k], cudaEventDisableTiming);
+    for (int k = 0; k < MAX_CHUNKS && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&m->chunk_ready[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->inputs_free, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->hit, plane);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->miss, plane);
@@ -531,7 +532,7 @@ extern "C" int b2s_mapping_destroy(b2s_mapping *m)
     m->d_packed.release();
     m->d_in.release(); m->d_datamap.release(); m->d_pmap.release();
     m->h_pose.release();
-    for (int k = 0; k < 8; ++k)
+    for (int k = 0; k < MAX_CHUNKS; ++k)
         if (m->chunk_ready[k]) cudaEventDestroy(m->chunk_ready[k]);
     if (m->inputs_free) cudaEventDestroy(m->inputs_free);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
@@ -564,7 +565,7 @@ struct HostBatch {
 };
 
 // Mapping.update for a batch, all-or-nothing like a Python exception raised before the loop.
-//   * the batch is cut into up to 8 chunks of scans; chunk k+1 crosses PCIe on the copy stream while
+//   * the batch is cut into up to 16 chunks of scans; chunk k+1 crosses PCIe on the copy stream while
 //     chunk k is screened and ray-cast on the compute stream
 //   * beams that int() would raise on ([MAP]:33-36) are skipped and counted by the kernels, so applying
 //     a chunk before the verdict on the whole batch is known is safe: a rejected batch is taken back
@@ -580,19 +581,21 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
     const size_t total = (size_t)scans * beams;
     int rc;
     int nchunk = 0;
-    int lo[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int lo[MAX_CHUNKS + 1] = {0};
     float *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_d = nullptr;  // ox|oy|cx|cy  or  ranges
     double *d_pose = nullptr, *d_cs = nullptr;
+    // (the transposed scratch plane of the ray-cast is folded back once, with the last chunk)
     auto launch = [&](int k, int sign, int32_t *counters) -> int {
         const size_t s0 = (size_t)lo[k];
         const int ns = lo[k + 1] - lo[k];
+        const bool fold = (k == nchunk - 1);
         if (hb.fused)
             return grid_raycast_ranges_signed(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y,
                                               d_a + s0 * beams, d_pose + 4 * s0, d_cs, hb.clamp, ns, beams, counters,
-                                              m->workspace, sign, m->stream);
+                                              m->workspace, sign, m->stream, fold);
         return grid_raycast_signed(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y,
                                    d_a + s0 * beams, d_b + s0 * beams, d_c + s0, d_d + s0, ns, beams, counters,
-                                   m->workspace, sign, m->stream);
+                                   m->workspace, sign, m->stream, fold);
     };
     if (total > 0) {
         const size_t pts = total * sizeof(float), a_pts = (pts + 15) & ~(size_t)15;
@@ -618,7 +621,7 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
         B2S_CUDA(cudaMemsetAsync(m->counters, 0, 2 * B2S_CNT_WORDS * sizeof(int32_t), m->stream));
         // the dirty-tile map describes THIS call
         B2S_CUDA(cudaMemsetAsync((char *)m->workspace + GRID_WS_HEADER, 0, grid_dirty_bytes(m->xw, m->yw), m->stream));
-        nchunk = (int)((total + (1u << 21) - 1) >> 21);  // ~2M beams per chunk
+        nchunk = (int)((total + (1u << 21) - 1) >> 21);  // ~2M beams per chunk; deeper pipelines measured no faster
         if (nchunk > 8) nchunk = 8;
         if (g_h2d_chunks > 0) nchunk = g_h2d_chunks;
         if (nchunk > scans) nchunk = scans;

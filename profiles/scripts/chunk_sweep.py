@@ -1,30 +1,34 @@
-"""Pipeline depth sweep of the host-buffer calls (1 GPU): ICP cfg 2 batch and grid cfg 3 batch."""
-import os, sys, time
+"""Pipeline depth of the host-buffer grid calls on one box: update_batch (endpoints) and update_scans (raw scans)."""
+import math, os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import b2slam
 from b2slam import synth, _lib
 
-xy, _ = synth.room_sequence(9001, 10000, 360)
-pt = torch.from_numpy(np.ascontiguousarray(xy[:-1])).pin_memory(); ps = torch.from_numpy(np.ascontiguousarray(xy[1:])).pin_memory()
-ht, hs = pt.numpy(), ps.numpy()
-icp = b2slam.ICP()
-host = synth.grid_scans(12001, 16384, 1080)
-pin = [torch.from_numpy(a).pin_memory() for a in host]
+G, K, N = 4096, 16384, 1080
+pin = [torch.from_numpy(a).pin_memory() for a in synth.grid_scans(12001, K, N)]
 h = [p.numpy() for p in pin]
-m = b2slam.Mapping(4096, 4096, 0.05)
+ranges, poses = synth.grid_scan_ranges(12001, K, N)
+pr = torch.from_numpy(ranges).pin_memory()
+hr = pr.numpy()
+m = b2slam.Mapping(G, G, 0.05)
 
 
-def timeit(fn, reps=10):
-    fn(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        fn()
+def timeit(fn, reps=8):
+    fn(); fn()
     torch.cuda.synchronize()
-    return (time.perf_counter() - t0) / reps * 1e3
+    best = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        best = min(best, (time.perf_counter() - t0) / reps * 1e3)
+    return best
 
 
-for c in (0, 1, 2, 3, 4, 6, 8):
-    _lib.check(_lib.lib().b2s_tune(b"h2d_chunks", c))
-    print("chunks %d  icp %.3f ms  grid(+map) %.3f ms" % (c, timeit(lambda: icp.process_batch(ht, hs)),
-                                                          timeit(lambda: m.update_batch(*h))))
+for rnd in range(2):
+    for c in (0, 4, 8, 12, 16):
+        _lib.check(_lib.lib().b2s_tune(b"h2d_chunks", c))
+        a = timeit(lambda: (m.reset(), m.update_batch(*h)))
+        b = timeit(lambda: (m.reset(), m.update_scans(hr, poses, -math.pi, math.pi)))
+        print("chunks %2d (0 = automatic): update_batch %.3f ms   update_scans %.3f ms" % (c, a, b), flush=True)
