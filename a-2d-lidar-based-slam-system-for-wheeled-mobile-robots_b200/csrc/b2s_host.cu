@@ -150,8 +150,10 @@ using namespace b2s;
 
 struct b2s_icp {
     int device;
-    cudaStream_t stream, copy_stream;
-    cudaEvent_t chunk_ready[MAX_CHUNKS];
+    // stream: results / read-back; stream2: every other chunk's solve, so that the long-tail CTAs of one chunk (pairs
+    // need 2..max_iter iterations) overlap the next chunk instead of idling the device; copy_stream: H2D
+    cudaStream_t stream, stream2, copy_stream;
+    cudaEvent_t chunk_ready[MAX_CHUNKS], joined;
     Buf d_tar, d_src, d_T, d_iters, d_aux;
 };
 
@@ -269,10 +271,13 @@ extern "C" int b2s_icp_create(b2s_icp **out, int device)
     b2s_icp *c = new (std::nothrow) b2s_icp();
     if (!c) return B2S_ERR_NOMEM;
     c->device = device;
-    c->stream = c->copy_stream = nullptr;
+    c->stream = c->stream2 = c->copy_stream = nullptr;
+    c->joined = nullptr;
     for (int k = 0; k < MAX_CHUNKS; ++k) c->chunk_ready[k] = nullptr;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->joined, cudaEventDisableTiming);
     for (int k = 0; k < MAX_CHUNKS && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&c->chunk_ready[k], cudaEventDisableTiming);
     if (e != cudaSuccess) {
         int rc = cuda_fail(e, "b2s_icp_create");
@@ -288,11 +293,14 @@ extern "C" int b2s_icp_destroy(b2s_icp *c)
     if (!c) return B2S_OK;
     DeviceGuard g(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     c->d_tar.release(); c->d_src.release(); c->d_T.release(); c->d_iters.release(); c->d_aux.release();
     for (int k = 0; k < MAX_CHUNKS; ++k)
         if (c->chunk_ready[k]) cudaEventDestroy(c->chunk_ready[k]);
+    if (c->joined) cudaEventDestroy(c->joined);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return B2S_OK;
@@ -334,17 +342,22 @@ extern "C" int b2s_icp_process(b2s_icp *c, const void *tar_xy, const void *src_x
     }
     for (int k = 0; k < nchunk; ++k) {
         const size_t p0 = (size_t)pairs * k / nchunk, p1 = (size_t)pairs * (k + 1) / nchunk;
-        B2S_CUDA(cudaStreamWaitEvent(c->stream, c->chunk_ready[k], 0));
+        cudaStream_t ks = (k & 1) ? c->stream2 : c->stream;
+        B2S_CUDA(cudaStreamWaitEvent(ks, c->chunk_ready[k], 0));
         double *dT = (double *)c->d_T.p + p0 * 9;
         int32_t *dI = (int32_t *)c->d_iters.p + p0;
         if (is_f64)
             rc = b2s_icp_batch_f64((const double *)((char *)c->d_tar.p + p0 * tpair), (const double *)((char *)c->d_src.p + p0 * spair),
-                                   (int)(p1 - p0), n_src, n_tar, max_iter, tol, dT, dI, c->stream);
+                                   (int)(p1 - p0), n_src, n_tar, max_iter, tol, dT, dI, ks);
         else
             rc = b2s_icp_batch_f32((const float *)((char *)c->d_tar.p + p0 * tpair), (const float *)((char *)c->d_src.p + p0 * spair),
-                                   (int)(p1 - p0), n_src, n_tar, max_iter, tol, dT, dI, c->stream);
+                                   (int)(p1 - p0), n_src, n_tar, max_iter, tol, dT, dI, ks);
         if (rc) return rc;
-        tr.mark("icp chunk done", k, c->stream);
+        tr.mark("icp chunk done", k, ks);
+    }
+    if (nchunk > 1) {
+        B2S_CUDA(cudaEventRecord(c->joined, c->stream2));
+        B2S_CUDA(cudaStreamWaitEvent(c->stream, c->joined, 0));
     }
     B2S_CUDA(cudaMemcpyAsync(T_out, c->d_T.p, (size_t)pairs * 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (iters_out)
@@ -358,16 +371,11 @@ extern "C" int b2s_icp_process(b2s_icp *c, const void *tar_xy, const void *src_x
 
 // LiDAR odometry over a scan sequence ([LOC9]:159-168, [SLAM]:109-113: the target of pair k is scan k, the source
 // is scan k + 1).  Every scan crosses PCIe ONCE (the pair form ships each scan twice) and the kernel reads the
-// pairs in place: tar = scans, src = scans + one scan, same pair stride.
-extern "C" int b2s_icp_process_sequence(b2s_icp *c, const void *scans_xy, int is_f64, int scans, int n,
-                                        int max_iter, double tol, double *T_out, int32_t *iters_out)
+// pairs in place: tar = scans, src = scans + one scan, same pair stride.  Enqueues copies and kernels only; the
+// results stay in c->d_T / c->d_iters for the caller to read back or chain.
+static int icp_sequence_enqueue(b2s_icp *c, Trace &tr, const void *scans_xy, int is_f64, int scans, int n, int max_iter,
+                                double tol)
 {
-    B2S_REQUIRE(c, "b2s_icp_process_sequence: null handle");
-    B2S_REQUIRE(scans >= 0 && n > 0 && max_iter >= 0, "b2s_icp_process_sequence: bad sizes");
-    if (scans <= 1) return B2S_OK;
-    B2S_REQUIRE(scans_xy && T_out, "b2s_icp_process_sequence: null pointer");
-    DeviceGuard g(c->device);
-    Trace tr(c->stream);
     const size_t el = is_f64 ? 8 : 4, scan_bytes = (size_t)2 * n * el;
     const int pairs = scans - 1;
     int rc;
@@ -390,21 +398,71 @@ extern "C" int b2s_icp_process_sequence(b2s_icp *c, const void *scans_xy, int is
     }
     for (int k = 0; k < nchunk; ++k) {
         const size_t p0 = (size_t)pairs * k / nchunk, p1 = (size_t)pairs * (k + 1) / nchunk;
-        B2S_CUDA(cudaStreamWaitEvent(c->stream, c->chunk_ready[k], 0));
+        cudaStream_t ks = (k & 1) ? c->stream2 : c->stream;
+        B2S_CUDA(cudaStreamWaitEvent(ks, c->chunk_ready[k], 0));
         const char *tar = (const char *)c->d_tar.p + p0 * scan_bytes;
         double *dT = (double *)c->d_T.p + p0 * 9;
         int32_t *dI = (int32_t *)c->d_iters.p + p0;
         if (is_f64)
             rc = b2s_icp_batch_f64((const double *)tar, (const double *)(tar + scan_bytes), (int)(p1 - p0), n, n, max_iter, tol,
-                                   dT, dI, c->stream);
+                                   dT, dI, ks);
         else
             rc = b2s_icp_batch_f32((const float *)tar, (const float *)(tar + scan_bytes), (int)(p1 - p0), n, n, max_iter, tol,
-                                   dT, dI, c->stream);
+                                   dT, dI, ks);
         if (rc) return rc;
-        tr.mark("icp chunk done", k, c->stream);
+        tr.mark("icp chunk done", k, ks);
     }
+    if (nchunk > 1) {  // everything downstream (read-back, pose chain) is ordered on c->stream
+        B2S_CUDA(cudaEventRecord(c->joined, c->stream2));
+        B2S_CUDA(cudaStreamWaitEvent(c->stream, c->joined, 0));
+    }
+    return B2S_OK;
+}
+
+extern "C" int b2s_icp_process_sequence(b2s_icp *c, const void *scans_xy, int is_f64, int scans, int n,
+                                        int max_iter, double tol, double *T_out, int32_t *iters_out)
+{
+    B2S_REQUIRE(c, "b2s_icp_process_sequence: null handle");
+    B2S_REQUIRE(scans >= 0 && n > 0 && max_iter >= 0, "b2s_icp_process_sequence: bad sizes");
+    if (scans <= 1) return B2S_OK;
+    B2S_REQUIRE(scans_xy && T_out, "b2s_icp_process_sequence: null pointer");
+    DeviceGuard g(c->device);
+    Trace tr(c->stream);
+    const int pairs = scans - 1;
+    int rc = icp_sequence_enqueue(c, tr, scans_xy, is_f64, scans, n, max_iter, tol);
+    if (rc) return rc;
     B2S_CUDA(cudaMemcpyAsync(T_out, c->d_T.p, (size_t)pairs * 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (iters_out)
+        B2S_CUDA(cudaMemcpyAsync(iters_out, c->d_iters.p, (size_t)pairs * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                 c->stream));
+    tr.mark("results d2h done", 0, c->stream);
+    B2S_CUDA(cudaStreamSynchronize(c->stream));
+    tr.mark("synchronized", 0, nullptr);
+    return B2S_OK;
+}
+
+// The whole W9 LiDAR-odometry loop for a recorded stream: the K - 1 scan-to-scan transforms (above) and the pose
+// chain xOdom (+)= T of [LOC9]:79-83 / [ICP]:185-190 as a parallel prefix over them, without the transforms leaving
+// the device in between.  traj_out [scans][3] starts at (x0, y0, th0); T_out / iters_out may be NULL.
+extern "C" int b2s_icp_odometry(b2s_icp *c, const void *scans_xy, int is_f64, int scans, int n, int max_iter,
+                                double tol, double x0, double y0, double th0, double *traj_out, double *T_out,
+                                int32_t *iters_out)
+{
+    B2S_REQUIRE(c, "b2s_icp_odometry: null handle");
+    B2S_REQUIRE(scans >= 1 && n > 0 && max_iter >= 0, "b2s_icp_odometry: bad sizes");
+    B2S_REQUIRE(traj_out && (scans_xy || scans == 1), "b2s_icp_odometry: null pointer");
+    DeviceGuard g(c->device);
+    Trace tr(c->stream);
+    const int pairs = scans - 1;
+    int rc;
+    if (pairs > 0 && (rc = icp_sequence_enqueue(c, tr, scans_xy, is_f64, scans, n, max_iter, tol))) return rc;
+    if ((rc = c->d_aux.reserve((size_t)scans * 3 * sizeof(double)))) return rc;
+    if ((rc = b2s_pose_chain((const double *)c->d_T.p, pairs, x0, y0, th0, (double *)c->d_aux.p, c->stream))) return rc;
+    tr.mark("pose chain done", 0, c->stream);
+    B2S_CUDA(cudaMemcpyAsync(traj_out, c->d_aux.p, (size_t)scans * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (T_out && pairs > 0)
+        B2S_CUDA(cudaMemcpyAsync(T_out, c->d_T.p, (size_t)pairs * 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (iters_out && pairs > 0)
         B2S_CUDA(cudaMemcpyAsync(iters_out, c->d_iters.p, (size_t)pairs * sizeof(int32_t), cudaMemcpyDeviceToHost,
                                  c->stream));
     tr.mark("results d2h done", 0, c->stream);

@@ -146,3 +146,28 @@ class ICP(object):
                 self.tolerance if tolerance is None else float(tolerance),
                 _lib.ptr(T), _lib.ptr(iters)))
         return T.reshape(P, 3, 3), iters
+
+    def odometry(self, scans, state=(0.0, 0.0, 0.0), max_iter=None, tolerance=None):
+        """The LiDAR-odometry loop of localization.py:66-83 for a recorded stream: process_sequence(scans) followed
+        by the pose chain `x += cos(th) T02 - sin(th) T12; y += sin(th) T02 + cos(th) T12; th += atan2(T10, T00)`
+        ([ICP]:185-190), the chain as a parallel prefix on the device (scan.compose_odometry_gpu) without the
+        transforms leaving it in between.
+
+        Returns (trajectory (K,3) = x, y, yaw starting at `state`, T (K-1,3,3), iterations (K-1,)).
+        """
+        scans = np.asarray(scans)
+        if scans.ndim != 3 or scans.shape[1] != 2 or scans.shape[0] < 1 or scans.shape[2] < 1:
+            raise ValueError("expected scans (K,2,N) with K, N >= 1, got %s" % (scans.shape,))
+        f64 = scans.dtype != np.float32
+        scans = np.ascontiguousarray(scans, dtype=np.float64 if f64 else np.float32)
+        K, N = scans.shape[0], scans.shape[2]
+        traj = np.empty((K, 3))
+        T = np.empty((K - 1, 9))
+        iters = np.empty(K - 1, dtype=np.int32)
+        _lib.check(self._L.b2s_icp_odometry(
+            self._h, _lib.ptr(scans), 1 if f64 else 0, K, N,
+            self.max_iter if max_iter is None else int(max_iter),
+            self.tolerance if tolerance is None else float(tolerance),
+            float(state[0]), float(state[1]), float(state[2]), _lib.ptr(traj),
+            _lib.ptr(T) if K > 1 else None, _lib.ptr(iters) if K > 1 else None))
+        return traj, T.reshape(K - 1, 3, 3), iters

@@ -224,6 +224,11 @@ int b2s_icp_process(b2s_icp *icp, const void *tar_xy, const void *src_xy, int is
  * NULL).  Same results as b2s_icp_process on the pairs, half the host-to-device bytes. */
 int b2s_icp_process_sequence(b2s_icp *icp, const void *scans_xy, int is_f64, int scans, int n, int max_iter,
                              double tol, double *T_out, int32_t *iters_out);
+/* The whole LiDAR-odometry loop of [LOC9]:66-83 for a recorded stream: b2s_icp_process_sequence followed by the
+ * pose chain of [LOC9]:79-83 / [ICP]:185-190 (b2s_pose_chain) on the device.  traj_out [scans][3] = x, y, yaw,
+ * row 0 = (x0, y0, th0); T_out [scans-1][9] and iters_out [scans-1] may be NULL. */
+int b2s_icp_odometry(b2s_icp *icp, const void *scans_xy, int is_f64, int scans, int n, int max_iter, double tol,
+                     double x0, double y0, double th0, double *traj_out, double *T_out, int32_t *iters_out);
 int b2s_icp_find_nearest(b2s_icp *icp, const double *src_xy, int n, const double *tar_xy, int m,
                          double *dist_out, int64_t *idx_out);
 int b2s_icp_get_transform(b2s_icp *icp, const double *src_xy, const double *tar_xy, int n,

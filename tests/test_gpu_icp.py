@@ -151,6 +151,43 @@ def test_sequence_form_equals_pair_form(env):
     assert np.array_equal(T1[0], T2[0])
 
 
+def test_odometry_is_sequence_plus_pose_chain(env):
+    """ICP.odometry == process_sequence + the sequential pose loop of [ICP]:185-190 on its transforms."""
+    from oracle import pyref
+    xy, _ = env.synth.room_sequence(9001, 400, 360)
+    traj, T, it = env.icp.odometry(xy, state=(0.5, -0.25, 0.1))
+    T2, it2 = env.icp.process_sequence(xy)
+    assert np.array_equal(T, T2) and np.array_equal(it, it2)
+    st = (0.5, -0.25, 0.1)
+    want = [st]
+    for t in T:
+        st = pyref.compose_pose(st, t)
+        want.append(st)
+    np.testing.assert_allclose(traj, np.array(want), rtol=0, atol=1e-10)
+    one, T1, it1 = env.icp.odometry(xy[:1], state=(1.0, 2.0, 3.0))
+    assert one.shape == (1, 3) and np.array_equal(one[0], [1.0, 2.0, 3.0]) and T1.shape == (0, 3, 3) and it1.shape == (0,)
+
+
+def test_cfg2_full_sequence_properties(env):
+    """cfg 2 at full size (10 000 scans, 9 999 pairs): every T is a proper rigid transform, a scan matched onto
+    itself gives the identity in one iteration ([ICP]:75-77: mean error 0 -> break), and 512 evenly spaced pairs
+    agree with the oracle."""
+    xy, _ = env.synth.room_sequence(9001, 10000, 360)
+    T, it = env.icp.process_sequence(xy)
+    assert T.shape == (9999, 3, 3) and it.min() >= 1 and it.max() <= 30
+    R = T[:, :2, :2]
+    assert np.abs(np.einsum("pij,pkj->pik", R, R) - np.identity(2)).max() < 1e-12
+    assert np.abs(np.linalg.det(R) - 1.0).max() < 1e-12
+    assert np.array_equal(T[:, 2, :], np.broadcast_to([0.0, 0.0, 1.0], (9999, 3)))
+    pick = np.linspace(0, 9998, 512).astype(int)
+    want_T, want_it = env.corc.icp_batch(xy[pick], xy[pick + 1], 30, 1e-3)
+    assert np.array_equal(it[pick], want_it)
+    np.testing.assert_allclose(T[pick], want_T, rtol=0, atol=T_ATOL)
+    Ts, its = env.icp.process_batch(xy[:256], xy[:256])
+    assert (its == 1).all()
+    np.testing.assert_allclose(Ts, np.broadcast_to(np.identity(3), Ts.shape), rtol=0, atol=1e-12)
+
+
 def test_cfg4_shape_sample_vs_oracle(env):
     """cfg 4 shape (1080-beam independent pairs) at a size the oracle finishes in seconds, plus a
     size-independent check on a larger batch: every pair of a batch gives the result it gives alone."""
