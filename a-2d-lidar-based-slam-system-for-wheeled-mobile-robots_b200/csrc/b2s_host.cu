@@ -162,8 +162,10 @@ struct b2s_mapping {
     int xw, yw;
     double xyreso, cells_per_m, off_x, off_y;
     double w_hit, w_miss, thresh;
-    cudaStream_t stream, copy_stream;
-    cudaEvent_t chunk_ready[MAX_CHUNKS], inputs_free;
+    // stream: everything ordered (zeroing, last chunk + fold, finalize, read-back); stream2: every other ray-cast
+    // chunk, so the ragged end of one chunk (beams differ in length) overlaps the next; copy_stream: H2D
+    cudaStream_t stream, stream2, copy_stream;
+    cudaEvent_t chunk_ready[MAX_CHUNKS], begun, joined;
     int32_t *hit, *miss;
     int32_t *counters;
     void *workspace;
@@ -550,14 +552,16 @@ extern "C" int b2s_mapping_create(b2s_mapping **out, int xw, int yw, double xyre
     m->pmap_valid = false;
     m->h_packed = nullptr;
     m->h_ids = nullptr;
-    m->stream = m->copy_stream = nullptr;
+    m->stream = m->stream2 = m->copy_stream = nullptr;
     for (int k = 0; k < MAX_CHUNKS; ++k) m->chunk_ready[k] = nullptr;
-    m->inputs_free = nullptr;
+    m->begun = m->joined = nullptr;
     const size_t plane = (size_t)xw * yw * sizeof(int32_t);
     cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
     for (int k = 0; k < MAX_CHUNKS && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&m->chunk_ready[k], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->inputs_free, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->begun, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->joined, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->hit, plane);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->miss, plane);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->counters, 2 * B2S_CNT_WORDS * sizeof(int32_t));
@@ -581,6 +585,7 @@ extern "C" int b2s_mapping_destroy(b2s_mapping *m)
     if (!m) return B2S_OK;
     DeviceGuard g(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->stream2) cudaStreamSynchronize(m->stream2);
     if (m->hit) cudaFree(m->hit);
     if (m->miss) cudaFree(m->miss);
     if (m->counters) cudaFree(m->counters);
@@ -592,8 +597,10 @@ extern "C" int b2s_mapping_destroy(b2s_mapping *m)
     m->h_pose.release();
     for (int k = 0; k < MAX_CHUNKS; ++k)
         if (m->chunk_ready[k]) cudaEventDestroy(m->chunk_ready[k]);
-    if (m->inputs_free) cudaEventDestroy(m->inputs_free);
+    if (m->begun) cudaEventDestroy(m->begun);
+    if (m->joined) cudaEventDestroy(m->joined);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    if (m->stream2) cudaStreamDestroy(m->stream2);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
     return B2S_OK;
@@ -643,17 +650,17 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
     float *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_d = nullptr;  // ox|oy|cx|cy  or  ranges
     double *d_pose = nullptr, *d_cs = nullptr;
     // (the transposed scratch plane of the ray-cast is folded back once, with the last chunk)
-    auto launch = [&](int k, int sign, int32_t *counters) -> int {
+    auto launch = [&](int k, int sign, int32_t *counters, cudaStream_t ks) -> int {
         const size_t s0 = (size_t)lo[k];
         const int ns = lo[k + 1] - lo[k];
         const bool fold = (k == nchunk - 1);
         if (hb.fused)
             return grid_raycast_ranges_signed(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y,
                                               d_a + s0 * beams, d_pose + 4 * s0, d_cs, hb.clamp, ns, beams, counters,
-                                              m->workspace, sign, m->stream, fold);
+                                              m->workspace, sign, ks, fold);
         return grid_raycast_signed(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y,
                                    d_a + s0 * beams, d_b + s0 * beams, d_c + s0, d_d + s0, ns, beams, counters,
-                                   m->workspace, sign, m->stream, fold);
+                                   m->workspace, sign, ks, fold);
     };
     if (total > 0) {
         const size_t pts = total * sizeof(float), a_pts = (pts + 15) & ~(size_t)15;
@@ -679,8 +686,12 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
         B2S_CUDA(cudaMemsetAsync(m->counters, 0, 2 * B2S_CNT_WORDS * sizeof(int32_t), m->stream));
         // the dirty-tile map describes THIS call
         B2S_CUDA(cudaMemsetAsync((char *)m->workspace + GRID_WS_HEADER, 0, grid_dirty_bytes(m->xw, m->yw), m->stream));
-        nchunk = (int)((total + (1u << 21) - 1) >> 21);  // ~2M beams per chunk; deeper pipelines measured no faster
-        if (nchunk > 8) nchunk = 8;
+        B2S_CUDA(cudaEventRecord(m->begun, m->stream));  // the second compute stream starts after the resets above
+        B2S_CUDA(cudaStreamWaitEvent(m->stream2, m->begun, 0));
+        // ~1M beams per chunk: with consecutive chunks overlapping on two compute streams an extra launch costs
+        // little, and the first ray-cast starts after 1/16 of the copy (measured: profiles/scripts/chunk_sweep.py)
+        nchunk = (int)((total + (1u << 20) - 1) >> 20);
+        if (nchunk > MAX_CHUNKS) nchunk = MAX_CHUNKS;
         if (g_h2d_chunks > 0) nchunk = g_h2d_chunks;
         if (nchunk > scans) nchunk = scans;
         if (nchunk < 1) nchunk = 1;
@@ -716,9 +727,17 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
             }
             B2S_CUDA(cudaEventRecord(m->chunk_ready[k], cs));
             tr.mark("h2d chunk done", k, cs);
-            B2S_CUDA(cudaStreamWaitEvent(m->stream, m->chunk_ready[k], 0));
-            if ((rc = launch(k, +1, m->counters))) return rc;
-            tr.mark("ray-cast chunk done", k, m->stream);
+            // odd chunks run on the second compute stream; the last chunk (which also folds the scratch plane)
+            // runs on the main stream after the second one has drained
+            const bool last = (k == nchunk - 1);
+            cudaStream_t ks = (!last && (k & 1)) ? m->stream2 : m->stream;
+            if (last && nchunk > 1) {
+                B2S_CUDA(cudaEventRecord(m->joined, m->stream2));
+                B2S_CUDA(cudaStreamWaitEvent(m->stream, m->joined, 0));
+            }
+            B2S_CUDA(cudaStreamWaitEvent(ks, m->chunk_ready[k], 0));
+            if ((rc = launch(k, +1, m->counters, ks))) return rc;
+            tr.mark("ray-cast chunk done", k, ks);
         }
     }
     int32_t cnt[2 * B2S_CNT_WORDS] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -788,7 +807,7 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
     const int saw_nan = cnt[B2S_CNT_NONFINITE], saw_inf = cnt[B2S_CNT_OVERFLOW];
     if (saw_nan || saw_inf || cnt[B2S_CNT_TOO_LONG] > 0) {
         for (int k = 0; k < nchunk; ++k)
-            if ((rc = launch(k, -1, nullptr))) return rc;
+            if ((rc = launch(k, -1, nullptr, m->stream))) return rc;
         if (pmap_out) {
             rc = b2s_grid_finalize(m->hit, m->miss, m->xw, m->yw, m->w_hit, m->w_miss, m->thresh, nullptr,
                                    (int8_t *)m->d_pmap.p, m->stream);
