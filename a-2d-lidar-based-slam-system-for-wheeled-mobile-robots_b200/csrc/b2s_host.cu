@@ -375,16 +375,23 @@ extern "C" int b2s_icp_process(b2s_icp *c, const void *tar_xy, const void *src_x
 // is scan k + 1).  Every scan crosses PCIe ONCE (the pair form ships each scan twice) and the kernel reads the
 // pairs in place: tar = scans, src = scans + one scan, same pair stride.  Enqueues copies and kernels only; the
 // results stay in c->d_T / c->d_iters for the caller to read back or chain.
+// `beam_cs` != NULL selects the raw-scan form: scans_xy holds one float range per beam and the kernel forms the
+// points itself (b2s_icp_batch_ranges), a quarter of the bytes of the float64 pair form.
 static int icp_sequence_enqueue(b2s_icp *c, Trace &tr, const void *scans_xy, int is_f64, int scans, int n, int max_iter,
-                                double tol)
+                                double tol, const double *beam_cs = nullptr, double clamp = 0.0)
 {
-    const size_t el = is_f64 ? 8 : 4, scan_bytes = (size_t)2 * n * el;
+    const size_t el = is_f64 ? 8 : 4, scan_bytes = (beam_cs ? (size_t)1 : (size_t)2) * n * el;
     const int pairs = scans - 1;
     int rc;
     if ((rc = c->d_tar.reserve((size_t)scans * scan_bytes))) return rc;
     if ((rc = c->d_T.reserve((size_t)pairs * 9 * sizeof(double)))) return rc;
     if ((rc = c->d_iters.reserve((size_t)pairs * sizeof(int32_t)))) return rc;
+    if (beam_cs) {
+        if ((rc = c->d_src.reserve((size_t)n * 2 * sizeof(double)))) return rc;
+        B2S_CUDA(cudaMemcpyAsync(c->d_src.p, beam_cs, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+    }
     int nchunk = (int)(((size_t)scans * scan_bytes + (8u << 20) - 1) / (8u << 20));  // ~8 MB of points per chunk
+    if (beam_cs && nchunk < 4 && pairs >= 4096) nchunk = 4;  // (raw scans are half the bytes: keep the pipeline depth)
     if (nchunk > 8) nchunk = 8;
     if (g_h2d_chunks > 0) nchunk = g_h2d_chunks;
     if (nchunk > pairs) nchunk = pairs;
@@ -405,7 +412,10 @@ static int icp_sequence_enqueue(b2s_icp *c, Trace &tr, const void *scans_xy, int
         const char *tar = (const char *)c->d_tar.p + p0 * scan_bytes;
         double *dT = (double *)c->d_T.p + p0 * 9;
         int32_t *dI = (int32_t *)c->d_iters.p + p0;
-        if (is_f64)
+        if (beam_cs)
+            rc = b2s_icp_batch_ranges((const float *)tar, (const float *)(tar + scan_bytes), (const double *)c->d_src.p, clamp,
+                                      (int)(p1 - p0), n, max_iter, tol, dT, dI, ks);
+        else if (is_f64)
             rc = b2s_icp_batch_f64((const double *)tar, (const double *)(tar + scan_bytes), (int)(p1 - p0), n, n, max_iter, tol,
                                    dT, dI, ks);
         else
@@ -421,6 +431,30 @@ static int icp_sequence_enqueue(b2s_icp *c, Trace &tr, const void *scans_xy, int
     return B2S_OK;
 }
 
+// Read-back shared by the sequence calls: optional pose chain, then trajectory / transforms / iteration counts.
+static int icp_sequence_finish(b2s_icp *c, Trace &tr, int scans, const double *state, double *traj_out, double *T_out,
+                               int32_t *iters_out)
+{
+    const int pairs = scans - 1;
+    int rc;
+    if (traj_out) {
+        if ((rc = c->d_aux.reserve((size_t)scans * 3 * sizeof(double)))) return rc;
+        if ((rc = b2s_pose_chain((const double *)c->d_T.p, pairs, state[0], state[1], state[2], (double *)c->d_aux.p, c->stream)))
+            return rc;
+        tr.mark("pose chain done", 0, c->stream);
+        B2S_CUDA(cudaMemcpyAsync(traj_out, c->d_aux.p, (size_t)scans * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (T_out && pairs > 0)
+        B2S_CUDA(cudaMemcpyAsync(T_out, c->d_T.p, (size_t)pairs * 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (iters_out && pairs > 0)
+        B2S_CUDA(cudaMemcpyAsync(iters_out, c->d_iters.p, (size_t)pairs * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                 c->stream));
+    tr.mark("results d2h done", 0, c->stream);
+    B2S_CUDA(cudaStreamSynchronize(c->stream));
+    tr.mark("synchronized", 0, nullptr);
+    return B2S_OK;
+}
+
 extern "C" int b2s_icp_process_sequence(b2s_icp *c, const void *scans_xy, int is_f64, int scans, int n,
                                         int max_iter, double tol, double *T_out, int32_t *iters_out)
 {
@@ -430,17 +464,9 @@ extern "C" int b2s_icp_process_sequence(b2s_icp *c, const void *scans_xy, int is
     B2S_REQUIRE(scans_xy && T_out, "b2s_icp_process_sequence: null pointer");
     DeviceGuard g(c->device);
     Trace tr(c->stream);
-    const int pairs = scans - 1;
     int rc = icp_sequence_enqueue(c, tr, scans_xy, is_f64, scans, n, max_iter, tol);
     if (rc) return rc;
-    B2S_CUDA(cudaMemcpyAsync(T_out, c->d_T.p, (size_t)pairs * 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (iters_out)
-        B2S_CUDA(cudaMemcpyAsync(iters_out, c->d_iters.p, (size_t)pairs * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                                 c->stream));
-    tr.mark("results d2h done", 0, c->stream);
-    B2S_CUDA(cudaStreamSynchronize(c->stream));
-    tr.mark("synchronized", 0, nullptr);
-    return B2S_OK;
+    return icp_sequence_finish(c, tr, scans, nullptr, nullptr, T_out, iters_out);
 }
 
 // The whole W9 LiDAR-odometry loop for a recorded stream: the K - 1 scan-to-scan transforms (above) and the pose
@@ -455,22 +481,31 @@ extern "C" int b2s_icp_odometry(b2s_icp *c, const void *scans_xy, int is_f64, in
     B2S_REQUIRE(traj_out && (scans_xy || scans == 1), "b2s_icp_odometry: null pointer");
     DeviceGuard g(c->device);
     Trace tr(c->stream);
-    const int pairs = scans - 1;
     int rc;
-    if (pairs > 0 && (rc = icp_sequence_enqueue(c, tr, scans_xy, is_f64, scans, n, max_iter, tol))) return rc;
-    if ((rc = c->d_aux.reserve((size_t)scans * 3 * sizeof(double)))) return rc;
-    if ((rc = b2s_pose_chain((const double *)c->d_T.p, pairs, x0, y0, th0, (double *)c->d_aux.p, c->stream))) return rc;
-    tr.mark("pose chain done", 0, c->stream);
-    B2S_CUDA(cudaMemcpyAsync(traj_out, c->d_aux.p, (size_t)scans * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (T_out && pairs > 0)
-        B2S_CUDA(cudaMemcpyAsync(T_out, c->d_T.p, (size_t)pairs * 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (iters_out && pairs > 0)
-        B2S_CUDA(cudaMemcpyAsync(iters_out, c->d_iters.p, (size_t)pairs * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                                 c->stream));
-    tr.mark("results d2h done", 0, c->stream);
-    B2S_CUDA(cudaStreamSynchronize(c->stream));
-    tr.mark("synchronized", 0, nullptr);
-    return B2S_OK;
+    if (scans > 1 && (rc = icp_sequence_enqueue(c, tr, scans_xy, is_f64, scans, n, max_iter, tol))) return rc;
+    const double state[3] = {x0, y0, th0};
+    return icp_sequence_finish(c, tr, scans, state, traj_out, T_out, iters_out);
+}
+
+// The same loop fed with what the sensor delivers: ranges [scans][n] (sensor_msgs/LaserScan.ranges) and the beam
+// table [n][2] = cos, sin of linspace(angle_min, angle_max, n).  laserToNumpy ([ICP]:216-229; with clamp_inf_to > 0
+// the W12 form [SLAM]:115-123) runs inside the ICP kernel in float64, so 4 bytes per beam cross PCIe instead of the 8
+// (float32 points) or 16 (the reference's float64 points).  state / traj_out may both be NULL (no pose chain).
+extern "C" int b2s_icp_process_scans(b2s_icp *c, const float *ranges, const double *beam_cs, double clamp_inf_to,
+                                     int scans, int n, int max_iter, double tol, const double *state3,
+                                     double *traj_out, double *T_out, int32_t *iters_out)
+{
+    B2S_REQUIRE(c, "b2s_icp_process_scans: null handle");
+    B2S_REQUIRE(scans >= 0 && n > 0 && max_iter >= 0, "b2s_icp_process_scans: bad sizes");
+    B2S_REQUIRE((traj_out == nullptr) == (state3 == nullptr), "b2s_icp_process_scans: state and traj_out go together");
+    if (scans == 0 || (scans == 1 && !traj_out)) return B2S_OK;
+    B2S_REQUIRE(ranges && beam_cs && (T_out || traj_out), "b2s_icp_process_scans: null pointer");
+    B2S_REQUIRE(clamp_inf_to == clamp_inf_to, "b2s_icp_process_scans: NaN clamp");
+    DeviceGuard g(c->device);
+    Trace tr(c->stream);
+    int rc;
+    if (scans > 1 && (rc = icp_sequence_enqueue(c, tr, ranges, 0, scans, n, max_iter, tol, beam_cs, clamp_inf_to))) return rc;
+    return icp_sequence_finish(c, tr, scans, state3, traj_out, T_out, iters_out);
 }
 
 extern "C" int b2s_icp_find_nearest(b2s_icp *c, const double *src_xy, int n, const double *tar_xy,

@@ -171,11 +171,29 @@ __device__ __forceinline__ void cta_rigid_fit(const double (&ax)[R], const doubl
 
 // Register cap: 80 per thread keeps 6 CTAs of 128 threads (360 beams) / 2 CTAs of 384 threads (1080 beams)
 // resident per SM; without it the allocation of some instances drifts above that step from build to build.
-template <typename TIn, int R, int PRUNE, int NN_BLK>
+//
+// RANGES = true is the fused-ingestion form: tar_xy / src_xy hold raw ranges (one float per beam, n == m)
+// and the points are formed here exactly as laserToNumpy does ([ICP]:216-229, [SLAM]:115-123): float64
+// (cos a * r, sin a * r) with the beam table computed by the host's NumPy, +inf -> clamp when clamp > 0.
+template <typename TIn, int R, int PRUNE, int NN_BLK, bool RANGES = false>
 __global__ void __maxnreg__(R <= 3 ? 80 : 104) icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__restrict__ src_xy, int n,
                                  int m, int max_iter, double tol, double *__restrict__ T_out,
-                                 int32_t *__restrict__ iters_out, int use_bulk)
+                                 int32_t *__restrict__ iters_out, int use_bulk,
+                                 const double2 *__restrict__ beam_cs = nullptr, double clamp = 0.0)
 {
+    constexpr int ROWS = RANGES ? 1 : 2;  // values per point in the input arrays
+    auto point = [&](const TIn *scan, int count, int i, double &x, double &y) {
+        if (RANGES) {
+            double r = (double)scan[i];
+            if (clamp > 0.0 && r == INFINITY) r = clamp;  // [SLAM]:119 (only +inf compares equal)
+            const double2 cs = beam_cs[i];
+            x = __dmul_rn(cs.x, r);
+            y = __dmul_rn(cs.y, r);
+        } else {
+            x = (double)scan[i];
+            y = (double)scan[count + i];
+        }
+    };
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [mbarrier 16 B][scratch][tar double2 * m][staging TIn * 2m]
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
@@ -185,8 +203,8 @@ __global__ void __maxnreg__(R <= 3 ? 80 : 104) icp_batch_kernel(const TIn *__res
 
     const int pair = blockIdx.x;
     const int tid = threadIdx.x;
-    const TIn *tar_g = tar_xy + (size_t)pair * 2 * m;
-    const TIn *src_g = src_xy + (size_t)pair * 2 * n;
+    const TIn *tar_g = tar_xy + (size_t)pair * ROWS * m;
+    const TIn *src_g = src_xy + (size_t)pair * ROWS * n;
 
     // ---- stage the target scan: global -> shared via the bulk-copy engine when alignment allows
     if (use_bulk) {
@@ -196,12 +214,12 @@ __global__ void __maxnreg__(R <= 3 ? 80 : 104) icp_batch_kernel(const TIn *__res
         }
         __syncthreads();
         if (tid == 0) {
-            const uint32_t bytes = 2u * (uint32_t)m * (uint32_t)sizeof(TIn);
+            const uint32_t bytes = (uint32_t)ROWS * (uint32_t)m * (uint32_t)sizeof(TIn);
             mbar_expect_tx(bar, bytes);
             bulk_g2s(stage, tar_g, bytes, bar);
         }
     } else {
-        for (int j = tid; j < 2 * m; j += blockDim.x) stage[j] = tar_g[j];
+        for (int j = tid; j < ROWS * m; j += blockDim.x) stage[j] = tar_g[j];
     }
 
     // ---- this thread's source points (registers for the whole solve); overlaps the copy
@@ -213,8 +231,7 @@ __global__ void __maxnreg__(R <= 3 ? 80 : 104) icp_batch_kernel(const TIn *__res
         const int i = tid + r * blockDim.x;
         sx[r] = sy[r] = 0.0;
         if (i < n) {
-            sx[r] = (double)src_g[i];
-            sy[r] = (double)src_g[n + i];
+            point(src_g, n, i, sx[r], sy[r]);
             count = r + 1;
             first[0] += sx[r];
             first[1] += sy[r];
@@ -224,7 +241,8 @@ __global__ void __maxnreg__(R <= 3 ? 80 : 104) icp_batch_kernel(const TIn *__res
     if (use_bulk) mbar_wait(bar, 0);
     else __syncthreads();
     for (int j = tid; j < m; j += blockDim.x) {
-        const double2 t = make_double2((double)stage[j], (double)stage[m + j]);
+        double2 t;
+        point(stage, m, j, t.x, t.y);
         tar[j] = t;
         first[2] += t.x;
         first[3] += t.y;
@@ -441,8 +459,8 @@ __global__ void __maxnreg__(R <= 3 ? 80 : 104) icp_batch_kernel(const TIn *__res
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int i = tid + r * blockDim.x;
-        ox_[r] = (i < n) ? (double)src_g[i] : 0.0;
-        oy_[r] = (i < n) ? (double)src_g[n + i] : 0.0;
+        ox_[r] = oy_[r] = 0.0;
+        if (i < n) point(src_g, n, i, ox_[r], oy_[r]);
     }
     cta_rigid_fit<R>(ox_, oy_, sx, sy, count, n, sax, say, sax, say, unused, scratch, phase, T);  // [ICP]:81
     if (tid == 0) {
@@ -511,6 +529,71 @@ static int launch_icp_r(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_s
 #undef B2S_ICP_GO
 }
 
+// Points per thread: work is proportional to the register slots (threads x points per thread, idle ones included).
+// Three is the measured optimum on B200 (360 and 1080 beams) and is taken unless it wastes more than 10 % over the
+// leanest choice; then 4, then 2.
+static int icp_points_per_thread(int n_src)
+{
+    if (g_icp_src_per_thread) return g_icp_src_per_thread;
+    int slots[5] = {0, 0, 0, 0, 0}, least = 1 << 30;
+    for (int c = 2; c <= 4; ++c) {
+        int threads = ((((n_src + c - 1) / c) + 31) / 32) * 32;
+        if (threads < 64) threads = 64;
+        slots[c] = threads <= 1024 ? threads * c : (1 << 30);
+        if (slots[c] < least) least = slots[c];
+    }
+    const int order[3] = {3, 4, 2};
+    for (int k = 0; k < 3; ++k)
+        if (slots[order[k]] < (1 << 30) && (long long)slots[order[k]] * 10 <= (long long)least * 11) return order[k];
+    return 4;
+}
+
+// Fused-ingestion form: raw ranges + beam table (always the default search, PRUNE = 2).
+template <int R, int NN_BLK>
+static int launch_icp_ranges_rb(const float *tar_r, const float *src_r, const double *beam_cs, double clamp, int pairs,
+                                int n, int max_iter, double tol, double *T_out, int32_t *iters_out, void *stream)
+{
+    int threads = ((((n + R - 1) / R) + 31) / 32) * 32;
+    if (threads < 64) threads = 64;
+    B2S_REQUIRE(threads <= 1024, "b2s_icp_batch_ranges: too many beams per scan");
+    const size_t smem = 16 + SCRATCH_DOUBLES * sizeof(double) + (size_t)n * sizeof(double2) + (size_t)n * 2 * sizeof(float);
+    B2S_REQUIRE(smem <= 227 * 1024, "b2s_icp_batch_ranges: too many beams for shared memory");
+    if (smem > 48 * 1024)
+        B2S_CUDA(cudaFuncSetAttribute(icp_batch_kernel<float, R, 2, NN_BLK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    const int use_bulk = ((uintptr_t)tar_r % 16 == 0) && (((size_t)n * sizeof(float)) % 16 == 0);
+    icp_batch_kernel<float, R, 2, NN_BLK, true><<<pairs, threads, smem, (cudaStream_t)stream>>>(
+        tar_r, src_r, n, n, max_iter, tol, T_out, iters_out, use_bulk, reinterpret_cast<const double2 *>(beam_cs), clamp);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+
+template <int R>
+static int launch_icp_ranges_r(const float *tar_r, const float *src_r, const double *beam_cs, double clamp, int pairs,
+                               int n, int max_iter, double tol, double *T_out, int32_t *iters_out, void *stream)
+{
+    const int blk = (g_icp_block == 8 || g_icp_block == 16 || g_icp_block == 32) ? g_icp_block : (n <= 600 ? 8 : 16);
+    if (blk == 8) return launch_icp_ranges_rb<R, 8>(tar_r, src_r, beam_cs, clamp, pairs, n, max_iter, tol, T_out, iters_out, stream);
+    if (blk == 16) return launch_icp_ranges_rb<R, 16>(tar_r, src_r, beam_cs, clamp, pairs, n, max_iter, tol, T_out, iters_out, stream);
+    return launch_icp_ranges_rb<R, 32>(tar_r, src_r, beam_cs, clamp, pairs, n, max_iter, tol, T_out, iters_out, stream);
+}
+
+static int launch_icp_ranges(const float *tar_r, const float *src_r, const double *beam_cs, double clamp, int pairs, int n,
+                             int max_iter, double tol, double *T_out, int32_t *iters_out, void *stream)
+{
+    B2S_REQUIRE(pairs >= 0 && n > 0 && max_iter >= 0, "b2s_icp_batch_ranges: bad sizes");
+    if (pairs == 0) return B2S_OK;
+    B2S_REQUIRE(tar_r && src_r && beam_cs && T_out, "b2s_icp_batch_ranges: null pointer");
+    B2S_REQUIRE((uintptr_t)beam_cs % 16 == 0, "b2s_icp_batch_ranges: the beam table must be 16-byte aligned");
+    B2S_REQUIRE(tol == tol && clamp == clamp, "b2s_icp_batch_ranges: NaN tolerance / clamp");
+    B2S_REQUIRE(n <= 4096, "b2s_icp_batch_ranges: more than 4096 beams per scan is not supported");
+    switch (icp_points_per_thread(n)) {
+    case 2: return launch_icp_ranges_r<2>(tar_r, src_r, beam_cs, clamp, pairs, n, max_iter, tol, T_out, iters_out, stream);
+    case 3: return launch_icp_ranges_r<3>(tar_r, src_r, beam_cs, clamp, pairs, n, max_iter, tol, T_out, iters_out, stream);
+    default: return launch_icp_ranges_r<4>(tar_r, src_r, beam_cs, clamp, pairs, n, max_iter, tol, T_out, iters_out, stream);
+    }
+}
+
 template <typename TIn>
 static int launch_icp(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_src, int n_tar,
                       int max_iter, double tol, double *T_out, int32_t *iters_out, void *stream)
@@ -520,23 +603,7 @@ static int launch_icp(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_src
     B2S_REQUIRE(tar_xy && src_xy && T_out, "b2s_icp_batch: null pointer");
     B2S_REQUIRE(tol == tol, "b2s_icp_batch: NaN tolerance");
     B2S_REQUIRE(n_src <= 4096, "b2s_icp_batch: n_src above 4096 points per scan is not supported");
-    int r = g_icp_src_per_thread;
-    if (r == 0) {
-        // Work is proportional to the register slots (threads x points per thread, idle ones included).  Three
-        // points per thread is the measured optimum on B200 (360 and 1080 beams) and is taken unless it wastes more
-        // than 10 % over the leanest choice; then 4, then 2.
-        int slots[5] = {0, 0, 0, 0, 0}, least = 1 << 30;
-        for (int c = 2; c <= 4; ++c) {
-            int threads = ((((n_src + c - 1) / c) + 31) / 32) * 32;
-            if (threads < 64) threads = 64;
-            slots[c] = threads <= 1024 ? threads * c : (1 << 30);
-            if (slots[c] < least) least = slots[c];
-        }
-        const int order[3] = {3, 4, 2};
-        for (int k = 0; k < 3 && r == 0; ++k)
-            if (slots[order[k]] < (1 << 30) && (long long)slots[order[k]] * 10 <= (long long)least * 11) r = order[k];
-        if (r == 0) r = 4;
-    }
+    const int r = icp_points_per_thread(n_src);
     switch (r) {
     case 2: return launch_icp_r<TIn, 2>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream);
     case 3: return launch_icp_r<TIn, 3>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream);

@@ -171,3 +171,42 @@ class ICP(object):
             float(state[0]), float(state[1]), float(state[2]), _lib.ptr(traj),
             _lib.ptr(T) if K > 1 else None, _lib.ptr(iters) if K > 1 else None))
         return traj, T.reshape(K - 1, 3, 3), iters
+
+    def process_scans(self, ranges, angle_min, angle_max, clamp_inf_to=None, state=None, max_iter=None,
+                      tolerance=None):
+        """process_sequence / odometry fed with what the sensor delivers: ranges (K,N) float32 (LaserScan.ranges of
+        K consecutive scans).  laserToNumpy -- [ICP]:216-229, or with clamp_inf_to (MAX_LASER_RANGE = 30) the W12
+        form slam_ekf.py:115-123 -- runs inside the ICP kernel in float64, so 4 bytes per beam cross PCIe instead
+        of the 16 of the reference's float64 points.  Same transforms as
+        process_sequence(stack of laser_to_points(ranges[k])[:2]), bit for bit.
+
+        Returns (T (K-1,3,3), iterations (K-1,)), or with state=(x, y, yaw) (trajectory (K,3), T, iterations).
+        """
+        from b2slam import scan
+        ranges = np.ascontiguousarray(ranges, dtype=np.float32)
+        if ranges.ndim != 2 or ranges.shape[1] < 1:
+            raise ValueError("expected ranges (K,N) with N >= 1, got %s" % (ranges.shape,))
+        K, N = ranges.shape
+        key = (float(angle_min), float(angle_max), N)
+        if getattr(self, "_beam_key", None) != key:
+            self._beam_cs = scan.beam_table(angle_min, angle_max, N)
+            self._beam_key = key
+        P = max(K - 1, 0)
+        T = np.empty((P, 9))
+        iters = np.empty(P, dtype=np.int32)
+        traj = None
+        st = None
+        if state is not None:
+            if K < 1:
+                raise ValueError("a trajectory needs at least one scan")
+            traj = np.empty((K, 3))
+            st = np.array([float(state[0]), float(state[1]), float(state[2])])
+        if K > 0:
+            _lib.check(self._L.b2s_icp_process_scans(
+                self._h, _lib.ptr(ranges), _lib.ptr(self._beam_cs), float(clamp_inf_to or 0.0), K, N,
+                self.max_iter if max_iter is None else int(max_iter),
+                self.tolerance if tolerance is None else float(tolerance),
+                _lib.ptr(st) if st is not None else None, _lib.ptr(traj) if traj is not None else None,
+                _lib.ptr(T), _lib.ptr(iters)))
+        T = T.reshape(P, 3, 3)
+        return (T, iters) if state is None else (traj, T, iters)

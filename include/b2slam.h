@@ -70,6 +70,12 @@ int b2s_measure_fp64_peak(double *tflops_out);
  *   max_iter / tol are rospy.get_param('/icp/max_iter', 30) / ('/icp/tolerance', 0.001). */
 int b2s_icp_batch_f32(const float *tar_xy, const float *src_xy, int pairs, int n_src, int n_tar,
                       int max_iter, double tol, double *T_out, int32_t *iters_out, void *stream);
+/* The same from raw scans (fused ingestion): tar_ranges / src_ranges [pairs][n] float ranges, beam_cs [n][2] =
+ * cos, sin of the beam angles (device, 16-byte aligned).  The kernel forms the points as laserToNumpy does
+ * ([ICP]:216-229; +inf -> clamp_inf_to when > 0, [SLAM]:119) in float64 before the solve. */
+int b2s_icp_batch_ranges(const float *tar_ranges, const float *src_ranges, const double *beam_cs,
+                         double clamp_inf_to, int pairs, int n, int max_iter, double tol, double *T_out,
+                         int32_t *iters_out, void *stream);
 int b2s_icp_batch_f64(const double *tar_xy, const double *src_xy, int pairs, int n_src, int n_tar,
                       int max_iter, double tol, double *T_out, int32_t *iters_out, void *stream);
 
@@ -229,6 +235,12 @@ int b2s_icp_process_sequence(b2s_icp *icp, const void *scans_xy, int is_f64, int
  * row 0 = (x0, y0, th0); T_out [scans-1][9] and iters_out [scans-1] may be NULL. */
 int b2s_icp_odometry(b2s_icp *icp, const void *scans_xy, int is_f64, int scans, int n, int max_iter, double tol,
                      double x0, double y0, double th0, double *traj_out, double *T_out, int32_t *iters_out);
+/* The same loop fed with what the sensor delivers: ranges [scans][n] (LaserScan.ranges) + the beam table [n][2]
+ * (cos, sin of linspace(angle_min, angle_max, n)); laserToNumpy runs inside the kernel (b2s_icp_batch_ranges).
+ * state3 = (x0, y0, th0) and traj_out [scans][3] are both NULL (transforms only) or both set (with the pose chain). */
+int b2s_icp_process_scans(b2s_icp *icp, const float *ranges, const double *beam_cs, double clamp_inf_to, int scans,
+                          int n, int max_iter, double tol, const double *state3, double *traj_out, double *T_out,
+                          int32_t *iters_out);
 int b2s_icp_find_nearest(b2s_icp *icp, const double *src_xy, int n, const double *tar_xy, int m,
                          double *dist_out, int64_t *idx_out);
 int b2s_icp_get_transform(b2s_icp *icp, const double *src_xy, const double *tar_xy, int n,

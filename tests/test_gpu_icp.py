@@ -168,6 +168,34 @@ def test_odometry_is_sequence_plus_pose_chain(env):
     assert one.shape == (1, 3) and np.array_equal(one[0], [1.0, 2.0, 3.0]) and T1.shape == (0, 3, 3) and it1.shape == (0,)
 
 
+def test_process_scans_equals_laser_to_numpy_plus_sequence(env):
+    """Fused ingestion for the ICP: ranges in, laserToNumpy inside the kernel.  Bit-identical to the
+    host conversion ([ICP]:216-229 / the W12 clamp [SLAM]:115-123) followed by process_sequence, and equal to the
+    oracle on the converted clouds."""
+    import math
+    from b2slam import scan
+    rng = np.random.Generator(np.random.PCG64(31))
+    for beams, scans in ((360, 120), (1080, 24), (100, 9), (361, 6)):   # 361: rows not 16-byte multiples
+        xy, _ = env.synth.room_sequence(9100 + beams, scans, beams)
+        ranges = np.hypot(xy[:, 0, :], xy[:, 1, :]).astype(np.float32)
+        for clamp in (None, 30.0):
+            r = ranges.copy()
+            if clamp is not None:
+                r[rng.integers(0, scans, 5), rng.integers(0, beams, 5)] = np.inf
+            clouds = np.stack([scan.laser_to_points(r[k], -math.pi, math.pi, clamp_inf_to=clamp)[:2] for k in range(scans)])
+            want_T, want_it = env.icp.process_sequence(clouds)
+            T, it = env.icp.process_scans(r, -math.pi, math.pi, clamp_inf_to=clamp)
+            assert np.array_equal(it, want_it) and np.array_equal(T, want_T), (beams, clamp)
+            traj, T2, it2 = env.icp.process_scans(r, -math.pi, math.pi, clamp_inf_to=clamp, state=(1.0, -2.0, 0.3))
+            traj3, T3, it3 = env.icp.odometry(clouds, state=(1.0, -2.0, 0.3))
+            assert np.array_equal(T2, T) and np.array_equal(traj, traj3)
+        oT, oit = env.corc.icp_batch(clouds[:-1], clouds[1:], 30, 1e-3)
+        assert np.array_equal(it, oit)
+        np.testing.assert_allclose(T, oT, rtol=0, atol=T_ATOL)
+    Te, ite = env.icp.process_scans(np.zeros((1, 16), dtype=np.float32), -1.0, 1.0)
+    assert Te.shape == (0, 3, 3) and ite.shape == (0,)
+
+
 def test_cfg2_full_sequence_properties(env):
     """cfg 2 at full size (10 000 scans, 9 999 pairs): every T is a proper rigid transform, a scan matched onto
     itself gives the identity in one iteration ([ICP]:75-77: mean error 0 -> break), and 512 evenly spaced pairs
