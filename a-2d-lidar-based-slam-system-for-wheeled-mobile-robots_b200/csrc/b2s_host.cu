@@ -721,8 +721,6 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
         B2S_CUDA(cudaMemsetAsync(m->counters, 0, 2 * B2S_CNT_WORDS * sizeof(int32_t), m->stream));
         // the dirty-tile map describes THIS call
         B2S_CUDA(cudaMemsetAsync((char *)m->workspace + GRID_WS_HEADER, 0, grid_dirty_bytes(m->xw, m->yw), m->stream));
-        B2S_CUDA(cudaEventRecord(m->begun, m->stream));  // the second compute stream starts after the resets above
-        B2S_CUDA(cudaStreamWaitEvent(m->stream2, m->begun, 0));
         // ~1M beams per chunk: with consecutive chunks overlapping on two compute streams an extra launch costs
         // little, and the first ray-cast starts after 1/16 of the copy (measured: profiles/scripts/chunk_sweep.py)
         nchunk = (int)((total + (1u << 20) - 1) >> 20);
@@ -731,6 +729,10 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
         if (nchunk > scans) nchunk = scans;
         if (nchunk < 1) nchunk = 1;
         for (int k = 0; k <= nchunk; ++k) lo[k] = (int)((long long)scans * k / nchunk);
+        if (nchunk > 1) {  // the second compute stream starts after the resets above (single-chunk calls never use it)
+            B2S_CUDA(cudaEventRecord(m->begun, m->stream));
+            B2S_CUDA(cudaStreamWaitEvent(m->stream2, m->begun, 0));
+        }
         const double *pose4 = hb.pose4;
         double *table = nullptr;
         if (hb.fused && hb.poses3) {
