@@ -27,6 +27,23 @@ __global__ void __launch_bounds__(256) k_redg(int *plane, unsigned mask, int ite
     }
 }
 
+// Runs of RUN adjacent lanes on the same word (what the ray-cast sees: adjacent beams share cells).  ALL = false:
+// only the run heads issue the RED, with the run length (the kernel's scheme, a divergent branch around the RED).
+// ALL = true: every lane issues it unconditionally, non-heads add 0 -- no branch, RUN times the lane-ops.
+template <int RUN, bool ALL>
+__global__ void __launch_bounds__(256) k_redg_runs(int *plane, unsigned mask, int iters)
+{
+    uint32_t s = blockIdx.x * 256 + threadIdx.x + 1;
+    const int lane = threadIdx.x & 31;
+    const bool head = (lane % RUN) == 0;
+    for (int i = 0; i < iters; ++i) {
+        uint32_t base = __shfl_sync(0xffffffffu, lcg(s), 0) & mask;
+        int *p = plane + base + lane / RUN;
+        if (ALL) asm volatile("red.global.add.s32 [%0], %1;" ::"l"(p), "r"(head ? RUN : 0) : "memory");
+        else if (head) asm volatile("red.global.add.s32 [%0], %1;" ::"l"(p), "r"(RUN) : "memory");
+    }
+}
+
 template <int ACTIVE>
 __global__ void __launch_bounds__(256) k_redg_scatter(int *plane, unsigned mask, int iters)
 {
@@ -155,6 +172,12 @@ int main()
     ms = time_ms([&] { k_redg<32, true><<<blocks, 256>>>(plane, mask, iters); }); REPORT("redg64 contiguous lanes", 32, ms);
     ms = time_ms([&] { k_redg<8, true><<<blocks, 256>>>(plane, mask, iters); }); REPORT("redg64 contiguous lanes", 8, ms);
     ms = time_ms([&] { k_redg<4, true><<<blocks, 256>>>(plane, mask, iters); }); REPORT("redg64 contiguous lanes", 4, ms);
+    ms = time_ms([&] { k_redg_runs<4, false><<<blocks, 256>>>(plane, mask, iters); }); REPORT("redg32 runs of 4, heads only", 8, ms);
+    ms = time_ms([&] { k_redg_runs<4, true><<<blocks, 256>>>(plane, mask, iters); }); REPORT("redg32 runs of 4, all lanes", 32, ms);
+    ms = time_ms([&] { k_redg_runs<8, false><<<blocks, 256>>>(plane, mask, iters); }); REPORT("redg32 runs of 8, heads only", 4, ms);
+    ms = time_ms([&] { k_redg_runs<8, true><<<blocks, 256>>>(plane, mask, iters); }); REPORT("redg32 runs of 8, all lanes", 32, ms);
+    ms = time_ms([&] { k_redg_runs<2, false><<<blocks, 256>>>(plane, mask, iters); }); REPORT("redg32 runs of 2, heads only", 16, ms);
+    ms = time_ms([&] { k_redg_runs<2, true><<<blocks, 256>>>(plane, mask, iters); }); REPORT("redg32 runs of 2, all lanes", 32, ms);
     ms = time_ms([&] { k_redg_scatter<32><<<blocks, 256>>>(plane, mask, iters); }); REPORT("redg32 scattered lanes", 32, ms);
     ms = time_ms([&] { k_redg_scatter<8><<<blocks, 256>>>(plane, mask, iters); }); REPORT("redg32 scattered lanes", 8, ms);
     CK(cudaFuncSetAttribute(k_atoms<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
