@@ -4,18 +4,22 @@
 //
 // Per pair the kernel reads 2*(N+M) coordinates once (target rows staged into shared memory
 // with a 1-D bulk async copy + mbarrier), then runs up to max_iter iterations of
-//   brute-force nearest neighbour  (N*M distance evaluations, strict '<', ascending j so the
-//                                   lowest index wins ties exactly like the reference loop)
-//   centroid + 2x2 cross-covariance (two-pass, as the reference centres before multiplying)
-//   closed-form proper rotation     (theta = atan2(W10-W01, W00+W11) == U.Vt with the W9 fix)
+//   nearest neighbour               (exact: the index of the N*M brute force with strict '<' in ascending j, i.e.
+//                                    the lowest index wins ties like the reference loop, found with a warp-level
+//                                    and a per-lane block-pruning test in front; PRUNE = 0 is the plain brute force)
+//   centroid + 2x2 cross-covariance (ONE reduction about fixed shifts; the reference centres, then multiplies)
+//   closed-form proper rotation     ((c, s) = (W00+W11, W10-W01) / norm == U.Vt with the W9 reflection fix)
 //   src <- T.src, mean-error stop rule
 // and the final re-fit of the original source onto the moved source ([ICP]:81).
 //
 // Numerics: everything is float64, like the reference.  B200 (sm_100a) issues FP64 at half the
 // FP32 rate, and an FP32 search would need a second-best tracker plus a float64 re-check of
 // near ties to keep correspondences identical, which costs about the same issue slots; see
-// DESIGN.md "ICP numerics".  Source points live in registers (SRC_PER_THREAD per thread) for
-// the whole solve; targets live in shared memory as double2 and are read as warp broadcasts.
+// DESIGN.md "ICP numerics".  Source points live in registers (R per thread) for the whole solve;
+// targets live in shared memory as double2 and are read as warp broadcasts.
+//
+// This header holds the kernel and its launch logic; b2s_icp_f32.cu / b2s_icp_f64.cu instantiate it per input
+// type (two translation units so the instances compile in parallel).
 #pragma once
 #include "b2s_common.cuh"
 
@@ -167,7 +171,8 @@ __device__ __forceinline__ void cta_rigid_fit(const double (&ax)[R], const doubl
     extra = v[8];
 }
 
-// Targets per pruning block: 16 is fastest at 360 beams, 32 at 1080 (measured); chosen per launch.
+// Targets per pruning block (NN_BLK): 8 is fastest at 360 beams, 16 at 1080 with the warp-level test in front
+// (16 / 32 with the per-lane test alone); chosen per launch, see launch_icp_r.
 
 // Register cap: 80 per thread keeps 6 CTAs of 128 threads (360 beams) / 2 CTAs of 384 threads (1080 beams)
 // resident per SM; without it the allocation of some instances drifts above that step from build to build.
