@@ -79,6 +79,30 @@ def icp_pairs_golden():
     np.savez_compressed(os.path.join(OUT, "icp_pairs.npz"), **blob)
 
 
+def _reference_pair(args):
+    """One whole ICP.process of the unmodified reference (worker of icp_pairs_1080_golden)."""
+    tar, src, max_iter, tol = args
+    icp, calls = _counting_icp({"/icp/tolerance": tol, "/icp/max_iter": max_iter})
+    T = icp.process(synth.homogeneous(tar.astype(np.float64)), synth.homogeneous(src.astype(np.float64)))
+    return np.asarray(T, dtype=np.float64), calls["n"]
+
+
+def icp_pairs_1080_golden(pairs=6):
+    """(i, cfg 4 shape) the first pairs of the cfg-4 stream (seed 4001, 1080 beams) through the reference itself:
+    ~1.2 M np.linalg.norm calls per iteration, about half a minute per pair, so the pairs run in parallel."""
+    import multiprocessing as mp
+    tar, src, truth = synth.icp_pairs(4001, pairs, 1080)
+    with mp.Pool(min(pairs, os.cpu_count() or 1)) as pool:
+        res = pool.map(_reference_pair, [(tar[p], src[p], 30, 0.001) for p in range(pairs)])
+    blob = {"count": pairs}
+    for i, (T, iters) in enumerate(res):
+        for k, v in dict(tar=tar[i], src=src[i], T=T, iters=iters, max_iter=30, tol=0.001, seed=4001,
+                         truth=truth[i]).items():
+            blob["%d_%s" % (i, k)] = v
+        print("icp seed=4001 beams=1080 pair=%d iters=%d" % (i, iters))
+    np.savez_compressed(os.path.join(OUT, "icp_pairs_1080.npz"), **blob)
+
+
 def nearest_and_fit_golden():
     """(ii) findNearest incl. exact ties, (iii) getTransform incl. reflection-branch inputs."""
     rng = np.random.Generator(np.random.PCG64(8101))
@@ -251,6 +275,7 @@ def main():
     nearest_and_fit_golden()
     mapping_golden()
     icp_pairs_golden()
+    icp_pairs_1080_golden()
 
 
 if __name__ == "__main__":

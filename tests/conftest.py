@@ -38,9 +38,12 @@ def golden():
 
 
 def icp_cases():
-    z = load_golden("icp_pairs.npz")
+    """Whole ICP.process runs of the reference itself: 120 / 360 beams (icp_pairs.npz) and the first pairs of the
+    cfg-4 stream at 1080 beams (icp_pairs_1080.npz); see oracle/make_golden.py."""
     out = []
-    for i in range(int(z["count"])):
-        out.append({k: z["%d_%s" % (i, k)] for k in
-                    ("tar", "src", "T", "iters", "max_iter", "tol", "seed", "truth")})
+    for name in ("icp_pairs.npz", "icp_pairs_1080.npz"):
+        z = load_golden(name)
+        for i in range(int(z["count"])):
+            out.append({k: z["%d_%s" % (i, k)] for k in
+                        ("tar", "src", "T", "iters", "max_iter", "tol", "seed", "truth")})
     return out
