@@ -13,6 +13,16 @@ T, it = icp.process_batch(tar, src)
 wT, wit = corc.icp_batch(tar, src, 30, 1e-3)
 assert np.array_equal(it, wit) and np.abs(T - wT).max() < 1e-9
 T2, it2 = icp.process_batch(tar[:, :, :97].copy(), src[:, :, :77].copy())     # unaligned: no bulk copy
+xy, _ = synth.room_sequence(9001, 12, 120)
+Ts, its = icp.process_sequence(xy)                                             # consecutive pairs in place
+traj, To, ito = icp.odometry(xy, state=(0.1, 0.2, 0.3))                        # + pose chain on the device
+assert np.array_equal(Ts, To)
+rng = np.hypot(xy[:, 0], xy[:, 1]).astype(np.float32)
+Tr, itr = icp.process_scans(rng, -math.pi, math.pi)                            # laserToNumpy inside the kernel
+for prune in (0, 1, 3, 2):                                                     # every search mode
+    _lib.check(_lib.lib().b2s_tune(b"icp_prune", prune))
+    Tp, itp = icp.process_sequence(xy)
+    assert np.array_equal(Tp, Ts) and np.array_equal(itp, its)
 d, i = icp.findNearest(src[0].T.astype(np.float64), tar[0].T.astype(np.float64))
 icp.getTransform(src[0].T.astype(np.float64), tar[0].T.astype(np.float64))
 for v in (1, 2, 3, 4):
