@@ -499,6 +499,11 @@ static int launch_icp_rp(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_
     // bulk copy needs 16-byte aligned source and size: every pair's target block must qualify
     const size_t pair_bytes = (size_t)2 * n_tar * sizeof(TIn);
     const int use_bulk = ((uintptr_t)tar_xy % 16 == 0) && (pair_bytes % 16 == 0);
+    if (threads > 512) {  // (large scans only: the query is not free)
+        cudaFuncAttributes fa;
+        B2S_CUDA(cudaFuncGetAttributes(&fa, icp_batch_kernel<TIn, R, PRUNE, NN_BLK>));
+        B2S_REQUIRE(threads <= fa.maxThreadsPerBlock, "b2s_icp_batch: scan too large for one CTA's registers");
+    }
     icp_batch_kernel<TIn, R, PRUNE, NN_BLK><<<pairs, threads, smem, (cudaStream_t)stream>>>(
         tar_xy, src_xy, n_src, n_tar, max_iter, tol, T_out, iters_out, use_bulk);
     B2S_CUDA(cudaGetLastError());
@@ -537,20 +542,25 @@ static int launch_icp_r(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_s
 // Points per thread: work is proportional to the register slots (threads x points per thread, idle ones included).
 // Three is the measured optimum on B200 (360 and 1080 beams) and is taken unless it wastes more than 10 % over the
 // leanest choice; then 4, then 2.
+constexpr int ICP_MAX_POINTS = 2304;  // per scan; see icp_points_per_thread
+
 static int icp_points_per_thread(int n_src)
 {
     if (g_icp_src_per_thread) return g_icp_src_per_thread;
+    // a CTA must fit the register file: 65536 / 80 registers (R <= 3) is 819 threads, 65536 / 104 (R = 4) is 630
+    // (the kernel's __maxnreg__); with a margin for the allocation granularity that is 768 / 576 threads, which is
+    // what bounds the scan size to ICP_MAX_POINTS = 3 x 768 (the launch re-checks against the kernel's attributes)
     int slots[5] = {0, 0, 0, 0, 0}, least = 1 << 30;
     for (int c = 2; c <= 4; ++c) {
         int threads = ((((n_src + c - 1) / c) + 31) / 32) * 32;
         if (threads < 64) threads = 64;
-        slots[c] = threads <= 1024 ? threads * c : (1 << 30);
+        slots[c] = threads <= (c <= 3 ? 768 : 576) ? threads * c : (1 << 30);
         if (slots[c] < least) least = slots[c];
     }
     const int order[3] = {3, 4, 2};
     for (int k = 0; k < 3; ++k)
         if (slots[order[k]] < (1 << 30) && (long long)slots[order[k]] * 10 <= (long long)least * 11) return order[k];
-    return 4;
+    return 3;
 }
 
 // Fused-ingestion form: raw ranges + beam table (always the default search, PRUNE = 2).
@@ -566,6 +576,11 @@ static int launch_icp_ranges_rb(const float *tar_r, const float *src_r, const do
     if (smem > 48 * 1024)
         B2S_CUDA(cudaFuncSetAttribute(icp_batch_kernel<float, R, 2, NN_BLK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
+    if (threads > 512) {  // (large scans only: the query is not free)
+        cudaFuncAttributes fa;
+        B2S_CUDA(cudaFuncGetAttributes(&fa, icp_batch_kernel<float, R, 2, NN_BLK, true>));
+        B2S_REQUIRE(threads <= fa.maxThreadsPerBlock, "b2s_icp_batch_ranges: scan too large for one CTA's registers");
+    }
     const int use_bulk = ((uintptr_t)tar_r % 16 == 0) && (((size_t)n * sizeof(float)) % 16 == 0);
     icp_batch_kernel<float, R, 2, NN_BLK, true><<<pairs, threads, smem, (cudaStream_t)stream>>>(
         tar_r, src_r, n, n, max_iter, tol, T_out, iters_out, use_bulk, reinterpret_cast<const double2 *>(beam_cs), clamp);
@@ -591,7 +606,7 @@ static int launch_icp_ranges(const float *tar_r, const float *src_r, const doubl
     B2S_REQUIRE(tar_r && src_r && beam_cs && T_out, "b2s_icp_batch_ranges: null pointer");
     B2S_REQUIRE((uintptr_t)beam_cs % 16 == 0, "b2s_icp_batch_ranges: the beam table must be 16-byte aligned");
     B2S_REQUIRE(tol == tol && clamp == clamp, "b2s_icp_batch_ranges: NaN tolerance / clamp");
-    B2S_REQUIRE(n <= 4096, "b2s_icp_batch_ranges: more than 4096 beams per scan is not supported");
+    B2S_REQUIRE(n <= ICP_MAX_POINTS, "b2s_icp_batch_ranges: more than 2304 beams per scan is not supported");
     switch (icp_points_per_thread(n)) {
     case 2: return launch_icp_ranges_r<2>(tar_r, src_r, beam_cs, clamp, pairs, n, max_iter, tol, T_out, iters_out, stream);
     case 3: return launch_icp_ranges_r<3>(tar_r, src_r, beam_cs, clamp, pairs, n, max_iter, tol, T_out, iters_out, stream);
@@ -607,7 +622,7 @@ static int launch_icp(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_src
     if (pairs == 0) return B2S_OK;
     B2S_REQUIRE(tar_xy && src_xy && T_out, "b2s_icp_batch: null pointer");
     B2S_REQUIRE(tol == tol, "b2s_icp_batch: NaN tolerance");
-    B2S_REQUIRE(n_src <= 4096, "b2s_icp_batch: n_src above 4096 points per scan is not supported");
+    B2S_REQUIRE(n_src <= ICP_MAX_POINTS, "b2s_icp_batch: more than 2304 source points per scan is not supported");
     const int r = icp_points_per_thread(n_src);
     switch (r) {
     case 2: return launch_icp_r<TIn, 2>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream);

@@ -67,7 +67,9 @@ int b2s_measure_fp64_peak(double *tflops_out);
  *   tar_xy [pairs][2][n_tar], src_xy [pairs][2][n_src]: x row then y row, i.e. rows 0-1 of the
  *   3xN homogeneous arrays the reference passes.  T_out [pairs][9] row-major 3x3 float64 mapping
  *   the source scan into the target frame; iters_out [pairs] iterations run (may be NULL).
- *   max_iter / tol are rospy.get_param('/icp/max_iter', 30) / ('/icp/tolerance', 0.001). */
+ *   max_iter / tol are rospy.get_param('/icp/max_iter', 30) / ('/icp/tolerance', 0.001).
+ *   Limits: n_src <= 2304 (one CTA holds a pair's source points in registers), n_tar bounded by the 227 KB of
+ *   shared memory (about 7000 points); beyond them the call returns B2S_ERR_INVALID_ARG. */
 int b2s_icp_batch_f32(const float *tar_xy, const float *src_xy, int pairs, int n_src, int n_tar,
                       int max_iter, double tol, double *T_out, int32_t *iters_out, void *stream);
 /* The same from raw scans (fused ingestion): tar_ranges / src_ranges [pairs][n] float ranges, beam_cs [n][2] =

@@ -106,6 +106,20 @@ def test_unequal_sizes_odd_counts_and_zero_iterations(env):
     assert Te.shape == (0, 3, 3) and ite.shape == (0,)
 
 
+def test_largest_supported_scan_and_the_limit(env):
+    """2304 points per scan is the documented ceiling (the CTA's register budget): it must run and agree with the
+    oracle; one point more is refused with a status code, not a launch failure."""
+    tar, src, _ = env.synth.icp_pairs(2400, 2, 2304)
+    T, it = env.icp.process_batch(tar, src)
+    want_T, want_it = env.corc.icp_batch(tar, src, 30, 1e-3)
+    assert np.array_equal(it, want_it)
+    np.testing.assert_allclose(T, want_T, rtol=0, atol=T_ATOL)
+    big = np.zeros((1, 2, 2305), dtype=np.float32)
+    with pytest.raises(Exception) as err:
+        env.icp.process_batch(big, big)
+    assert "2304" in str(err.value)
+
+
 def test_device_pointer_abi_and_sequence_chain(env):
     """Layer 1 on CUDA tensors; cfg-2 style consecutive pairs of a room sequence."""
     xy, _ = env.synth.room_sequence(9001, 65, 360)
