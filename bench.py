@@ -9,11 +9,15 @@ half of the metric the HBM roofline target applies to; the same line carries the
 measurement (9 999 consecutive 360-beam pairs) under "icp".  `--workload icp` swaps the roles.
 
 A step is one pass of the hot path over one batch of synthetic scans resident in HBM:
-  grid: zero the count planes, ray-cast SCANS x 1080 beams, (N>1: all-reduce the int32 count
-        deltas over NCCL), finalize to the int8 occupancy map
+  grid: zero the count planes, ray-cast SCANS x 1080 beams, (N>1: merge the int32 count deltas
+        over NVLink peer memory, or all-reduce them over NCCL with --merge nccl), finalize to the
+        int8 occupancy map
   icp : ICP.process over the whole batch of pairs (one CTA per pair)
-`e2e` is the same step through the host-buffer API (Mapping.update_batch / ICP.process_batch):
-pinned host arrays in, host arrays out, copies inside the timed region.
+`e2e` is the same step through the host-buffer API (Mapping.update_batch; ICP.process_sequence,
+cfg 2 being a scan stream): pinned host arrays in, host arrays out, copies inside the timed region,
+after untimed calls that bring the GPU back to full clocks.  Beside it: `e2e_fused_ingestion` (the
+raw-scan entry points Mapping.update_scans / ICP.process_scans, half the bytes) and, for the ICP,
+`e2e_pair_form` (ICP.process_batch on explicit pairs, twice the bytes).
 
 `--impl reference` times the reference's own CPU algorithm (the literal Python/NumPy port in
 oracle/pyref.py -- the reference is pure Python, so there is nothing faster to be fair to) on
