@@ -40,6 +40,7 @@ extern int g_grid_variant;
 extern int g_icp_src_per_thread;
 extern int g_icp_prune;
 extern int g_icp_block;
+int g_icp_graph = 1;  // 1: single-pair ICP calls replay a captured CUDA graph (default); 0: plain stream calls (tuning hook)
 constexpr int MAX_CHUNKS = 16;
 int g_h2d_chunks = 0;  // 0: automatic; 1..MAX_CHUNKS force the pipeline depth of the host-buffer calls (tuning hook)
 
@@ -155,6 +156,16 @@ struct b2s_icp {
     cudaStream_t stream, stream2, copy_stream;
     cudaEvent_t chunk_ready[MAX_CHUNKS], joined;
     Buf d_tar, d_src, d_T, d_iters, d_aux;
+    // The per-scan call of the ROS node (ICP.process: ONE pair) is launch-bound, so its device work -- two uploads,
+    // the solve, two read-backs -- is captured once into a CUDA graph and replayed with one launch.  The graph is
+    // tied to the sizes, parameters and buffer addresses below and re-captured when any of them changes.
+    Buf h_one;  // pinned staging: [tar][src][T (9 doubles)][iterations]
+    cudaGraphExec_t one_exec;
+    struct {
+        int is_f64, n_src, n_tar, max_iter;
+        double tol;
+        void *d_tar, *d_src, *d_T, *d_iters, *h;
+    } one_key;
 };
 
 struct b2s_mapping {
@@ -221,6 +232,11 @@ extern "C" int b2s_tune(const char *key, int value)
         g_icp_block = value;
         return B2S_OK;
     }
+    if (strcmp(key, "icp_graph") == 0) {
+        B2S_REQUIRE(value == 0 || value == 1, "b2s_tune: icp_graph must be 0 or 1");
+        g_icp_graph = value;
+        return B2S_OK;
+    }
     if (strcmp(key, "icp_prune") == 0) {
         B2S_REQUIRE(value >= 0 && value <= 3, "b2s_tune: icp_prune must be 0..3");
         g_icp_prune = value;
@@ -275,6 +291,9 @@ extern "C" int b2s_icp_create(b2s_icp **out, int device)
     c->device = device;
     c->stream = c->stream2 = c->copy_stream = nullptr;
     c->joined = nullptr;
+    c->one_exec = nullptr;
+    memset(&c->one_key, 0, sizeof(c->one_key));
+    c->h_one.pinned = true;
     for (int k = 0; k < MAX_CHUNKS; ++k) c->chunk_ready[k] = nullptr;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
@@ -297,7 +316,9 @@ extern "C" int b2s_icp_destroy(b2s_icp *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream2) cudaStreamSynchronize(c->stream2);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->one_exec) cudaGraphExecDestroy(c->one_exec);
     c->d_tar.release(); c->d_src.release(); c->d_T.release(); c->d_iters.release(); c->d_aux.release();
+    c->h_one.release();
     for (int k = 0; k < MAX_CHUNKS; ++k)
         if (c->chunk_ready[k]) cudaEventDestroy(c->chunk_ready[k]);
     if (c->joined) cudaEventDestroy(c->joined);
@@ -305,6 +326,69 @@ extern "C" int b2s_icp_destroy(b2s_icp *c)
     if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
+    return B2S_OK;
+}
+
+// ICP.process for ONE pair through the captured graph (see b2s_icp::one_exec).
+static int icp_process_one_graph(b2s_icp *c, const void *tar_xy, const void *src_xy, int is_f64, int n_src, int n_tar,
+                                 int max_iter, double tol, double *T_out, int32_t *iters_out)
+{
+    const size_t el = is_f64 ? 8 : 4;
+    const size_t tb = ((size_t)2 * n_tar * el + 15) & ~(size_t)15, sb = ((size_t)2 * n_src * el + 15) & ~(size_t)15;
+    int rc;
+    if ((rc = c->d_tar.reserve(tb))) return rc;
+    if ((rc = c->d_src.reserve(sb))) return rc;
+    if ((rc = c->d_T.reserve(9 * sizeof(double)))) return rc;
+    if ((rc = c->d_iters.reserve(sizeof(int32_t)))) return rc;
+    if ((rc = c->h_one.reserve(tb + sb + 9 * sizeof(double) + 16))) return rc;
+    char *h_tar = (char *)c->h_one.p, *h_src = h_tar + tb;
+    double *h_T = (double *)(h_src + sb);
+    int32_t *h_it = (int32_t *)(h_T + 9);
+    memcpy(h_tar, tar_xy, (size_t)2 * n_tar * el);
+    memcpy(h_src, src_xy, (size_t)2 * n_src * el);
+    auto &k = c->one_key;
+    const bool hit = c->one_exec && k.is_f64 == is_f64 && k.n_src == n_src && k.n_tar == n_tar && k.max_iter == max_iter &&
+                     k.tol == tol && k.d_tar == c->d_tar.p && k.d_src == c->d_src.p && k.d_T == c->d_T.p &&
+                     k.d_iters == c->d_iters.p && k.h == c->h_one.p;
+    if (!hit) {
+        if (c->one_exec) {
+            cudaGraphExecDestroy(c->one_exec);
+            c->one_exec = nullptr;
+        }
+        cudaGraph_t graph = nullptr;
+        B2S_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        cudaError_t e = cudaMemcpyAsync(c->d_tar.p, h_tar, (size_t)2 * n_tar * el, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_src.p, h_src, (size_t)2 * n_src * el, cudaMemcpyHostToDevice, c->stream);
+        rc = B2S_OK;
+        if (e == cudaSuccess)
+            rc = is_f64 ? b2s_icp_batch_f64((const double *)c->d_tar.p, (const double *)c->d_src.p, 1, n_src, n_tar, max_iter, tol,
+                                            (double *)c->d_T.p, (int32_t *)c->d_iters.p, c->stream)
+                        : b2s_icp_batch_f32((const float *)c->d_tar.p, (const float *)c->d_src.p, 1, n_src, n_tar, max_iter, tol,
+                                            (double *)c->d_T.p, (int32_t *)c->d_iters.p, c->stream);
+        if (e == cudaSuccess && rc == B2S_OK)
+            e = cudaMemcpyAsync(h_T, c->d_T.p, 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && rc == B2S_OK)
+            e = cudaMemcpyAsync(h_it, c->d_iters.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+        const cudaError_t e_end = cudaStreamEndCapture(c->stream, &graph);  // always leave capture mode
+        if (rc != B2S_OK || e != cudaSuccess || e_end != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            if (rc != B2S_OK) return rc;  // argument errors keep their message (b2s_icp_batch: ...)
+            return cuda_fail(e != cudaSuccess ? e : e_end, "b2s_icp_process: graph capture");
+        }
+        e = cudaGraphInstantiate(&c->one_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            c->one_exec = nullptr;
+            return cuda_fail(e, "b2s_icp_process: cudaGraphInstantiate");
+        }
+        k.is_f64 = is_f64; k.n_src = n_src; k.n_tar = n_tar; k.max_iter = max_iter; k.tol = tol;
+        k.d_tar = c->d_tar.p; k.d_src = c->d_src.p; k.d_T = c->d_T.p; k.d_iters = c->d_iters.p; k.h = c->h_one.p;
+    }
+    B2S_CUDA(cudaGraphLaunch(c->one_exec, c->stream));
+    B2S_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(T_out, h_T, 9 * sizeof(double));
+    if (iters_out) *iters_out = *h_it;
     return B2S_OK;
 }
 
@@ -317,6 +401,8 @@ extern "C" int b2s_icp_process(b2s_icp *c, const void *tar_xy, const void *src_x
     if (pairs == 0) return B2S_OK;
     B2S_REQUIRE(tar_xy && src_xy && T_out, "b2s_icp_process: null pointer");
     DeviceGuard g(c->device);
+    if (pairs == 1 && g_icp_graph && !getenv("B2S_TRACE"))
+        return icp_process_one_graph(c, tar_xy, src_xy, is_f64, n_src, n_tar, max_iter, tol, T_out, iters_out);
     Trace tr(c->stream);
     const size_t el = is_f64 ? 8 : 4;
     const size_t tb = (size_t)pairs * 2 * n_tar * el, sb = (size_t)pairs * 2 * n_src * el;

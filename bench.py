@@ -505,6 +505,15 @@ def drop_in_latency(torch, synth):
     for _ in range(50):
         icp.process(t3, s3)
     out["ICP.process cfg1 (360 beams, max_iter 10, tolerance 0) ms"] = (time.perf_counter() - t0) / 50 * 1e3
+    from b2slam import _lib
+    _lib.check(_lib.lib().b2s_tune(b"icp_graph", 0))                  # the same call as plain stream operations
+    for _ in range(5):
+        icp.process(t3, s3)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        icp.process(t3, s3)
+    out["ICP.process cfg1 without the captured CUDA graph ms"] = (time.perf_counter() - t0) / 50 * 1e3
+    _lib.check(_lib.lib().b2s_tune(b"icp_graph", 1))
     ox, oy, cx, cy = synth.grid_scans(12001, 64, 1080, half_extent_m=8.0)
     for shape, reso in (((200, 200), 0.1), ((4096, 4096), 0.05)):
         m = b2slam.Mapping(shape[0], shape[1], reso)

@@ -106,6 +106,38 @@ def test_unequal_sizes_odd_counts_and_zero_iterations(env):
     assert Te.shape == (0, 3, 3) and ite.shape == (0,)
 
 
+def test_single_pair_graph_path(env):
+    """ICP.process (one pair) replays a captured CUDA graph; it must give the bits of the plain stream path and of
+    the batched call, survive changing sizes / parameters / dtypes (re-capture) and interleaved batched calls
+    (device buffers may move), and keep returning fresh results on replay."""
+    tune = env.lib.lib().b2s_tune
+    rng = np.random.Generator(np.random.PCG64(5))
+    seen = []
+    try:
+        for rep, (n, m, dtype, max_iter, tol) in enumerate([(360, 360, np.float32, 30, 1e-3), (360, 360, np.float32, 30, 1e-3),
+                                                          (120, 97, np.float64, 30, 1e-3), (360, 360, np.float32, 10, 0.0),
+                                                          (1080, 1080, np.float32, 30, 1e-3), (360, 360, np.float32, 30, 1e-3)]):
+            tar, src, _ = env.synth.icp_pairs(100 + rep, 1, max(n, m))
+            tar, src = tar[:, :, :m].astype(dtype), src[:, :, :n].astype(dtype)
+            assert tune(b"icp_graph", 1) == 0
+            Tg, ig = env.icp.process_batch(tar, src, max_iter=max_iter, tolerance=tol)
+            Tg2, ig2 = env.icp.process_batch(tar, src, max_iter=max_iter, tolerance=tol)      # replay
+            assert tune(b"icp_graph", 0) == 0
+            Tp, ip = env.icp.process_batch(tar, src, max_iter=max_iter, tolerance=tol)
+            assert np.array_equal(Tg, Tp) and np.array_equal(ig, ip) and np.array_equal(Tg2, Tp), rep
+            both = np.concatenate([tar, tar]), np.concatenate([src, src])
+            Tb, ib = env.icp.process_batch(*both, max_iter=max_iter, tolerance=tol)          # batched call in between
+            assert np.array_equal(Tb[0], Tp[0]) and np.array_equal(Tb[1], Tp[0]) and ib[0] == ip[0]
+            seen.append(Tg)
+        assert not np.array_equal(seen[0], seen[1])      # different pairs, same shape: the replay read the new inputs
+        assert tune(b"icp_graph", 1) == 0
+        cloud = np.vstack([rng.normal(0, 3, (2, 200)), np.ones((1, 200))])
+        T = env.icp.process(cloud, cloud)                # the reference-signature call
+        np.testing.assert_allclose(T, np.identity(3), rtol=0, atol=1e-12)
+    finally:
+        tune(b"icp_graph", 1)
+
+
 def test_largest_supported_scan_and_the_limit(env):
     """2304 points per scan is the documented ceiling (the CTA's register budget): it must run and agree with the
     oracle; one point more is refused with a status code, not a launch failure."""
