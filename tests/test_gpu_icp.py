@@ -138,6 +138,29 @@ def test_single_pair_graph_path(env):
         tune(b"icp_graph", 1)
 
 
+def test_call_timeline_trace_does_not_change_results(env, capfd):
+    """B2S_TRACE=1 prints the timeline of the host-buffer calls (and routes single pairs through the plain stream
+    path); results are unchanged and the marks arrive on stderr."""
+    import os
+    xy, _ = env.synth.room_sequence(9001, 40, 360)
+    T0, it0 = env.icp.process_sequence(xy)
+    ox, oy, cx, cy = env.synth.grid_scans(3, 6, 360, half_extent_m=5.0)
+    m0 = env.b2slam.Mapping(256, 256, 0.05)
+    p0 = m0.update_batch(ox, oy, cx, cy).copy()
+    os.environ["B2S_TRACE"] = "1"
+    try:
+        T1, it1 = env.icp.process_sequence(xy)
+        T2, it2 = env.icp.process_batch(xy[:1], xy[1:2])
+        m1 = env.b2slam.Mapping(256, 256, 0.05)
+        p1 = m1.update_batch(ox, oy, cx, cy).copy()
+    finally:
+        del os.environ["B2S_TRACE"]
+    err = capfd.readouterr().err
+    assert "[b2s trace]" in err and "icp chunk done" in err and "ray-cast chunk done" in err
+    assert np.array_equal(T1, T0) and np.array_equal(it1, it0) and np.array_equal(T2[0], T0[0])
+    assert np.array_equal(p1, p0)
+
+
 def test_largest_supported_scan_and_the_limit(env):
     """2304 points per scan is the documented ceiling (the CTA's register budget): it must run and agree with the
     oracle; one point more is refused with a status code, not a launch failure."""
