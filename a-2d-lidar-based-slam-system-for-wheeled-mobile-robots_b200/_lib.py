@@ -37,13 +37,18 @@ SIGNATURES = {
     "b2s_rigid_fit_f64": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "b2s_grid_raycast": (_i32, [_vp, _vp, _i32, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp,
                                 _i32, _i32, _vp, _vp]),
+    "b2s_grid_raycast_f64": (_i32, [_vp, _vp, _i32, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp,
+                                    _i32, _i32, _vp, _vp]),
     "b2s_grid_workspace_bytes": (_sz, [_i32, _i32]),
     "b2s_grid_workspace_init": (_i32, [_vp, _i32, _i32, _vp]),
     "b2s_grid_raycast_ws": (_i32, [_vp, _vp, _i32, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp,
                                    _i32, _i32, _vp, _vp, _vp]),
+    "b2s_grid_raycast_ws_f64": (_i32, [_vp, _vp, _i32, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp,
+                                       _i32, _i32, _vp, _vp, _vp]),
     "b2s_grid_raycast_ranges": (_i32, [_vp, _vp, _i32, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp, _dbl,
                                        _i32, _i32, _vp, _vp, _vp]),
     "b2s_grid_validate": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "b2s_grid_validate_f64": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "b2s_grid_finalize": (_i32, [_vp, _vp, _i32, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
     "b2s_grid_pack_ros": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "b2s_bresenham_paths": (_i32, [_vp, _i32, _vp, _vp, _vp]),
@@ -80,6 +85,9 @@ SIGNATURES = {
     "b2s_mapping_destroy": (_i32, [_vp]),
     "b2s_mapping_reset": (_i32, [_vp]),
     "b2s_mapping_update": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "b2s_mapping_update_f64": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "b2s_mapping_update_incremental_f64": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32,
+                                                  ctypes.POINTER(_i32)]),
     "b2s_mapping_update_incremental": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32,
                                               ctypes.POINTER(_i32)]),
     "b2s_mapping_update_ranges": (_i32, [_vp, _vp, _vp, _vp, _dbl, _i32, _i32, _vp]),

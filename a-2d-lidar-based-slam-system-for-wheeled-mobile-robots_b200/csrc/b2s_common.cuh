@@ -44,7 +44,7 @@ inline size_t grid_dirty_bytes(int xw, int yw)
 }
 
 int grid_raycast_signed(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m, double off_x,
-                        double off_y, const float *ox, const float *oy, const float *cx, const float *cy,
+                        double off_y, const void *ox, const void *oy, const void *cx, const void *cy, bool is_f64,
                         int scans, int beams, int32_t *counters, void *workspace, int sign, void *stream,
                         bool fold = true);
 int grid_finalize_dirty(const int32_t *hit, const int32_t *miss, int xw, int yw, double w_hit, double w_miss,

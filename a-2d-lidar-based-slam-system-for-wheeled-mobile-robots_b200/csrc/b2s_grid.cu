@@ -103,17 +103,18 @@ __device__ __forceinline__ void bres_step(double &acc, int &minor, double slope,
 // ------------------------------------------------------------------------------------------
 // Variant 1: one beam per thread, one RED.ADD per in-grid cell.
 
+template <typename CT>
 __global__ void __launch_bounds__(256)
 grid_raycast_v1(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int xw, int yw,
-                double cells_per_m, double off_x, double off_y, const float *__restrict__ ox,
-                const float *__restrict__ oy, const float *__restrict__ cx,
-                const float *__restrict__ cy, long long total, int beams, int32_t *counters)
+                double cells_per_m, double off_x, double off_y, const CT *__restrict__ ox,
+                const CT *__restrict__ oy, const CT *__restrict__ cx,
+                const CT *__restrict__ cy, long long total, int beams, int32_t *counters)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int s = (int)(i / beams);
     Beam b;
-    const int st = beam_setup(__ldg(ox + i), __ldg(oy + i), __ldg(cx + s), __ldg(cy + s), xw, yw,
+    const int st = beam_setup((double)__ldg(ox + i), (double)__ldg(oy + i), (double)__ldg(cx + s), (double)__ldg(cy + s), xw, yw,
                               cells_per_m, off_x, off_y, b);
     if (st != BEAM_OK) {
         count_status(st, counters);
@@ -147,11 +148,12 @@ grid_raycast_v1(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int xw, i
 // they are sorted by angle, equal cells sit in adjacent lanes: one shuffle + ballot finds the
 // runs and only the head lane of each run issues RED.ADD with the run length.
 
+template <typename CT>
 __global__ void __launch_bounds__(256)
 grid_raycast_v2(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int xw, int yw,
-                double cells_per_m, double off_x, double off_y, const float *__restrict__ ox,
-                const float *__restrict__ oy, const float *__restrict__ cx,
-                const float *__restrict__ cy, long long total, int beams, int32_t *counters)
+                double cells_per_m, double off_x, double off_y, const CT *__restrict__ ox,
+                const CT *__restrict__ oy, const CT *__restrict__ cx,
+                const CT *__restrict__ cy, long long total, int beams, int32_t *counters)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -159,7 +161,7 @@ grid_raycast_v2(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int xw, i
     int st = BEAM_NOOP;
     if (i < total) {
         const int s = (int)(i / beams);
-        st = beam_setup(__ldg(ox + i), __ldg(oy + i), __ldg(cx + s), __ldg(cy + s), xw, yw,
+        st = beam_setup((double)__ldg(ox + i), (double)__ldg(oy + i), (double)__ldg(cx + s), (double)__ldg(cy + s), xw, yw,
                         cells_per_m, off_x, off_y, b);
         if (st != BEAM_OK) count_status(st, counters);
     }
@@ -240,11 +242,12 @@ __device__ __forceinline__ void march_step(int t, int delay, double slope, doubl
     if (head && emit) atomicAdd(miss + key, run);
 }
 
+template <typename CT>
 __global__ void __launch_bounds__(256)
 grid_raycast_v3(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int xw, int yw,
-                double cells_per_m, double off_x, double off_y, const float *__restrict__ ox,
-                const float *__restrict__ oy, const float *__restrict__ cx,
-                const float *__restrict__ cy, long long total, int beams, int32_t *counters)
+                double cells_per_m, double off_x, double off_y, const CT *__restrict__ ox,
+                const CT *__restrict__ oy, const CT *__restrict__ cx,
+                const CT *__restrict__ cy, long long total, int beams, int32_t *counters)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31;
@@ -254,7 +257,7 @@ grid_raycast_v3(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int xw, i
     int st = BEAM_NOOP;
     if (i < total) {
         const int s = (int)(i / beams);
-        st = beam_setup(__ldg(ox + i), __ldg(oy + i), __ldg(cx + s), __ldg(cy + s), xw, yw,
+        st = beam_setup((double)__ldg(ox + i), (double)__ldg(oy + i), (double)__ldg(cx + s), (double)__ldg(cy + s), xw, yw,
                         cells_per_m, off_x, off_y, b);
         if (st != BEAM_OK) count_status(st, counters);
     }
@@ -374,30 +377,37 @@ __device__ __forceinline__ void march_step4(int t, int delay, double slope, doub
         : "memory");
 }
 
-// Where a beam's endpoints come from.  FUSED = false: world-frame endpoints ox, oy + sensor position
-// cx, cy (the arguments of Mapping.update).  FUSED = true: raw ranges + pose, i.e. the node's
+// Where a beam's endpoints come from.  IN_F32 / IN_F64: world-frame endpoints ox, oy + sensor position
+// cx, cy (the arguments of Mapping.update) as float32, or as the float64 the reference's callers pass
+// ([SLAM]:89-90: obs and xEst are float64).  IN_FUSED: raw ranges + pose, i.e. the node's
 // laserToNumpy ([SLAM]:115-123) and `u2T(xEst).dot(np_msg)` ([SLAM]:130-137,89) evaluated per beam in
 // float64: p = (cos a * r, sin a * r) with inf -> clamp, o = (cw*px + (-sw)*py) + x, (sw*px + cw*py) + y.
 // cos/sin of the beam angles and of the yaw are computed by the host exactly as the reference
 // computes them (NumPy / math), so the device only multiplies and adds.
+enum { IN_F32 = 0, IN_FUSED = 1, IN_F64 = 2 };
 struct ScanInput {
-    const float *ox, *oy, *cx, *cy;  // endpoints mode
+    const void *ox, *oy, *cx, *cy;   // endpoints modes: float32 (IN_F32) or float64 (IN_F64, the reference's dtype)
     const float *ranges;             // fused mode: [scans][beams]
     const double *pose4;             // fused mode: [scans][4] = x, y, cos(yaw), sin(yaw)
     const double *beam_cs;           // fused mode: [beams][2] = cos(angle), sin(angle)
     double clamp;                    // fused mode: replacement for +inf ranges (MAX_LASER_RANGE), <= 0: none
 };
 
-template <bool FUSED>
+template <int MODE>
 __device__ __forceinline__ void load_beam(const ScanInput &in, long long i, int beams, double &fox, double &foy,
                                           double &fcx, double &fcy)
 {
     const int s = (int)(i / beams);
-    if (!FUSED) {
-        fox = (double)__ldg(in.ox + i);
-        foy = (double)__ldg(in.oy + i);
-        fcx = (double)__ldg(in.cx + s);
-        fcy = (double)__ldg(in.cy + s);
+    if (MODE == IN_F32) {
+        fox = (double)__ldg((const float *)in.ox + i);
+        foy = (double)__ldg((const float *)in.oy + i);
+        fcx = (double)__ldg((const float *)in.cx + s);
+        fcy = (double)__ldg((const float *)in.cy + s);
+    } else if (MODE == IN_F64) {  // [MAP]:33-36 consumes float64: nothing is narrowed on the way to int()
+        fox = __ldg((const double *)in.ox + i);
+        foy = __ldg((const double *)in.oy + i);
+        fcx = __ldg((const double *)in.cx + s);
+        fcy = __ldg((const double *)in.cy + s);
     } else {
         const int j = (int)(i - (long long)s * beams);
         double r = (double)__ldg(in.ranges + i);
@@ -414,7 +424,7 @@ __device__ __forceinline__ void load_beam(const ScanInput &in, long long i, int 
 }
 
 // SIGN = +1 applies a batch, SIGN = -1 takes the same batch back out (exact inverse: integer adds).
-template <int SIGN, bool FUSED>
+template <int SIGN, int MODE>
 __global__ void __launch_bounds__(256, 8)
 grid_raycast_v4(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int32_t *__restrict__ scratch_t,
                 GridWorkspace *__restrict__ ws, uint8_t *__restrict__ dirty, int xw, int yw, double cells_per_m,
@@ -428,7 +438,7 @@ grid_raycast_v4(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int32_t *
     int st = BEAM_NOOP;
     if (i < total) {
         double fox, foy, fcx, fcy;
-        load_beam<FUSED>(in, i, beams, fox, foy, fcx, fcy);
+        load_beam<MODE>(in, i, beams, fox, foy, fcx, fcy);
         st = beam_setup(fox, foy, fcx, fcy, xw, yw, cells_per_m, off_x, off_y, b);
         if (st != BEAM_OK && SIGN > 0) count_status(st, counters);
     }
@@ -545,21 +555,22 @@ grid_fold_kernel(int32_t *__restrict__ miss, int32_t *__restrict__ scratch_t, co
 // Input screening for the host-buffer API: flags[0] |= NaN anywhere, flags[1] |= inf in oy or in a
 // sensor position -- the values int() raises on in [MAP]:33-36 (inf in ox alone is legal, [MAP]:30).
 
+template <typename CT>
 __global__ void __launch_bounds__(256)
-grid_validate_kernel(const float *__restrict__ ox, const float *__restrict__ oy, long long total,
-                     const float *__restrict__ cx, const float *__restrict__ cy, int scans,
+grid_validate_kernel(const CT *__restrict__ ox, const CT *__restrict__ oy, long long total,
+                     const CT *__restrict__ cx, const CT *__restrict__ cy, int scans,
                      int32_t *__restrict__ flags)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
     bool has_nan = false, has_inf = false;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const float x = __ldg(ox + i), y = __ldg(oy + i);
+        const CT x = __ldg(ox + i), y = __ldg(oy + i);
         if (isinf(x)) continue;  // the beam is skipped before oy is looked at
         has_nan |= isnan(x) || isnan(y);
         has_inf |= isinf(y);
     }
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < scans; i += stride) {
-        const float x = __ldg(cx + i), y = __ldg(cy + i);
+        const CT x = __ldg(cx + i), y = __ldg(cy + i);
         has_nan |= isnan(x) || isnan(y);
         has_inf |= isinf(x) || isinf(y);
     }
@@ -663,10 +674,11 @@ bresenham_paths_kernel(const int32_t *__restrict__ segs, int count, const int64_
 
 using namespace b2s;
 
-extern "C" int b2s_grid_raycast(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m,
-                                double off_x, double off_y, const float *ox, const float *oy,
-                                const float *cx, const float *cy, int scans, int beams,
-                                int32_t *counters, void *stream)
+namespace b2s {
+template <typename CT>
+static int raycast_plain(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m, double off_x, double off_y,
+                         const CT *ox, const CT *oy, const CT *cx, const CT *cy, int scans, int beams,
+                         int32_t *counters, void *stream)
 {
     B2S_REQUIRE(hit && miss && ox && oy && cx && cy, "b2s_grid_raycast: null pointer");
     B2S_REQUIRE(xw > 0 && yw > 0 && (long long)xw * yw < (1ll << 31), "b2s_grid_raycast: grid size");
@@ -679,16 +691,35 @@ extern "C" int b2s_grid_raycast(int32_t *hit, int32_t *miss, int xw, int yw, dou
     B2S_REQUIRE(blocks < (1ll << 31), "b2s_grid_raycast: too many beams for one launch");
     cudaStream_t st = (cudaStream_t)stream;
     if (g_grid_variant == 1)
-        grid_raycast_v1<<<(unsigned)blocks, threads, 0, st>>>(hit, miss, xw, yw, cells_per_m, off_x, off_y,
-                                                              ox, oy, cx, cy, total, beams, counters);
+        grid_raycast_v1<CT><<<(unsigned)blocks, threads, 0, st>>>(hit, miss, xw, yw, cells_per_m, off_x, off_y,
+                                                                  ox, oy, cx, cy, total, beams, counters);
     else if (g_grid_variant == 2)
-        grid_raycast_v2<<<(unsigned)blocks, threads, 0, st>>>(hit, miss, xw, yw, cells_per_m, off_x, off_y,
-                                                              ox, oy, cx, cy, total, beams, counters);
+        grid_raycast_v2<CT><<<(unsigned)blocks, threads, 0, st>>>(hit, miss, xw, yw, cells_per_m, off_x, off_y,
+                                                                  ox, oy, cx, cy, total, beams, counters);
     else  // 3, and 4 without a workspace
-        grid_raycast_v3<<<(unsigned)blocks, threads, 0, st>>>(hit, miss, xw, yw, cells_per_m, off_x, off_y,
-                                                              ox, oy, cx, cy, total, beams, counters);
+        grid_raycast_v3<CT><<<(unsigned)blocks, threads, 0, st>>>(hit, miss, xw, yw, cells_per_m, off_x, off_y,
+                                                                  ox, oy, cx, cy, total, beams, counters);
     B2S_CUDA(cudaGetLastError());
     return B2S_OK;
+}
+}  // namespace b2s
+
+extern "C" int b2s_grid_raycast(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m,
+                                double off_x, double off_y, const float *ox, const float *oy,
+                                const float *cx, const float *cy, int scans, int beams,
+                                int32_t *counters, void *stream)
+{
+    return raycast_plain<float>(hit, miss, xw, yw, cells_per_m, off_x, off_y, ox, oy, cx, cy, scans, beams, counters,
+                                stream);
+}
+
+extern "C" int b2s_grid_raycast_f64(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m,
+                                    double off_x, double off_y, const double *ox, const double *oy,
+                                    const double *cx, const double *cy, int scans, int beams,
+                                    int32_t *counters, void *stream)
+{
+    return raycast_plain<double>(hit, miss, xw, yw, cells_per_m, off_x, off_y, ox, oy, cx, cy, scans, beams, counters,
+                                 stream);
 }
 
 extern "C" size_t b2s_grid_workspace_bytes(int xw, int yw)
@@ -712,7 +743,7 @@ namespace b2s {
 // Shared by b2s_grid_raycast_ws / b2s_grid_raycast_ranges (sign +1) and the host layer's roll-back of a
 // rejected batch (sign -1).
 static int raycast_v4_launch(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m, double off_x,
-                             double off_y, const ScanInput &in, bool fused, int scans, int beams, int32_t *counters,
+                             double off_y, const ScanInput &in, int mode, int scans, int beams, int32_t *counters,
                              void *workspace, int sign, void *stream, bool fold)
 {
     B2S_REQUIRE(hit && miss && workspace, "b2s_grid_raycast_ws: null pointer");
@@ -734,9 +765,9 @@ static int raycast_v4_launch(int32_t *hit, int32_t *miss, int xw, int yw, double
                                                                    cells_per_m, off_x, off_y, in, total, beams, \
                                                                    counters)
     if (sign >= 0) {
-        if (fused) B2S_V4(1, true); else B2S_V4(1, false);
+        if (mode == IN_FUSED) B2S_V4(1, IN_FUSED); else if (mode == IN_F64) B2S_V4(1, IN_F64); else B2S_V4(1, IN_F32);
     } else {
-        if (fused) B2S_V4(-1, true); else B2S_V4(-1, false);
+        if (mode == IN_FUSED) B2S_V4(-1, IN_FUSED); else if (mode == IN_F64) B2S_V4(-1, IN_F64); else B2S_V4(-1, IN_F32);
     }
 #undef B2S_V4
     B2S_CUDA(cudaGetLastError());
@@ -749,13 +780,13 @@ static int raycast_v4_launch(int32_t *hit, int32_t *miss, int xw, int yw, double
 }
 
 int grid_raycast_signed(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m, double off_x,
-                        double off_y, const float *ox, const float *oy, const float *cx, const float *cy,
+                        double off_y, const void *ox, const void *oy, const void *cx, const void *cy, bool is_f64,
                         int scans, int beams, int32_t *counters, void *workspace, int sign, void *stream, bool fold)
 {
     B2S_REQUIRE(ox && oy && cx && cy, "b2s_grid_raycast_ws: null pointer");
     ScanInput in = {ox, oy, cx, cy, nullptr, nullptr, nullptr, 0.0};
-    return raycast_v4_launch(hit, miss, xw, yw, cells_per_m, off_x, off_y, in, false, scans, beams, counters,
-                             workspace, sign, stream, fold);
+    return raycast_v4_launch(hit, miss, xw, yw, cells_per_m, off_x, off_y, in, is_f64 ? IN_F64 : IN_F32, scans, beams,
+                             counters, workspace, sign, stream, fold);
 }
 
 int grid_raycast_ranges_signed(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m, double off_x,
@@ -767,7 +798,7 @@ int grid_raycast_ranges_signed(int32_t *hit, int32_t *miss, int xw, int yw, doub
     B2S_REQUIRE((uintptr_t)pose4 % 16 == 0 && (uintptr_t)beam_cs % 16 == 0,
                 "b2s_grid_raycast_ranges: pose and beam tables must be 16-byte aligned");
     ScanInput in = {nullptr, nullptr, nullptr, nullptr, ranges, pose4, beam_cs, clamp};
-    return raycast_v4_launch(hit, miss, xw, yw, cells_per_m, off_x, off_y, in, true, scans, beams, counters,
+    return raycast_v4_launch(hit, miss, xw, yw, cells_per_m, off_x, off_y, in, IN_FUSED, scans, beams, counters,
                              workspace, sign, stream, fold);
 }
 }  // namespace b2s
@@ -789,7 +820,19 @@ extern "C" int b2s_grid_raycast_ws(int32_t *hit, int32_t *miss, int xw, int yw, 
     if (workspace == nullptr || g_grid_variant != 4)
         return b2s_grid_raycast(hit, miss, xw, yw, cells_per_m, off_x, off_y, ox, oy, cx, cy, scans, beams,
                                 counters, stream);
-    return grid_raycast_signed(hit, miss, xw, yw, cells_per_m, off_x, off_y, ox, oy, cx, cy, scans, beams,
+    return grid_raycast_signed(hit, miss, xw, yw, cells_per_m, off_x, off_y, ox, oy, cx, cy, false, scans, beams,
+                               counters, workspace, +1, stream);
+}
+
+extern "C" int b2s_grid_raycast_ws_f64(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m,
+                                       double off_x, double off_y, const double *ox, const double *oy,
+                                       const double *cx, const double *cy, int scans, int beams,
+                                       int32_t *counters, void *workspace, void *stream)
+{
+    if (workspace == nullptr || g_grid_variant != 4)
+        return b2s_grid_raycast_f64(hit, miss, xw, yw, cells_per_m, off_x, off_y, ox, oy, cx, cy, scans, beams,
+                                    counters, stream);
+    return grid_raycast_signed(hit, miss, xw, yw, cells_per_m, off_x, off_y, ox, oy, cx, cy, true, scans, beams,
                                counters, workspace, +1, stream);
 }
 
@@ -887,8 +930,10 @@ extern "C" int b2s_grid_clear_dirty(int32_t *hit, int32_t *miss, int xw, int yw,
     return B2S_OK;
 }
 
-extern "C" int b2s_grid_validate(const float *ox, const float *oy, const float *cx, const float *cy,
-                                 int scans, int beams, int32_t *flags, void *stream)
+namespace b2s {
+template <typename CT>
+static int validate_impl(const CT *ox, const CT *oy, const CT *cx, const CT *cy, int scans, int beams, int32_t *flags,
+                         void *stream)
 {
     B2S_REQUIRE(scans >= 0 && beams >= 0, "b2s_grid_validate: negative count");
     B2S_REQUIRE(flags, "b2s_grid_validate: null flags");
@@ -899,9 +944,22 @@ extern "C" int b2s_grid_validate(const float *ox, const float *oy, const float *
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    grid_validate_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ox, oy, total, cx, cy, scans, flags);
+    grid_validate_kernel<CT><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ox, oy, total, cx, cy, scans, flags);
     B2S_CUDA(cudaGetLastError());
     return B2S_OK;
+}
+}  // namespace b2s
+
+extern "C" int b2s_grid_validate(const float *ox, const float *oy, const float *cx, const float *cy,
+                                 int scans, int beams, int32_t *flags, void *stream)
+{
+    return validate_impl<float>(ox, oy, cx, cy, scans, beams, flags, stream);
+}
+
+extern "C" int b2s_grid_validate_f64(const double *ox, const double *oy, const double *cx, const double *cy,
+                                     int scans, int beams, int32_t *flags, void *stream)
+{
+    return validate_impl<double>(ox, oy, cx, cy, scans, beams, flags, stream);
 }
 
 extern "C" int b2s_grid_finalize(const int32_t *hit, const int32_t *miss, int xw, int yw, double w_hit,

@@ -743,7 +743,8 @@ namespace {
 // One host batch in either input form.
 struct HostBatch {
     bool fused;
-    const float *ox, *oy, *cx, *cy;  // endpoints form
+    bool f64;                        // endpoints form: float64 (the reference's dtype) instead of float32
+    const void *ox, *oy, *cx, *cy;   // endpoints form
     const float *ranges;             // fused form
     const double *pose4, *beam_cs;   // pose4 [scans][4] = x, y, cos yaw, sin yaw ...
     double clamp;
@@ -768,7 +769,8 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
     int rc;
     int nchunk = 0;
     int lo[MAX_CHUNKS + 1] = {0};
-    float *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_d = nullptr;  // ox|oy|cx|cy  or  ranges
+    char *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_d = nullptr;  // ox|oy|cx|cy  or  ranges
+    const size_t el = (!hb.fused && hb.f64) ? sizeof(double) : sizeof(float);  // bytes per input coordinate
     double *d_pose = nullptr, *d_cs = nullptr;
     // (the transposed scratch plane of the ray-cast is folded back once, with the last chunk)
     auto launch = [&](int k, int sign, int32_t *counters, cudaStream_t ks) -> int {
@@ -777,31 +779,31 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
         const bool fold = (k == nchunk - 1);
         if (hb.fused)
             return grid_raycast_ranges_signed(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y,
-                                              d_a + s0 * beams, d_pose + 4 * s0, d_cs, hb.clamp, ns, beams, counters,
-                                              m->workspace, sign, ks, fold);
+                                              (const float *)d_a + s0 * beams, d_pose + 4 * s0, d_cs, hb.clamp, ns, beams,
+                                              counters, m->workspace, sign, ks, fold);
         return grid_raycast_signed(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y,
-                                   d_a + s0 * beams, d_b + s0 * beams, d_c + s0, d_d + s0, ns, beams, counters,
-                                   m->workspace, sign, ks, fold);
+                                   d_a + s0 * beams * el, d_b + s0 * beams * el, d_c + s0 * el, d_d + s0 * el, hb.f64, ns,
+                                   beams, counters, m->workspace, sign, ks, fold);
     };
     if (total > 0) {
-        const size_t pts = total * sizeof(float), a_pts = (pts + 15) & ~(size_t)15;
+        const size_t pts = total * el, a_pts = (pts + 15) & ~(size_t)15;
         char *base;
         if (hb.fused) {
             const size_t poses = (size_t)scans * 4 * sizeof(double), table = (size_t)beams * 2 * sizeof(double);
             if ((rc = m->d_in.reserve(a_pts + poses + table))) return rc;
             base = (char *)m->d_in.p;
-            d_a = (float *)base;
+            d_a = base;
             d_pose = (double *)(base + a_pts);
             d_cs = (double *)(base + a_pts + poses);
             B2S_CUDA(cudaMemcpyAsync(d_cs, hb.beam_cs, table, cudaMemcpyHostToDevice, m->copy_stream));
         } else {
-            const size_t ctr = (size_t)scans * sizeof(float), a_ctr = (ctr + 15) & ~(size_t)15;
+            const size_t ctr = (size_t)scans * el, a_ctr = (ctr + 15) & ~(size_t)15;
             if ((rc = m->d_in.reserve(2 * a_pts + 2 * a_ctr))) return rc;
             base = (char *)m->d_in.p;
-            d_a = (float *)base;
-            d_b = (float *)(base + a_pts);
-            d_c = (float *)(base + 2 * a_pts);
-            d_d = (float *)(base + 2 * a_pts + a_ctr);
+            d_a = base;
+            d_b = base + a_pts;
+            d_c = base + 2 * a_pts;
+            d_d = base + 2 * a_pts + a_ctr;
         }
         // counters[0..3]: the ray-cast kernel's own (B2S_CNT_*); counters[4]: dirty-tile count of this call
         B2S_CUDA(cudaMemsetAsync(m->counters, 0, 2 * B2S_CNT_WORDS * sizeof(int32_t), m->stream));
@@ -809,7 +811,7 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
         B2S_CUDA(cudaMemsetAsync((char *)m->workspace + GRID_WS_HEADER, 0, grid_dirty_bytes(m->xw, m->yw), m->stream));
         // ~1M beams per chunk: with consecutive chunks overlapping on two compute streams an extra launch costs
         // little, and the first ray-cast starts after 1/16 of the copy (measured: profiles/scripts/chunk_sweep.py)
-        nchunk = (int)((total + (1u << 20) - 1) >> 20);
+        nchunk = (int)((total * (el / sizeof(float)) + (1u << 20) - 1) >> 20);
         if (nchunk > MAX_CHUNKS) nchunk = MAX_CHUNKS;
         if (g_h2d_chunks > 0) nchunk = g_h2d_chunks;
         if (nchunk > scans) nchunk = scans;
@@ -840,13 +842,13 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
                         table[4 * s + 2] = cos(hb.poses3[3 * s + 2]);
                         table[4 * s + 3] = sin(hb.poses3[3 * s + 2]);
                     }
-                B2S_CUDA(cudaMemcpyAsync(d_a + s0 * beams, hb.ranges + s0 * beams, ns * beams * sizeof(float), cudaMemcpyHostToDevice, cs));
+                B2S_CUDA(cudaMemcpyAsync(d_a + s0 * beams * sizeof(float), hb.ranges + s0 * beams, ns * beams * sizeof(float), cudaMemcpyHostToDevice, cs));
                 B2S_CUDA(cudaMemcpyAsync(d_pose + 4 * s0, pose4 + 4 * s0, ns * 4 * sizeof(double), cudaMemcpyHostToDevice, cs));
             } else {
-                B2S_CUDA(cudaMemcpyAsync(d_a + s0 * beams, hb.ox + s0 * beams, ns * beams * sizeof(float), cudaMemcpyHostToDevice, cs));
-                B2S_CUDA(cudaMemcpyAsync(d_b + s0 * beams, hb.oy + s0 * beams, ns * beams * sizeof(float), cudaMemcpyHostToDevice, cs));
-                B2S_CUDA(cudaMemcpyAsync(d_c + s0, hb.cx + s0, ns * sizeof(float), cudaMemcpyHostToDevice, cs));
-                B2S_CUDA(cudaMemcpyAsync(d_d + s0, hb.cy + s0, ns * sizeof(float), cudaMemcpyHostToDevice, cs));
+                B2S_CUDA(cudaMemcpyAsync(d_a + s0 * beams * el, (const char *)hb.ox + s0 * beams * el, ns * beams * el, cudaMemcpyHostToDevice, cs));
+                B2S_CUDA(cudaMemcpyAsync(d_b + s0 * beams * el, (const char *)hb.oy + s0 * beams * el, ns * beams * el, cudaMemcpyHostToDevice, cs));
+                B2S_CUDA(cudaMemcpyAsync(d_c + s0 * el, (const char *)hb.cx + s0 * el, ns * el, cudaMemcpyHostToDevice, cs));
+                B2S_CUDA(cudaMemcpyAsync(d_d + s0 * el, (const char *)hb.cy + s0 * el, ns * el, cudaMemcpyHostToDevice, cs));
             }
             B2S_CUDA(cudaEventRecord(m->chunk_ready[k], cs));
             tr.mark("h2d chunk done", k, cs);
@@ -957,7 +959,17 @@ extern "C" int b2s_mapping_update(b2s_mapping *m, const float *ox, const float *
     B2S_REQUIRE(m, "b2s_mapping_update: null handle");
     B2S_REQUIRE(scans >= 0 && beams >= 0, "b2s_mapping_update: negative count");
     B2S_REQUIRE((size_t)scans * beams == 0 || (ox && oy && cx && cy), "b2s_mapping_update: null pointer");
-    HostBatch hb = {false, ox, oy, cx, cy, nullptr, nullptr, nullptr, 0.0, nullptr};
+    HostBatch hb = {false, false, ox, oy, cx, cy, nullptr, nullptr, nullptr, 0.0, nullptr};
+    return mapping_update_impl(m, hb, scans, beams, pmap_out);
+}
+
+extern "C" int b2s_mapping_update_f64(b2s_mapping *m, const double *ox, const double *oy, const double *cx,
+                                      const double *cy, int scans, int beams, int8_t *pmap_out)
+{
+    B2S_REQUIRE(m, "b2s_mapping_update_f64: null handle");
+    B2S_REQUIRE(scans >= 0 && beams >= 0, "b2s_mapping_update_f64: negative count");
+    B2S_REQUIRE((size_t)scans * beams == 0 || (ox && oy && cx && cy), "b2s_mapping_update_f64: null pointer");
+    HostBatch hb = {false, true, ox, oy, cx, cy, nullptr, nullptr, nullptr, 0.0, nullptr};
     return mapping_update_impl(m, hb, scans, beams, pmap_out);
 }
 
@@ -968,7 +980,18 @@ extern "C" int b2s_mapping_update_incremental(b2s_mapping *m, const float *ox, c
     B2S_REQUIRE(m && pmap_inout, "b2s_mapping_update_incremental: null pointer");
     B2S_REQUIRE(scans >= 0 && beams >= 0 && tiles_cap >= 0, "b2s_mapping_update_incremental: negative count");
     B2S_REQUIRE((size_t)scans * beams == 0 || (ox && oy && cx && cy), "b2s_mapping_update_incremental: null pointer");
-    HostBatch hb = {false, ox, oy, cx, cy, nullptr, nullptr, nullptr, 0.0, nullptr};
+    HostBatch hb = {false, false, ox, oy, cx, cy, nullptr, nullptr, nullptr, 0.0, nullptr};
+    return mapping_update_impl(m, hb, scans, beams, pmap_inout, true, tiles_out, tiles_cap, tiles_count);
+}
+
+extern "C" int b2s_mapping_update_incremental_f64(b2s_mapping *m, const double *ox, const double *oy, const double *cx,
+                                                  const double *cy, int scans, int beams, int8_t *pmap_inout,
+                                                  int32_t *tiles_out, int tiles_cap, int *tiles_count)
+{
+    B2S_REQUIRE(m && pmap_inout, "b2s_mapping_update_incremental_f64: null pointer");
+    B2S_REQUIRE(scans >= 0 && beams >= 0 && tiles_cap >= 0, "b2s_mapping_update_incremental_f64: negative count");
+    B2S_REQUIRE((size_t)scans * beams == 0 || (ox && oy && cx && cy), "b2s_mapping_update_incremental_f64: null pointer");
+    HostBatch hb = {false, true, ox, oy, cx, cy, nullptr, nullptr, nullptr, 0.0, nullptr};
     return mapping_update_impl(m, hb, scans, beams, pmap_inout, true, tiles_out, tiles_cap, tiles_count);
 }
 
@@ -979,7 +1002,7 @@ extern "C" int b2s_mapping_update_ranges(b2s_mapping *m, const float *ranges, co
     B2S_REQUIRE(m, "b2s_mapping_update_ranges: null handle");
     B2S_REQUIRE(scans >= 0 && beams >= 0, "b2s_mapping_update_ranges: negative count");
     B2S_REQUIRE((size_t)scans * beams == 0 || (ranges && pose4 && beam_cs), "b2s_mapping_update_ranges: null pointer");
-    HostBatch hb = {true, nullptr, nullptr, nullptr, nullptr, ranges, pose4, beam_cs, clamp_inf_to, nullptr};
+    HostBatch hb = {true, false, nullptr, nullptr, nullptr, nullptr, ranges, pose4, beam_cs, clamp_inf_to, nullptr};
     return mapping_update_impl(m, hb, scans, beams, pmap_out);
 }
 
@@ -990,7 +1013,7 @@ extern "C" int b2s_mapping_update_scans(b2s_mapping *m, const float *ranges, con
     B2S_REQUIRE(m, "b2s_mapping_update_scans: null handle");
     B2S_REQUIRE(scans >= 0 && beams >= 0, "b2s_mapping_update_scans: negative count");
     B2S_REQUIRE((size_t)scans * beams == 0 || (ranges && poses3 && beam_cs), "b2s_mapping_update_scans: null pointer");
-    HostBatch hb = {true, nullptr, nullptr, nullptr, nullptr, ranges, nullptr, beam_cs, clamp_inf_to, poses3};
+    HostBatch hb = {true, false, nullptr, nullptr, nullptr, nullptr, ranges, nullptr, beam_cs, clamp_inf_to, poses3};
     return mapping_update_impl(m, hb, scans, beams, pmap_out);
 }
 

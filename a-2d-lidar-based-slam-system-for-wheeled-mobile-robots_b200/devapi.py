@@ -55,14 +55,19 @@ def new_workspace(xw, yw, device=None):
 
 
 def grid_raycast(hit, miss, cells_per_m, off_x, off_y, ox, oy, cx, cy, counters=None, workspace=None):
-    """b2s_grid_raycast[_ws]: hit/miss int32 (xw,yw); ox, oy float32 (K,N); cx, cy float32 (K,)."""
+    """b2s_grid_raycast_ws[_f64]: hit/miss int32 (xw,yw); ox, oy (K,N); cx, cy (K,), all float32 or all float64
+    (float64 is what the reference's Mapping.update evaluates the cell transform on)."""
     xw, yw = hit.shape
     K, N = ox.shape
-    rc = _lib.lib().b2s_grid_raycast_ws(
+    dt = ox.dtype
+    if dt not in (torch.float32, torch.float64):
+        raise ValueError("ox must be float32 or float64")
+    fn = _lib.lib().b2s_grid_raycast_ws if dt == torch.float32 else _lib.lib().b2s_grid_raycast_ws_f64
+    rc = fn(
         _chk(hit, torch.int32, "hit"), _chk(miss, torch.int32, "miss"), xw, yw,
         float(cells_per_m), float(off_x), float(off_y),
-        _chk(ox, torch.float32, "ox"), _chk(oy, torch.float32, "oy"),
-        _chk(cx, torch.float32, "cx"), _chk(cy, torch.float32, "cy"), K, N,
+        _chk(ox, dt, "ox"), _chk(oy, dt, "oy"),
+        _chk(cx, dt, "cx"), _chk(cy, dt, "cy"), K, N,
         None if counters is None else _chk(counters, torch.int32, "counters"),
         None if workspace is None else _chk(workspace, torch.int32, "workspace"), _stream())
     _lib.check(rc)

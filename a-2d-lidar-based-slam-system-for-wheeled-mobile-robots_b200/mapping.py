@@ -73,19 +73,21 @@ class Mapping(object):
         """[MAP]:22-51.  ox, oy (N,) world-frame endpoints, center_* scalar (or 1-element array,
         as slam_ekf.py:90 passes).  Returns the (xw, yw) float64 occupancy in {0, 50, 100}.
 
-        Raises ValueError / OverflowError on NaN / inf where the reference's int() does
-        (infinite ox alone is skipped, [MAP]:30) -- but before any beam is applied.
+        Coordinates cross the boundary as float64, the dtype the reference evaluates int(10*(v+10)) on
+        ([MAP]:33-36; slam_ekf.py:89-90 passes float64 obs and xEst), so a coordinate on or next to a cell
+        boundary lands in the reference's cell.  Raises ValueError / OverflowError on NaN / inf where the
+        reference's int() does (infinite ox alone is skipped, [MAP]:30) -- but before any beam is applied.
         """
-        ox = np.ascontiguousarray(np.asarray(ox, dtype=np.float32).reshape(1, -1))
-        oy = np.ascontiguousarray(np.asarray(oy, dtype=np.float32).reshape(1, -1))
-        cx = np.asarray(center_x, dtype=np.float32).reshape(-1)[:1].copy()
-        cy = np.asarray(center_y, dtype=np.float32).reshape(-1)[:1].copy()
+        ox = np.ascontiguousarray(np.asarray(ox, dtype=np.float64).reshape(1, -1))
+        oy = np.ascontiguousarray(np.asarray(oy, dtype=np.float64).reshape(1, -1))
+        cx = np.asarray(center_x, dtype=np.float64).reshape(-1)[:1].copy()
+        cy = np.asarray(center_y, dtype=np.float64).reshape(-1)[:1].copy()
         if ox.shape != oy.shape:
             raise ValueError("ox and oy differ in length: %s vs %s" % (ox.shape, oy.shape))
         # incremental read-back: only the 64 x 64-cell tiles this scan touched cross PCIe and are patched
         # into the host maps, so the call costs the same on a 4096^2 map as on the reference's 200^2
         count = ctypes.c_int(-1)
-        rc = self._L.b2s_mapping_update_incremental(
+        rc = self._L.b2s_mapping_update_incremental_f64(
             self._h, _lib.ptr(ox), _lib.ptr(oy), _lib.ptr(cx), _lib.ptr(cy), 1, ox.shape[1], _lib.ptr(self._pmap8),
             _lib.ptr(self._tiles), self._tiles.shape[0], ctypes.byref(count))
         self._raise_nonfinite(rc)
@@ -111,22 +113,30 @@ class Mapping(object):
     # ------------------------------------------------------------------ batched entry points
 
     def update_batch(self, ox, oy, cx, cy, want_pmap=True):
-        """K scans at once: ox, oy (K,N); cx, cy (K,).  Coordinates are consumed as float32.
+        """K scans at once: ox, oy (K,N); cx, cy (K,).
+
+        The coordinates are consumed in the dtype they arrive in: float32 arrays (all four) take the
+        float32 entry point -- half the bytes over PCIe, exact because float32 -> float64 is -- and anything
+        else is carried as float64, which is what [MAP]:33-36 evaluates int(10*(v+10)) on; the result is
+        then bit-identical to K reference update() calls on the same arrays.
 
         Returns the refreshed occupancy as int8 (xw, yw) in {0, 50, 100} (a view of the object's
         host buffer, overwritten by the next call), or None with want_pmap=False."""
-        ox = np.ascontiguousarray(ox, dtype=np.float32)
-        oy = np.ascontiguousarray(oy, dtype=np.float32)
-        cx = np.ascontiguousarray(cx, dtype=np.float32).reshape(-1)
-        cy = np.ascontiguousarray(cy, dtype=np.float32).reshape(-1)
+        f32 = all(getattr(a, "dtype", None) == np.float32 for a in (ox, oy, cx, cy))
+        dt = np.float32 if f32 else np.float64
+        ox = np.ascontiguousarray(ox, dtype=dt)
+        oy = np.ascontiguousarray(oy, dtype=dt)
+        cx = np.ascontiguousarray(cx, dtype=dt).reshape(-1)
+        cy = np.ascontiguousarray(cy, dtype=dt).reshape(-1)
         if ox.ndim != 2 or ox.shape != oy.shape or cx.shape[0] != ox.shape[0] \
                 or cy.shape[0] != ox.shape[0]:
             raise ValueError("expected ox, oy (K,N) and cx, cy (K,), got %s %s %s %s"
                              % (ox.shape, oy.shape, cx.shape, cy.shape))
         out = self._pmap8 if want_pmap else None
         self._pmap64 = None
-        rc = self._L.b2s_mapping_update(self._h, _lib.ptr(ox), _lib.ptr(oy), _lib.ptr(cx),
-                                        _lib.ptr(cy), ox.shape[0], ox.shape[1], _lib.ptr(out))
+        call = self._L.b2s_mapping_update if f32 else self._L.b2s_mapping_update_f64
+        rc = call(self._h, _lib.ptr(ox), _lib.ptr(oy), _lib.ptr(cx), _lib.ptr(cy), ox.shape[0], ox.shape[1],
+                  _lib.ptr(out))
         self._raise_nonfinite(rc)
         _lib.check(rc)
         if want_pmap:

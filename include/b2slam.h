@@ -51,10 +51,13 @@ int b2s_version(void);
 const char *b2s_status_string(int status);
 const char *b2s_last_error(void); /* thread-local, valid until the next call on this thread */
 int b2s_device_count(int *count);
-/* Kernel-variant switch for benchmarking (key "grid_variant": 1 = one RED per visit, 2 = warp-
- * aggregated runs, 3 = lean loop, 4 = transposed scratch plane, the default; "icp_prune" 0/1,
- * "icp_block" 0/16/32, "icp_src_per_thread" 0/2/3/4, "h2d_chunks" 0..8).  Not part of the reference
- * surface; process-global, set it before the calls it should affect. */
+/* Kernel-variant switch for benchmarking.  Keys: "grid_variant" 1 = one RED per visit, 2 = warp-aggregated
+ * runs, 3 = lean loop, 4 = transposed scratch plane (default); "icp_prune" 0 = brute force, 1 = per-lane
+ * block pruning, 2 = warp-level + per-lane (default), 3 = warp-level only; "icp_block" 0 (automatic) / 8 /
+ * 16 / 32 targets per pruning block; "icp_src_per_thread" 0 (automatic) / 2 / 3 / 4; "icp_graph" 0 / 1
+ * (single-pair calls replay a captured CUDA graph); "h2d_chunks" 0 (automatic) .. 16 pipeline depth of the
+ * host-buffer calls.  Not part of the reference surface; process-global, set it before the calls it should
+ * affect (cached single-pair graphs are re-captured after a change). */
 int b2s_tune(const char *key, int value);
 /* Same-run FP64 FMA issue peak of the current device in TFLOP/s (8 independent DFMA chains per thread);
  * bench.py quotes the ICP kernel against it.  Not part of the reference surface. */
@@ -100,6 +103,15 @@ int b2s_grid_raycast(int32_t *hit, int32_t *miss, int xw, int yw, double cells_p
                      const float *cx, const float *cy, int scans, int beams, int32_t *counters,
                      void *stream);
 
+/* The same update on float64 endpoints and sensor positions -- the dtype the reference's callers pass
+ * ([SLAM]:89-90: obs = u2T(xEst).dot(np_msg) and xEst are float64, and [MAP]:33-36 applies int() to the
+ * float64 value).  Nothing is narrowed before the cell transform, so a coordinate on or next to a cell
+ * boundary lands in the reference's cell; float32 input upcast to float64 gives the float32 entry point's result. */
+int b2s_grid_raycast_f64(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m,
+                         double off_x, double off_y, const double *ox, const double *oy,
+                         const double *cx, const double *cy, int scans, int beams, int32_t *counters,
+                         void *stream);
+
 /* Same update with a caller-provided workspace, which enables the fastest kernel: y-major beams
  * accumulate into a transposed scratch plane inside the workspace (so that the 32 beams of a warp
  * touch consecutive words in either orientation) and a transpose-add folds it into `miss` before the
@@ -113,6 +125,11 @@ int b2s_grid_raycast_ws(int32_t *hit, int32_t *miss, int xw, int yw, double cell
                         double off_x, double off_y, const float *ox, const float *oy,
                         const float *cx, const float *cy, int scans, int beams, int32_t *counters,
                         void *workspace, void *stream);
+
+int b2s_grid_raycast_ws_f64(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m,
+                            double off_x, double off_y, const double *ox, const double *oy,
+                            const double *cx, const double *cy, int scans, int beams,
+                            int32_t *counters, void *workspace, void *stream);
 
 /* Fused scan ingestion -- replaces laserToNumpy ([SLAM]:115-123), u2T(xEst).dot(np_msg) ([SLAM]:130-137,89)
  * and Mapping.update ([MAP]:22-51) in one kernel: raw ranges [scans][beams] float32 and, per scan,
@@ -131,6 +148,9 @@ int b2s_grid_raycast_ranges(int32_t *hit, int32_t *miss, int xw, int yw, double 
  * OverflowError); ox = +-inf alone is legal ([MAP]:30).  flags: device int32[2], caller-zeroed. */
 int b2s_grid_validate(const float *ox, const float *oy, const float *cx, const float *cy, int scans,
                       int beams, int32_t *flags, void *stream);
+
+int b2s_grid_validate_f64(const double *ox, const double *oy, const double *cx, const double *cy, int scans,
+                          int beams, int32_t *flags, void *stream);
 
 /* Evidence score and occupancy from the counts -- replaces the per-visit rule of [MAP]:42-50
  * (w_hit 20) / [MAPO]:43-51 (w_hit 4): datamap = w_miss*miss + w_hit*hit (float32 out),
@@ -253,11 +273,18 @@ int b2s_mapping_create(b2s_mapping **out, int xw, int yw, double xyreso, double 
                        double w_miss, double thresh, int device);
 int b2s_mapping_destroy(b2s_mapping *map);
 int b2s_mapping_reset(b2s_mapping *map);
-/* Mapping.update -- [MAP]:22-51 for `scans` scans at once.  Validates like the reference
- * (B2S_ERR_NONFINITE where int() would raise) BEFORE touching the planes; when pmap_out is
- * not NULL it receives the refreshed occupancy [xw][yw]. */
+/* Mapping.update -- [MAP]:22-51 for `scans` scans at once, all-or-nothing: a batch holding a coordinate the
+ * reference's int() raises on (B2S_ERR_NONFINITE) or an over-long beam (B2S_ERR_TOO_LONG) leaves the planes
+ * as they were.  The chunks are applied while the later ones still cross PCIe (the kernels skip and count
+ * the offending beams); a rejected batch is then taken back out with the sign -1 kernel, which is exact on
+ * integer counts.  When pmap_out is not NULL it receives the refreshed occupancy [xw][yw].
+ * b2s_mapping_update consumes float32 coordinates (the fast path: half the bytes over PCIe);
+ * b2s_mapping_update_f64 consumes the float64 the reference's callers pass and is the form that is
+ * bit-identical to [MAP]:33-36 on any input. */
 int b2s_mapping_update(b2s_mapping *map, const float *ox, const float *oy, const float *cx,
                        const float *cy, int scans, int beams, int8_t *pmap_out);
+int b2s_mapping_update_f64(b2s_mapping *map, const double *ox, const double *oy, const double *cx,
+                           const double *cy, int scans, int beams, int8_t *pmap_out);
 /* Mapping.update with an incremental read-back: pmap_inout must still hold the map written by the previous
  * call on this object (any of the update calls with a map pointer); only the 64 x 64-cell tiles this batch
  * touched are finalized, copied and patched into it, so a single scan on a large map costs microseconds
@@ -267,6 +294,9 @@ int b2s_mapping_update(b2s_mapping *map, const float *ox, const float *oy, const
 int b2s_mapping_update_incremental(b2s_mapping *map, const float *ox, const float *oy, const float *cx,
                                    const float *cy, int scans, int beams, int8_t *pmap_inout,
                                    int32_t *tiles_out, int tiles_cap, int *tiles_count);
+int b2s_mapping_update_incremental_f64(b2s_mapping *map, const double *ox, const double *oy, const double *cx,
+                                       const double *cy, int scans, int beams, int8_t *pmap_inout,
+                                       int32_t *tiles_out, int tiles_cap, int *tiles_count);
 /* The same for raw scans (fused ingestion, see b2s_grid_raycast_ranges): ranges [scans][beams], pose4
  * [scans][4], beam_cs [beams][2] on the host. */
 int b2s_mapping_update_ranges(b2s_mapping *map, const float *ranges, const double *pose4,

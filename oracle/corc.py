@@ -34,6 +34,8 @@ def lib():
         L.orc_bresenham.restype = i64
         L.orc_grid_raycast.argtypes = [vp, vp, i32, i32, dbl, dbl, dbl, vp, vp, vp, vp, i32, i32]
         L.orc_grid_raycast.restype = i64
+        L.orc_grid_raycast_f64.argtypes = [vp, vp, i32, i32, dbl, dbl, dbl, vp, vp, vp, vp, i32, i32]
+        L.orc_grid_raycast_f64.restype = i64
         L.orc_grid_raycast_ranges.argtypes = [vp, vp, i32, i32, dbl, dbl, dbl, vp, vp, vp, dbl, i32, i32]
         L.orc_grid_raycast_ranges.restype = i64
         L.orc_grid_finalize.argtypes = [vp, vp, i64, dbl, dbl, dbl, vp, vp]
@@ -85,9 +87,22 @@ def bresenham(start, end):
 
 
 def grid_raycast(hit, miss, cells_per_m, off_x, off_y, ox, oy, cx, cy):
-    """In-place integer update of hit/miss int32 (xw,yw); ox, oy (K,N); cx, cy (K,). Returns visits."""
+    """In-place integer update of hit/miss int32 (xw,yw); ox, oy (K,N); cx, cy (K,). Returns visits.
+    float32 arrays go through the float32 entry (upcast exactly); anything else is consumed as float64,
+    like the reference consumes it ([MAP]:33-36)."""
     assert hit.dtype == np.int32 and miss.dtype == np.int32
     assert hit.flags.c_contiguous and miss.flags.c_contiguous
+    if not all(np.asarray(a).dtype == np.float32 for a in (ox, oy, cx, cy)):
+        ox = np.ascontiguousarray(np.atleast_2d(ox), dtype=np.float64)
+        oy = np.ascontiguousarray(np.atleast_2d(oy), dtype=np.float64)
+        cx = np.ascontiguousarray(np.atleast_1d(cx), dtype=np.float64)
+        cy = np.ascontiguousarray(np.atleast_1d(cy), dtype=np.float64)
+        K, N = ox.shape
+        v = lib().orc_grid_raycast_f64(_p(hit), _p(miss), hit.shape[0], hit.shape[1], float(cells_per_m),
+                                       float(off_x), float(off_y), _p(ox), _p(oy), _p(cx), _p(cy), K, N)
+        if v < 0:
+            raise ValueError("non-finite coordinate")
+        return int(v)
     ox = np.ascontiguousarray(np.atleast_2d(ox), dtype=np.float32)
     oy = np.ascontiguousarray(np.atleast_2d(oy), dtype=np.float32)
     cx = np.ascontiguousarray(np.atleast_1d(cx), dtype=np.float32)

@@ -229,6 +229,70 @@ def mapping_golden():
     np.savez_compressed(os.path.join(OUT, "mapping.npz"), **blob)
 
 
+def _sparse(datamap, pmap):
+    """Non-zero cells of the reference's datamap (flat [x][y] indices), their scores and occupancies."""
+    idx = np.flatnonzero(np.asarray(datamap).reshape(-1))
+    return idx.astype(np.int64), np.asarray(datamap).reshape(-1)[idx], np.asarray(pmap).reshape(-1)[idx].astype(np.int8)
+
+
+def mapping_f64_golden():
+    """(v-f64) Mapping.update fed what slam_ekf.py:89-90 feeds it: UNROUNDED float64 endpoints and sensor
+    positions, at three grid scales.  The reference hard-codes int(10*(v+10)) ([MAP]:33-36), so on the larger
+    grids the world simply extends to 10*(v+10) < xw: coordinates up to ~400 m (4096^2) and ~1628 m (16384^2),
+    where a float32 narrowing of the coordinate moves the cell of roughly one beam in 10^4 / 10^3."""
+    blob = {}
+    for tag, side, span, scans, beams, seed in (("g200", 200, 19.0, 8, 160, 8501), ("g4096", 4096, 405.0, 6, 200, 8502),
+                                                ("g16384", 16384, 1630.0, 6, 200, 8503)):
+        rng = np.random.Generator(np.random.PCG64(seed))
+        Mapping, _ = ref_loader.load_mapping_classes()
+        MappingO, _ = ref_loader.load_mapping_online_classes()
+        m, mo = Mapping(side, side, 0.1), (MappingO(side, side, 0.1) if side == 200 else None)
+        oxs, oys, cxs, cys = [], [], [], []
+        for k in range(scans):
+            # sensor somewhere in the (extended) world, not float32-representable
+            cx = float(rng.uniform(-9.5, span - 10.5))
+            cy = float(rng.uniform(-9.5, span - 10.5))
+            if k == 1:
+                cx, cy = 0.30000000000000004, 0.7                  # 0.1 + 0.2; 10*(0.7+10) = 106.99999999999999
+            ang = np.linspace(-np.pi, np.pi, beams)
+            r = rng.uniform(0.3, 28.0, size=beams)
+            ox = cx + r * np.cos(ang)
+            oy = cy + r * np.sin(ang)
+            # endpoints exactly on the decimal cell boundaries: k/10 is not a binary fraction, and 10*(k/10+10)
+            # falls on either side of the integer (9.9 -> 198.99999999999997 -> cell 198, not 199)
+            nb = beams // 4
+            ticks = np.round(np.clip(cx + rng.uniform(-25, 25, size=nb), -9.9, span - 10.1), 1)
+            ox[:nb] = ticks
+            oy[:nb] = np.round(cy + rng.uniform(-20, 20, size=nb), 1)
+            # one ulp either side of a boundary
+            ox[nb] = np.nextafter(np.round(cx + 3.0, 1), np.inf)
+            ox[nb + 1] = np.nextafter(np.round(cx + 3.0, 1), -np.inf)
+            ox[nb + 2], oy[nb + 2] = np.inf, cy                      # skipped ([MAP]:30)
+            ox[nb + 3], oy[nb + 3] = cx + 1e-9, cy - 1e-9            # same cell: no update
+            ox[nb + 4], oy[nb + 4] = -10.05, cy                      # truncation toward zero -> cell 0
+            ox[nb + 5], oy[nb + 5] = cx, span + 50.0                 # leaves the grid: clipped, no hit
+            pm = m.update(ox, oy, cx, cy)
+            if mo is not None:
+                pmo = mo.update(ox, oy, cx, cy)
+            oxs.append(ox); oys.append(oy); cxs.append(cx); cys.append(cy)
+        blob[tag + "_ox"], blob[tag + "_oy"] = np.array(oxs), np.array(oys)
+        blob[tag + "_cx"], blob[tag + "_cy"] = np.array(cxs), np.array(cys)
+        blob[tag + "_side"] = side
+        blob[tag + "_cells"], blob[tag + "_score"], blob[tag + "_pmap"] = _sparse(m.datamap, pm)
+        if mo is not None:
+            blob[tag + "_cells_w4"], blob[tag + "_score_w4"], blob[tag + "_pmap_w4"] = _sparse(mo.datamap, pmo)
+        # how many cells of these very scans move when the coordinates are narrowed to float32 first (informational)
+        f = lambda v: np.trunc(10 * (np.asarray(v, dtype=np.float64) + 10))
+        g = lambda v: np.trunc(10 * (np.asarray(v, dtype=np.float32).astype(np.float64) + 10))
+        fin = np.isfinite(blob[tag + "_ox"])
+        moved = int(((f(blob[tag + "_ox"][fin]) != g(blob[tag + "_ox"][fin])) | (f(blob[tag + "_oy"][fin]) != g(blob[tag + "_oy"][fin]))).sum())
+        blob[tag + "_moved_by_f32"] = moved
+        print("mapping f64 %s: %d touched cells, %d endpoints would move under float32 narrowing" % (
+            tag, len(blob[tag + "_cells"]), moved))
+        del m, mo
+    np.savez_compressed(os.path.join(OUT, "mapping_f64.npz"), **blob)
+
+
 class _Scan(object):
     """Duck-typed sensor_msgs/LaserScan."""
 
@@ -270,6 +334,12 @@ def main():
     if not ref_loader.available():
         raise SystemExit("reference tree not found at %s" % ref_loader.REF_ROOT)
     os.makedirs(OUT, exist_ok=True)
+    only = sys.argv[1:]
+    if only:                      # python oracle/make_golden.py mapping_f64_golden ...
+        for name in only:
+            globals()[name]()
+        return
+    mapping_f64_golden()
     ingestion_golden()
     bresenham_golden()
     nearest_and_fit_golden()

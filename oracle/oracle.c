@@ -251,6 +251,23 @@ int64_t orc_grid_raycast(int32_t *hit, int32_t *miss, int xw, int yw, double cel
     return visits;
 }
 
+/* The same on float64 endpoints / sensor positions: the dtype [MAP]:22-51 is called with by slam_ekf.py:89-90
+ * (obs and xEst are float64), so int(10*(v+10)) sees the unrounded value. */
+int64_t orc_grid_raycast_f64(int32_t *hit, int32_t *miss, int xw, int yw, double cells_per_m,
+                             double off_x, double off_y, const double *ox, const double *oy,
+                             const double *cx, const double *cy, int scans, int beams)
+{
+    int64_t visits = 0;
+    for (int s = 0; s < scans; ++s) {
+        const double fcx = cx[s], fcy = cy[s];
+        for (int b = 0; b < beams; ++b)
+            if (raycast_beam(hit, miss, xw, yw, cells_per_m, off_x, off_y, ox[(size_t)s * beams + b],
+                             oy[(size_t)s * beams + b], fcx, fcy, &visits))
+                return -1;
+    }
+    return visits;
+}
+
 /* Raw scans: laserToNumpy (slam_ekf.py:115-123) + u2T(xEst).dot(np_msg) (slam_ekf.py:130-137,89) + the update,
  * per beam in float64, products and sums rounded separately, left to right.  pose4 [scans][4] = x, y,
  * cos(yaw), sin(yaw); beam_cs [beams][2] = cos, sin of the beam angle; clamp > 0 replaces +inf ranges. */

@@ -60,9 +60,8 @@ def test_node_flow_through_the_dropin_modules():
         state = pyref.compose_pose(state, T)                                                  # odometry only (no EKF here)
         obs = scan.u2T(np.array(state)).dot(np_msg)                                           # [SLAM]:89
         pmap = mapping.update(obs[0], obs[1], np.array([state[0]]), np.array([state[1]]))     # [SLAM]:90 (1-element arrays)
-        o32 = obs.astype(np.float32).astype(np.float64)        # the boundary consumes coordinates as float32
-        c32 = np.array(state[:2], dtype=np.float32).astype(np.float64)
-        pyref.grid_update_evidence(datamap, pmap_ref, o32[0], o32[1], c32[0], c32[1], 10.0, 10.0, 10.0)
+        # float64 straight through, as the reference consumes it ([MAP]:33-36): nothing is rounded on either side
+        pyref.grid_update_evidence(datamap, pmap_ref, obs[0], obs[1], state[0], state[1], 10.0, 10.0, 10.0)
         assert np.array_equal(pmap, pmap_ref), k
         data = np.trunc(np.asarray(list(pmap.T.reshape(-1)))).astype(np.int8)                 # publishMap, [SLAM]:270-271
         assert data.shape == (40000,) and set(np.unique(data)) <= {0, 50, 100}

@@ -145,6 +145,47 @@ def test_mapping_counts_reproduce_reference_maps(tag, w_hit):
         assert not ambiguous.any() and np.array_equal(pmap, z[tag + "_pmap"])
 
 
+def _score_from_counts(hit, miss, cells, w_hit):
+    return 0.01 * miss.reshape(-1)[cells].astype(np.float64) + w_hit * hit.reshape(-1)[cells].astype(np.float64)
+
+
+@pytest.mark.parametrize("tag", ["g200", "g4096", "g16384"])
+def test_mapping_float64_inputs_reproduce_reference(tag):
+    """The reference fed UNROUNDED float64 endpoints / sensor positions (what slam_ekf.py:89-90 passes), at three
+    grid scales, incl. endpoints exactly on decimal cell boundaries: the float64 oracle touches exactly the
+    reference's cells with the reference's evidence; narrowing the inputs to float32 first does not."""
+    z = load_golden("mapping_f64.npz")
+    side = int(z[tag + "_side"])
+    hit = np.zeros((side, side), dtype=np.int32)
+    miss = np.zeros((side, side), dtype=np.int32)
+    corc.grid_raycast(hit, miss, 10.0, 10.0, 10.0, z[tag + "_ox"], z[tag + "_oy"], z[tag + "_cx"], z[tag + "_cy"])
+    cells = z[tag + "_cells"]
+    touched = np.flatnonzero((hit.reshape(-1) != 0) | (miss.reshape(-1) != 0))
+    assert np.array_equal(touched, cells)
+    np.testing.assert_allclose(_score_from_counts(hit, miss, cells, 20.0), z[tag + "_score"], rtol=1e-12, atol=0)
+    h, m = hit.reshape(-1)[cells], miss.reshape(-1)[cells]
+    pm = np.where(0.01 * m + 20.0 * h > 10.0, 100, 0).astype(np.int8)
+    assert np.array_equal(pm, z[tag + "_pmap"])
+    if tag == "g200":
+        cw = z[tag + "_cells_w4"]
+        assert np.array_equal(cw, cells)
+        np.testing.assert_allclose(_score_from_counts(hit, miss, cw, 4.0), z[tag + "_score_w4"], rtol=1e-12, atol=0)
+        # the literal port agrees scan by scan on the small map
+        h2 = np.zeros((side, side), dtype=np.int32)
+        m2 = np.zeros((side, side), dtype=np.int32)
+        for ox, oy, cx, cy in zip(z[tag + "_ox"], z[tag + "_oy"], z[tag + "_cx"], z[tag + "_cy"]):
+            pyref.grid_update_counts(h2, m2, ox, oy, float(cx), float(cy), 10.0, 10.0, 10.0)
+        assert np.array_equal(h2, hit) and np.array_equal(m2, miss)
+    # float32 narrowing is NOT the reference: these very scans land in other cells
+    assert int(z[tag + "_moved_by_f32"]) > 0
+    h32 = np.zeros((side, side), dtype=np.int32)
+    m32 = np.zeros((side, side), dtype=np.int32)
+    fin = np.where(np.isfinite(z[tag + "_ox"]), z[tag + "_ox"], 0.0)
+    corc.grid_raycast(h32, m32, 10.0, 10.0, 10.0, fin.astype(np.float32), z[tag + "_oy"].astype(np.float32),
+                      z[tag + "_cx"].astype(np.float32), z[tag + "_cy"].astype(np.float32))
+    assert not (np.array_equal(h32, hit) and np.array_equal(m32, miss))
+
+
 def test_miss_stream_threshold_matches_reference():
     z = load_golden("mapping.npz")
     for m, score, pm in zip(z["miss_stream_counts"], z["miss_stream_score"], z["miss_stream_pmap"]):

@@ -40,6 +40,26 @@ def test_reference_mapping_equals_oracle_counts(loader, w_hit):
         assert np.array_equal(pmap, np.asarray(pm).astype(np.int8))
 
 
+def test_reference_mapping_on_unrounded_float64_equals_oracle():
+    """Fresh float64 coordinates (never rounded to float32), incl. decimal cell boundaries, through the unmodified
+    reference and the float64 oracle entry."""
+    Mapping, _ = ref_loader.load_mapping_classes()
+    ref = Mapping(200, 200, 0.1)
+    rng = np.random.Generator(np.random.PCG64(20260001))
+    hit = np.zeros((200, 200), dtype=np.int32)
+    miss = np.zeros((200, 200), dtype=np.int32)
+    for k in range(5):
+        cx, cy = rng.uniform(-9, 9, size=2)
+        ox = np.concatenate([np.round(rng.uniform(-9.9, 9.9, 60), 1), rng.uniform(-12, 12, 60)])
+        oy = np.concatenate([np.round(rng.uniform(-9.9, 9.9, 60), 1), rng.uniform(-12, 12, 60)])
+        pm = ref.update(ox, oy, cx, cy)
+        corc.grid_raycast(hit, miss, 10.0, 10.0, 10.0, ox[None], oy[None], [cx], [cy])
+    score, pmap = corc.grid_finalize(hit, miss, 20.0)
+    np.testing.assert_allclose(score, ref.datamap, rtol=1e-12, atol=0)
+    assert np.array_equal((hit + miss) > 0, np.asarray(ref.datamap) > 0)
+    assert np.array_equal(pmap, np.asarray(pm).astype(np.int8))
+
+
 def test_reference_icp_equals_oracle_on_fresh_pairs():
     tar, src, _ = synth.icp_pairs(99001, 3, 120)
     for p in range(3):
