@@ -42,6 +42,7 @@ extern int g_icp_prune;
 extern int g_icp_block;
 int g_icp_graph = 1;  // 1: single-pair ICP calls replay a captured CUDA graph (default); 0: plain stream calls (tuning hook)
 constexpr int MAX_CHUNKS = 16;
+int g_tune_gen = 0;    // bumped by every b2s_tune: cached single-pair graphs captured under other settings are stale
 int g_h2d_chunks = 0;  // 0: automatic; 1..MAX_CHUNKS force the pipeline depth of the host-buffer calls (tuning hook)
 
 // Growable device / pinned-host staging buffer.
@@ -162,7 +163,7 @@ struct b2s_icp {
     Buf h_one;  // pinned staging: [tar][src][T (9 doubles)][iterations]
     cudaGraphExec_t one_exec;
     struct {
-        int is_f64, n_src, n_tar, max_iter;
+        int is_f64, n_src, n_tar, max_iter, tune_gen;
         double tol;
         void *d_tar, *d_src, *d_T, *d_iters, *h;
     } one_key;
@@ -217,6 +218,7 @@ extern "C" int b2s_device_count(int *count)
 extern "C" int b2s_tune(const char *key, int value)
 {
     B2S_REQUIRE(key, "b2s_tune: null key");
+    ++g_tune_gen;
     if (strcmp(key, "grid_variant") == 0) {
         B2S_REQUIRE(value >= 1 && value <= 4, "b2s_tune: grid_variant must be 1..4");
         g_grid_variant = value;
@@ -347,7 +349,7 @@ static int icp_process_one_graph(b2s_icp *c, const void *tar_xy, const void *src
     memcpy(h_tar, tar_xy, (size_t)2 * n_tar * el);
     memcpy(h_src, src_xy, (size_t)2 * n_src * el);
     auto &k = c->one_key;
-    const bool hit = c->one_exec && k.is_f64 == is_f64 && k.n_src == n_src && k.n_tar == n_tar && k.max_iter == max_iter &&
+    const bool hit = c->one_exec && k.tune_gen == g_tune_gen && k.is_f64 == is_f64 && k.n_src == n_src && k.n_tar == n_tar && k.max_iter == max_iter &&
                      k.tol == tol && k.d_tar == c->d_tar.p && k.d_src == c->d_src.p && k.d_T == c->d_T.p &&
                      k.d_iters == c->d_iters.p && k.h == c->h_one.p;
     if (!hit) {
@@ -382,6 +384,7 @@ static int icp_process_one_graph(b2s_icp *c, const void *tar_xy, const void *src
             c->one_exec = nullptr;
             return cuda_fail(e, "b2s_icp_process: cudaGraphInstantiate");
         }
+        k.tune_gen = g_tune_gen;
         k.is_f64 = is_f64; k.n_src = n_src; k.n_tar = n_tar; k.max_iter = max_iter; k.tol = tol;
         k.d_tar = c->d_tar.p; k.d_src = c->d_src.p; k.d_T = c->d_T.p; k.d_iters = c->d_iters.p; k.h = c->h_one.p;
     }
@@ -1055,6 +1058,7 @@ extern "C" int b2s_mapping_write(b2s_mapping *m, const int32_t *hit, const int32
 extern "C" int b2s_mapping_planes(b2s_mapping *m, int32_t **hit, int32_t **miss, void **stream)
 {
     B2S_REQUIRE(m, "b2s_mapping_planes: null handle");
+    m->pmap_valid = false;  // the caller may change the planes behind the object's back: next read-back is a full one
     if (hit) *hit = m->hit;
     if (miss) *miss = m->miss;
     if (stream) *stream = (void *)m->stream;

@@ -28,16 +28,17 @@ nearest_kernel(const double *__restrict__ src_xy, int n, const double *__restric
             tile[j] = make_double2(tar_xy[2 * (size_t)(base + j)], tar_xy[2 * (size_t)(base + j) + 1]);
         __syncthreads();
         for (int j = 0; j < cnt; ++j) {
-            const double dx = sx - tile[j].x, dy = sy - tile[j].y;
-            const double d2 = fma(dy, dy, dx * dx);
-            if (d2 < best) {
-                best = d2;
+            // the reference's own expression ([ICP]:102: np.linalg.norm of the difference), square root included:
+            // sqrt merges neighbouring doubles, and the ties it creates go to the lower index
+            const double d = ref_dist(sx - tile[j].x, sy - tile[j].y);
+            if (d < best) {
+                best = d;
                 arg = base + j;
             }
         }
     }
     if (i < n) {
-        dist_out[i] = (best == INFINITY) ? 0.0 : sqrt(best);
+        dist_out[i] = (best == INFINITY) ? 0.0 : best;
         idx_out[i] = arg;
     }
 }

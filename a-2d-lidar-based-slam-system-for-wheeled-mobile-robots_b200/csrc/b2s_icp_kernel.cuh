@@ -171,6 +171,62 @@ __device__ __forceinline__ void cta_rigid_fit(const double (&ax)[R], const doubl
     extra = v[8];
 }
 
+// ---------------------------------------------------------------- the reference's distance and its ties
+//
+// findNearest orders candidates by np.linalg.norm(src[i] - tar[j]) with a strict '<' in ascending j ([ICP]:99-106).
+// NumPy evaluates that norm as sqrt(x.dot(x)), the dot product through the BLAS ddot whose scalar tail is contracted
+// to fma(x1, x1, x0 * x0) on every x86-64 FMA3 build -- pinned by running the unmodified reference on 10^4 near-tie
+// cases (tests/golden/icp_ties.npz; oracle/oracle.c: ref_norm2).  So the squared distance of the hot loop,
+// fma(dy, dy, dx * dx), IS the reference's radicand bit for bit; what an argmin over it still misses is that sqrt
+// merges neighbouring doubles: two candidates whose radicands differ in the last bits are a TIE for the reference
+// (lowest j wins).  The search therefore works in two tiers:
+//   * the hot loop compares only the HIGH 32 bits of the squared distance (non-negative doubles order like their
+//     bit patterns; NaN patterns are above +inf and never win), which decides every pair of candidates that differ
+//     by more than 2^-19 relative -- far outside anything a square root can merge -- and raises a flag whenever two
+//     compared values are within one unit of that word (an integer subtract + min, no FP64 issue slot);
+//   * a flagged source point (a few per 10^4) is re-done by the whole warp with the reference's own expression,
+//     square root included: ref_dist / warp_careful_nearest.
+__device__ __forceinline__ double ref_dist(double dx, double dy)
+{
+    return __dsqrt_rn(__fma_rn(dy, dy, __dmul_rn(dx, dx)));  // [ICP]:102
+}
+
+// Exhaustive search for ONE source point (px, py: warp-uniform) over all m targets by the reference's rule; the 32
+// lanes take every 32nd target and the partial winners are merged with "smaller distance, then lower index".
+static __device__ __noinline__ int warp_careful_nearest(double px, double py, const double2 *tar, int m, int lane)
+{
+    double bd = INFINITY;
+    int bj = 0;
+    for (int j = lane; j < m; j += 32) {
+        const double2 t = tar[j];
+        const double d = ref_dist(px - t.x, py - t.y);
+        if (d < bd) {
+            bd = d;
+            bj = j;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (od < bd || (od == bd && oj < bj)) {
+            bd = od;
+            bj = oj;
+        }
+    }
+    return bj;
+}
+
+// hi-word compare + near-tie flag of the hot loop
+#define B2S_NN_STEP(FH, BH, BJ, J, NEAR)                    \
+    do {                                                    \
+        NEAR |= ((FH) - (BH) + 1u) < 3u;                    \
+        if ((FH) < (BH)) {                                  \
+            BH = (FH);                                      \
+            BJ = (J);                                       \
+        }                                                   \
+    } while (0)
+
 // Targets per pruning block (NN_BLK): 8 is fastest at 360 beams, 16 at 1080 with the warp-level test in front
 // (16 / 32 with the per-lane test alone); chosen per launch, see launch_icp_r.
 
@@ -302,12 +358,26 @@ __global__ void __maxnreg__(R <= 3 ? 80 : 104) icp_batch_kernel(const TIn *__res
     int iters = 0;
     for (int it = 0; it < max_iter; ++it) {
         // ---- nearest neighbour ([ICP]:99-106)
-        double best[R];
+        const int lane_id = tid & 31;
+        // re-do flagged points (near ties: see ref_dist) with the reference's expression; warp-uniform
+        auto settle = [&](bool flagged, double px, double py, int &winner) {
+            unsigned need = __ballot_sync(0xffffffffu, flagged);
+            while (need) {
+                const int src_lane = __ffs(need) - 1;
+                need &= need - 1;
+                const double qx = __shfl_sync(0xffffffffu, px, src_lane), qy = __shfl_sync(0xffffffffu, py, src_lane);
+                const int j = warp_careful_nearest(qx, qy, tar, m, lane_id);
+                if (lane_id == src_lane) winner = j;
+            }
+        };
         if (!PRUNE) {
+            unsigned bh[R];
+            bool near[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                best[r] = INFINITY;
+                bh[r] = 0x7ff00000u;  // +inf
                 arg[r] = 0;
+                near[r] = false;
             }
 #pragma unroll 4
             for (int j = 0; j < m; ++j) {
@@ -315,13 +385,12 @@ __global__ void __maxnreg__(R <= 3 ? 80 : 104) icp_batch_kernel(const TIn *__res
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const double dx = sx[r] - t.x, dy = sy[r] - t.y;
-                    const double d2 = fma(dy, dy, dx * dx);
-                    if (d2 < best[r]) {
-                        best[r] = d2;
-                        arg[r] = j;
-                    }
+                    const unsigned fh = (unsigned)__double2hiint(fma(dy, dy, dx * dx));
+                    B2S_NN_STEP(fh, bh[r], arg[r], j, near[r]);
                 }
             }
+#pragma unroll
+            for (int r = 0; r < R; ++r) settle(near[r] && r < count, sx[r], sy[r], arg[r]);
         } else {
             // Exact search with pruning.  ANY target gives an upper bound ub on the nearest distance; a block
             // whose every point is provably farther than sqrt(ub) cannot contain the nearest point nor tie
@@ -351,11 +420,12 @@ __global__ void __maxnreg__(R <= 3 ? 80 : 104) icp_batch_kernel(const TIn *__res
                 // NN_CHAINS independent running minima (target j feeds chain j % NN_CHAINS) shorten the serial
                 // compare-select dependency; they are merged below with the lower index winning ties, which is
                 // what one ascending strict '<' scan gives.
-                double bst[NN_CHAINS];
+                unsigned bh[NN_CHAINS];  // high word of the chain's smallest squared distance
                 int bj[NN_CHAINS];
+                bool near = false;
 #pragma unroll
                 for (int q = 0; q < NN_CHAINS; ++q) {
-                    bst[q] = INFINITY;
+                    bh[q] = 0x7ff00000u;  // +inf
                     bj[q] = 0;
                 }
                 auto visit = [&](int b) {
@@ -365,21 +435,15 @@ __global__ void __maxnreg__(R <= 3 ? 80 : 104) icp_batch_kernel(const TIn *__res
                         for (int jj = 0; jj < NN_BLK; ++jj) {
                             const double2 t = tar[j0 + jj];
                             const double dx = px - t.x, dy = py - t.y;
-                            const double d2 = fma(dy, dy, dx * dx);
-                            if (d2 < bst[jj % NN_CHAINS]) {
-                                bst[jj % NN_CHAINS] = d2;
-                                bj[jj % NN_CHAINS] = j0 + jj;
-                            }
+                            const unsigned fh = (unsigned)__double2hiint(fma(dy, dy, dx * dx));
+                            B2S_NN_STEP(fh, bh[jj % NN_CHAINS], bj[jj % NN_CHAINS], j0 + jj, near);
                         }
                     } else {
                         for (int j = j0; j < m; ++j) {
                             const double2 t = tar[j];
                             const double dx = px - t.x, dy = py - t.y;
-                            const double d2 = fma(dy, dy, dx * dx);
-                            if (d2 < bst[0] || (d2 == bst[0] && j < bj[0])) {
-                                bst[0] = d2;
-                                bj[0] = j;
-                            }
+                            const unsigned fh = (unsigned)__double2hiint(fma(dy, dy, dx * dx));
+                            B2S_NN_STEP(fh, bh[0], bj[0], j, near);  // (the ragged block is the last one: still ascending)
                         }
                     }
                 };
@@ -423,13 +487,9 @@ __global__ void __maxnreg__(R <= 3 ? 80 : 104) icp_batch_kernel(const TIn *__res
                     }
                 }
 #pragma unroll
-                for (int q = 1; q < NN_CHAINS; ++q)
-                    if (bst[q] < bst[0] || (bst[q] == bst[0] && bj[q] < bj[0])) {
-                        bst[0] = bst[q];
-                        bj[0] = bj[q];
-                    }
-                best[r] = bst[0];
+                for (int q = 1; q < NN_CHAINS; ++q) B2S_NN_STEP(bh[q], bh[0], bj[0], bj[q], near);
                 arg[r] = bj[0];
+                settle(near && real, px, py, arg[r]);
             }
         }
         // ---- matched targets, distances ([ICP]:69,75)
@@ -441,7 +501,10 @@ __global__ void __maxnreg__(R <= 3 ? 80 : 104) icp_batch_kernel(const TIn *__res
             const double2 t = tar[arg[r]];
             bx[r] = t.x;
             by[r] = t.y;
-            if (r < count) dsum += (best[r] == INFINITY) ? 0.0 : sqrt(best[r]);
+            if (r < count) {
+                const double d = ref_dist(sx[r] - t.x, sy[r] - t.y);  // [ICP]:102; inf / NaN: nothing was matched,
+                dsum += (d < INFINITY) ? d : 0.0;                     // the reference keeps distance 0 ([ICP]:95)
+            }
         }
         double T[6];
         cta_rigid_fit<R>(sx, sy, bx, by, count, n, sax, say, sbx, sby, dsum, scratch, phase, T);

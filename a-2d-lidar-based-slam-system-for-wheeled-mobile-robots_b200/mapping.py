@@ -231,6 +231,7 @@ class Mapping(object):
     def device_planes(self):
         """(hit_ptr, miss_ptr, stream_ptr) integers for layer-1 calls and collectives."""
         h, m, s = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        self._pmap64 = None      # the planes may change behind our back: the next update() rebuilds the live array
         _lib.check(self._L.b2s_mapping_planes(self._h, ctypes.byref(h), ctypes.byref(m),
                                               ctypes.byref(s)))
         return h.value, m.value, s.value or 0

@@ -310,7 +310,8 @@ int b2s_mapping_update_scans(b2s_mapping *m, const float *ranges, const double *
 int b2s_mapping_read(b2s_mapping *map, int32_t *hit, int32_t *miss, float *datamap, int8_t *pmap);
 /* Overwrite the count planes from host arrays [xw][yw] (checkpoint restore; the reference has none). */
 int b2s_mapping_write(b2s_mapping *map, const int32_t *hit, const int32_t *miss);
-/* The planes themselves, for layer-1 calls and collectives. */
+/* The planes themselves, for layer-1 calls and collectives.  Handing them out invalidates the object's cached
+ * occupancy: the next update call with a map pointer refreshes the whole map instead of patching dirty tiles. */
 int b2s_mapping_planes(b2s_mapping *map, int32_t **hit, int32_t **miss, void **stream);
 /* bresenham(start,end).path on host arrays (segs [count][4], cells_xy sized by the caller). */
 int b2s_bresenham_host(const int32_t *segs, int count, const int64_t *offsets, int32_t *cells_xy);

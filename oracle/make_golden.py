@@ -141,6 +141,87 @@ def nearest_and_fit_golden():
     np.savez_compressed(os.path.join(OUT, "icp_pieces.npz"), **blob)
 
 
+def nearest_ties_golden():
+    """(ii-b) ties that only the reference's sqrt creates.  findNearest compares np.linalg.norm values ([ICP]:102-103),
+    and sqrt maps neighbouring doubles onto one: src (0,0) with targets (1, 2^-26), (-1, 0) has squared distances
+    1 + 2^-52 and 1 but BOTH norms are exactly 1.0, so the reference keeps index 0 where an argmin over squared
+    distances returns 1.  10^4 generated cases of that kind + whole ICP.process runs whose
+    first-iteration correspondences hinge on such ties."""
+    rng = np.random.Generator(np.random.PCG64(8601))
+    icp = ref_loader.load_icp_class({})()
+    blob = {}
+    d, i = icp.findNearest(np.array([[0.0, 0.0]]), np.array([[1.0, 2.0 ** -26], [-1.0, 0.0]]))
+    blob.update(repro_src=np.array([[0.0, 0.0]]), repro_tar=np.array([[1.0, 2.0 ** -26], [-1.0, 0.0]]),
+                repro_dist=d, repro_idx=np.asarray(i, dtype=np.int64))
+    assert int(i[0]) == 0 and d[0] == 1.0
+    # generated cases: one source point each, 6 targets: a near-tied pair (x, k*2^-26*x) / mirror image in
+    # either index order, k = 0..3 (k = 0 exact tie, 1 sqrt-tie, 2-3 no tie), and four farther decoys
+    n_cases = 10000
+    srcs = np.zeros((n_cases, 2))
+    tars = np.zeros((n_cases, 6, 2))
+    for c in range(n_cases):
+        x = float(np.float32(rng.uniform(0.5, 8.0)))
+        k = int(rng.integers(0, 4))
+        th = float(rng.uniform(-np.pi, np.pi)) if c % 2 else 0.0       # half axis-aligned, half rotated (inexact products)
+        cs, sn = np.cos(th), np.sin(th)
+        a = np.array([x, k * 2.0 ** -26 * x])
+        b = np.array([-x, 0.0])
+        R = np.array([[cs, -sn], [sn, cs]])
+        a, b = R @ a, R @ b
+        o = rng.uniform(-3, 3, size=2) if c % 3 == 0 else np.zeros(2)
+        pts = [a + o, b + o] if rng.integers(0, 2) else [b + o, a + o]
+        decoys = [o + (R @ np.array([x * f, x * g])) for f, g in ((1.5, 0.1), (-1.4, 0.3), (0.2, 1.7), (0.1, -1.3))]
+        slot = rng.permutation(6)
+        allp = pts + decoys
+        # keep the relative order of the tied pair as drawn, shuffle where the pair sits among the decoys
+        order = sorted(range(6), key=lambda q: slot[q] if q >= 2 else min(slot[0], slot[1]) + 0.1 * q)
+        tars[c] = np.array([allp[q] for q in order])
+        srcs[c] = o
+    idx = np.zeros(n_cases, dtype=np.int64)
+    dist = np.zeros(n_cases)
+    for c in range(n_cases):
+        dd, ii = icp.findNearest(srcs[c:c + 1], tars[c])
+        idx[c], dist[c] = int(ii[0]), dd[0]
+    # how many of them an argmin over the squared distance gets wrong: (a) the radicand NumPy's norm actually takes the
+    # root of, fma(dy, dy, dx*dx) (exact rational arithmetic, rounded once); (b) the textbook dx*dx + dy*dy
+    from fractions import Fraction
+    diff = srcs[:, None, :] - tars
+    q_fma = np.array([[float(Fraction(d[1]) * Fraction(d[1]) + Fraction(d[0] * d[0])) for d in row] for row in diff])
+    q_sum = diff[..., 0] * diff[..., 0] + diff[..., 1] * diff[..., 1]
+    assert np.array_equal(np.sqrt(q_fma)[np.arange(n_cases), idx], dist)   # the norm IS sqrt(fma(dy, dy, dx*dx)) here
+    blob.update(gen_src=srcs, gen_tar=tars, gen_idx=idx, gen_dist=dist,
+                gen_d2_argmin_differs=int((q_fma.argmin(1) != idx).sum()),
+                gen_plain_sum_differs=int((np.sqrt(q_sum).argmin(1) != idx).sum()))
+    print("nearest ties: of %d cases %d differ from an argmin over the radicand, %d from sqrt(dx*dx + dy*dy)" % (
+        n_cases, blob["gen_d2_argmin_differs"], blob["gen_plain_sum_differs"]))
+    # whole ICP.process (max_iter 1 and the defaults): source points ON the mirror axis of a target cloud whose mirror
+    # images are displaced by sqrt-tie amounts, so the correspondences of iteration 1 are all decided by the tie rule
+    cases = []
+    for c in range(6):
+        m = 24
+        xs = np.array([float(np.float32(v)) for v in rng.uniform(0.5, 4.0, m)])
+        ys = np.array([float(np.float32(v)) for v in np.linspace(-3, 3, m)])
+        k = rng.integers(0, 3, size=m)
+        right = np.stack([xs, ys + k * 2.0 ** -26 * xs], axis=1)
+        left = np.stack([-xs, ys], axis=1)
+        tar = np.empty((2 * m, 2))
+        first_right = rng.integers(0, 2, size=m).astype(bool)
+        tar[0::2] = np.where(first_right[:, None], right, left)
+        tar[1::2] = np.where(first_right[:, None], left, right)
+        src = np.stack([np.zeros(m), ys], axis=1)
+        src = np.concatenate([src, rng.uniform(-1, 1, size=(5, 2)) + np.array([0.7, 0.0])])   # a few asymmetric points
+        for max_iter, tol in ((1, 0.0), (30, 0.001)):
+            obj, calls = _counting_icp({"/icp/tolerance": tol, "/icp/max_iter": max_iter})
+            T = obj.process(synth.homogeneous(tar.T.copy()), synth.homogeneous(src.T.copy()))
+            cases.append(dict(tar=tar.T.copy(), src=src.T.copy(), T=np.asarray(T, dtype=np.float64), iters=calls["n"],
+                              max_iter=max_iter, tol=tol))
+    blob["icp_count"] = len(cases)
+    for n, cse in enumerate(cases):
+        for key, v in cse.items():
+            blob["icp%d_%s" % (n, key)] = v
+    np.savez_compressed(os.path.join(OUT, "icp_ties.npz"), **blob)
+
+
 def bresenham_golden():
     """(iv) rasteriser: every (dx,dy) with |dx|,|dy| <= 24 in all octants, a dx<=96 sweep of the
     first octant (where float64 != integer Bresenham shows up), long random segments."""
@@ -340,6 +421,7 @@ def main():
             globals()[name]()
         return
     mapping_f64_golden()
+    nearest_ties_golden()
     ingestion_golden()
     bresenham_golden()
     nearest_and_fit_golden()

@@ -24,7 +24,20 @@
 
 /* ------------------------------------------------------------------ ICP pieces */
 
-/* [ICP]:90-114  nearest neighbour: strict '<' on sqrt(dx^2+dy^2), ascending j. */
+/* np.linalg.norm(src[i] - tar[j]) of [ICP]:102 for a 2-vector.  NumPy evaluates it as sqrt(x.dot(x)), and the dot of
+ * two float64 values goes to the BLAS ddot, whose scalar tail loop (`dot += y[i] * x[i]`, OpenBLAS kernel/x86_64/ddot.c,
+ * built with FMA contraction for every FMA3 target) computes fma(x1, x1, x0 * x0): ONE rounding for the first product,
+ * one for the fused second step.  That is what the unmodified reference returns in this container (NumPy 2.3.5,
+ * OpenBLAS 0.3.30) and what tests/golden/icp_ties.npz pins on 10^4 near-tie cases -- a plain dx*dx + dy*dy disagrees
+ * with the reference on 86 of them.  NumPy pins no arithmetic and the reference pins no NumPy,
+ * so this is "the reference as run here", on x86-64 with FMA3 (any host of a B200). */
+static inline double ref_norm2(double dx, double dy)
+{
+    return sqrt(__builtin_fma(dy, dy, dx * dx));
+}
+
+/* [ICP]:90-114  nearest neighbour: strict '<' on the norm (square root INCLUDED: sqrt merges neighbouring doubles,
+ * and the ties it creates go to the lowest j), ascending j. */
 void orc_nearest(const double *src_xy, int n, const double *tar_xy, int m,
                  double *dist_out, int32_t *idx_out)
 {
@@ -36,7 +49,7 @@ void orc_nearest(const double *src_xy, int n, const double *tar_xy, int m,
         for (int j = 0; j < m; ++j) {
             const double dx = sx - tar_xy[2 * j];
             const double dy = sy - tar_xy[2 * j + 1];
-            const double d = sqrt(dx * dx + dy * dy);
+            const double d = ref_norm2(dx, dy);
             if (d < best) {
                 best = d;
                 arg = j;

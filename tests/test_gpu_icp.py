@@ -58,6 +58,49 @@ def test_find_nearest_ties_and_golden(env):
     assert np.array_equal(idx, oi) and np.allclose(dist, od, rtol=0, atol=1e-14)
 
 
+def test_find_nearest_sqrt_ties_follow_the_reference(env):
+    """src (0,0), tar [(1, 2^-26), (-1, 0)] -> both norms are exactly 1.0, the reference returns
+    index 0, an argmin over squared distances returns 1.  Plus the 10^4 generated cases of the golden."""
+    z = load_golden("icp_ties.npz")
+    dist, idx = env.icp.findNearest(z["repro_src"], z["repro_tar"])
+    assert int(idx[0]) == 0 and dist[0] == 1.0
+    # every case is its own (1 x 6) problem; run them as one batch of block-diagonal problems by offsetting the clouds
+    # far apart (exact: the offsets are multiples of 2^10, coordinates below 2^4, so sums and differences are exact
+    # in float64 up to 2^-39 ... NOT exact) -> instead call case by case for a slice and in bulk through process below
+    for c in range(0, 10000, 23):
+        d, i = env.icp.findNearest(z["gen_src"][c:c + 1], z["gen_tar"][c])
+        assert int(i[0]) == int(z["gen_idx"][c]) and d[0] == z["gen_dist"][c], c
+
+
+def test_batched_search_resolves_sqrt_ties_like_the_reference(env):
+    """The batched kernel (every search mode) on clouds whose first-iteration correspondences are all decided by the
+    tie rule: T and the iteration count of the unmodified reference (max_iter 1 and the defaults)."""
+    z = load_golden("icp_ties.npz")
+    L = env.lib.lib()
+    try:
+        for prune in (0, 1, 2, 3):
+            assert L.b2s_tune(b"icp_prune", prune) == 0
+            for n in range(int(z["icp_count"])):
+                icp = env.b2slam.ICP(max_iter=int(z["icp%d_max_iter" % n]), tolerance=float(z["icp%d_tol" % n]))
+                tar, src = z["icp%d_tar" % n], z["icp%d_src" % n]
+                T, it = icp.process_batch(np.repeat(tar[None], 3, 0), np.repeat(src[None], 3, 0))
+                assert (it == int(z["icp%d_iters" % n])).all(), (prune, n)
+                np.testing.assert_allclose(T[1], z["icp%d_T" % n], rtol=0, atol=T_ATOL, err_msg="prune %d case %d" % (prune, n))
+    finally:
+        L.b2s_tune(b"icp_prune", 2)
+    # the 10^4 generated single-point cases through the batched kernel with max_iter = 1: the transform of a one-point
+    # source is the pure translation onto its match, so T's translation names the chosen target
+    tar = np.ascontiguousarray(np.transpose(z["gen_tar"], (0, 2, 1)))            # (P, 2, 6)
+    src = np.ascontiguousarray(z["gen_src"][:, :, None])                          # (P, 2, 1)
+    icp = env.b2slam.ICP(max_iter=1, tolerance=0.0)
+    T, it = icp.process_batch(tar, src)
+    want = z["gen_tar"][np.arange(len(tar)), z["gen_idx"]] - z["gen_src"]
+    others = z["gen_tar"] - z["gen_src"][:, None, :]
+    got_idx = np.abs(others - T[:, None, :2, 2]).sum(-1).argmin(1)
+    assert np.array_equal(got_idx, z["gen_idx"]), "%d cases matched another target" % int((got_idx != z["gen_idx"]).sum())
+    np.testing.assert_allclose(T[:, :2, 2], want, rtol=0, atol=1e-12)
+
+
 def test_get_transform_golden_including_reflections(env):
     z = load_golden("icp_pieces.npz")
     for a, b, T in zip(z["fit_src"], z["fit_tar"], z["fit_T"]):

@@ -71,6 +71,31 @@ def test_nearest_ties_lowest_index_wins():
     assert z["tie_idx"][0] == 3  # triplicated target 3/17/30 -> index 3
 
 
+def test_nearest_sqrt_ties_follow_the_reference():
+    """Ties that exist only after the reference's sqrt (np.linalg.norm): the squared distances differ in the last
+    bits, the norms are equal, the lowest index wins ([ICP]:102-103).  Golden: the reference on 10^4 such cases."""
+    z = load_golden("icp_ties.npz")
+    for fn in (pyref.nearest_targets, corc.nearest):
+        dist, idx = fn(z["repro_src"], z["repro_tar"])
+        assert int(idx[0]) == 0 == int(z["repro_idx"][0]) and dist[0] == 1.0
+    assert int(z["gen_d2_argmin_differs"]) > 100          # an argmin over squared distances is NOT the reference
+    got = np.array([corc.nearest(s[None], t)[1][0] for s, t in zip(z["gen_src"], z["gen_tar"])])
+    assert np.array_equal(got, z["gen_idx"])
+    gd = np.array([corc.nearest(s[None], t)[0][0] for s, t in zip(z["gen_src"][:500], z["gen_tar"][:500])])
+    assert np.array_equal(gd, z["gen_dist"][:500])
+    for c in range(0, 400):                                # literal port on a slice (pure Python)
+        assert int(pyref.nearest_targets(z["gen_src"][c:c + 1], z["gen_tar"][c])[1][0]) == int(z["gen_idx"][c])
+
+
+def test_icp_process_on_tie_decided_clouds_matches_reference():
+    z = load_golden("icp_ties.npz")
+    for n in range(int(z["icp_count"])):
+        tar, src = z["icp%d_tar" % n], z["icp%d_src" % n]
+        T, iters = corc.icp_batch(tar[None], src[None], int(z["icp%d_max_iter" % n]), float(z["icp%d_tol" % n]))
+        assert int(iters[0]) == int(z["icp%d_iters" % n])
+        np.testing.assert_allclose(T[0], z["icp%d_T" % n], rtol=0, atol=1e-12)
+
+
 def test_rigid_fit_matches_reference_including_reflection_branch():
     z = load_golden("icp_pieces.npz")
     for a, b, T in zip(z["fit_src"], z["fit_tar"], z["fit_T"]):
