@@ -60,6 +60,13 @@ SIGNATURES = {
     "b2s_grid_merge_p2p": (_i32, [_vp, _vp, _vp, _i32, _sz, _sz, _vp, _vp, _dbl, _dbl, _dbl, _vp]),
     "b2s_grid_merge_p2p_tiles": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _dbl, _dbl,
                                         _dbl, _vp]),
+    "b2s_p2p_flag_bytes": (_sz, [_i32]),
+    "b2s_p2p_dirty_stride": (_sz, [_i32, _i32]),
+    "b2s_p2p_publish": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, ctypes.c_uint32, _vp]),
+    "b2s_grid_merge_p2p_tiles_sync": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, ctypes.c_uint32, _i32, _i32, _i32, _i32,
+                                             _vp, _vp, _dbl, _dbl, _dbl, _vp]),
+    "b2s_p2p_wait_done": (_i32, [_vp, _i32, ctypes.c_uint32, _vp]),
+    "b2s_p2p_status": (_i32, [_vp, _i32, ctypes.POINTER(_i32), ctypes.POINTER(_i64), _vp]),
     "b2s_grid_workspace_dirty": (_vp, [_vp]),
     "b2s_grid_tile_count": (_i32, [_i32, _i32, ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
     "b2s_grid_clear_dirty": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp]),

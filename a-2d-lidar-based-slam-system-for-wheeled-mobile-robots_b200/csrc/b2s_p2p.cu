@@ -103,22 +103,131 @@ grid_merge_p2p_kernel(PeerPlanes pp, int nranks_rt, long long cell_lo, long long
     }
 }
 
+// ------------------------------------------------------------------ flag words over peer memory
+//
+// The step needs two rendezvous between the ranks: "every rank's ray-cast is done and its dirty map is here"
+// before the merge reads peer planes, and "every rank's merge is done" before the map is consumed and the delta
+// planes are cleared.  Two NCCL micro-collectives per step cost more than the merge itself at 8 GPUs, so the
+// rendezvous are plain words in CUDA-IPC-mapped memory instead: a rank PUSHES its epoch number into a slot of every
+// peer's flag block (st.release.sys after a system-scope fence), and waits by spinning on its OWN block
+// (ld.acquire.sys on local memory, no NVLink traffic while waiting).  Flag block of a rank, uint32 words:
+//   [0, R)     ready[src]  epoch of the last ray-cast + dirty map published by rank src
+//   [R, 2R)    done[src]   epoch of the last merge finished by rank src
+//   [2R, 3R)   bad[src]    beams rank src dropped in that step (NaN / inf / over-long), 0 in a healthy run
+//   [3R]       arrival counter of this rank's merge CTAs;  [3R + 1]  set to 1 if a wait timed out
+// Epochs only grow, so a flag never has to be reset.
+
+struct PeerSync {
+    uint32_t *flags[MAX_RANKS];
+    uint8_t *all_dirty[MAX_RANKS];  // every rank's [nranks][dirty_stride] table of gathered dirty maps
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// the gathered dirty maps are written by the peers while this GPU runs: never through the non-coherent path
+__device__ __forceinline__ unsigned ld_u8_sys(const uint8_t *p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.sys.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+constexpr unsigned long long SPIN_LIMIT_NS = 20ull * 1000 * 1000 * 1000;  // a dead peer must not hang the GPU
+
+// Spin until *flag has reached `epoch` (wrap-safe).  On a timeout the error word is set and the wait gives up: the
+// results of this step are then garbage, and the host sees the word (b2s_p2p_status).
+__device__ __forceinline__ void wait_epoch(const uint32_t *flag, uint32_t epoch, uint32_t *err)
+{
+    if ((int32_t)(ld_acquire_sys(flag) - epoch) >= 0) return;
+    const unsigned long long t0 = global_ns();
+    while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
+        __nanosleep(40);
+        if (global_ns() - t0 > SPIN_LIMIT_NS) {
+            *err = 1;
+            return;
+        }
+    }
+}
+
+// After the ray-cast: CTA r copies this rank's dirty map into rank r's table and then raises ready[rank] there.
+__global__ void __launch_bounds__(256)
+p2p_publish_kernel(PeerSync ps, const uint8_t *__restrict__ dirty, const int32_t *__restrict__ counters, int nranks,
+                   int rank, int dirty_stride, uint32_t epoch)
+{
+    const int r = blockIdx.x;
+    const uint4 *src = reinterpret_cast<const uint4 *>(dirty);
+    uint4 *dst = reinterpret_cast<uint4 *>(ps.all_dirty[r] + (size_t)rank * dirty_stride);
+    for (int k = threadIdx.x; k < dirty_stride / 16; k += blockDim.x) dst[k] = src[k];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t bad = 0;
+        if (counters) bad = (uint32_t)(counters[B2S_CNT_NONFINITE] + counters[B2S_CNT_OVERFLOW] + counters[B2S_CNT_TOO_LONG]);
+        ps.flags[r][2 * nranks + rank] = bad;
+        __threadfence_system();
+        st_release_sys(ps.flags[r] + rank, epoch);
+    }
+}
+
+// End of the step: wait until every rank has finished its merge (so this rank's map is complete and nobody reads
+// its delta planes any more).
+__global__ void __launch_bounds__(32)
+p2p_wait_kernel(uint32_t *flags, int first, int count, uint32_t epoch, int err_word)
+{
+    if ((int)threadIdx.x < count) wait_epoch(flags + first + threadIdx.x, epoch, flags + err_word);
+}
+
 // Tile-sparse form of the merge.  The ray-cast marks the 64 x 64-cell tiles it touches in a dirty map
-// (one byte per tile, inside its workspace); the maps of all ranks are gathered first (that gather is
-// also the fence that orders this kernel after every rank's ray-cast).  A CTA takes one tile of the
+// (one byte per tile, inside its workspace); the maps of all ranks are gathered first.  A CTA takes one tile of the
 // rank's shard of tiles: if no rank dirtied it, nothing is read or written -- counts and occupancy are
 // unchanged; otherwise only the ranks that did are read.  Cost follows the touched area, not the grid.
 // The rank's shard of the global counts is stored tile-major: [tile - tile_lo][64][64].
+//
+// NR > 0: the rank loop is unrolled and ALL peer loads of a pass (2 planes x NR ranks, 16 bytes each) are issued
+// before the first add, which is what keeps an NVLink read stream busy; NR = 0 is the generic loop.
+// SYNC: the kernel itself waits for every rank's ready flag (first thing every CTA does; the flags are raised by the
+// peers' publish kernels, which depend on nothing this kernel does), and the last CTA to finish raises done[rank]
+// in every rank's block -- no host-side collective brackets the launch.
+template <int NR, bool SYNC>
 __global__ void __launch_bounds__(256)
-grid_merge_tiles_kernel(PeerPlanes pp, const uint8_t *__restrict__ all_dirty, int nranks, int ntiles, int tile_lo,
-                        int tile_count, int xw, int yw, int32_t *__restrict__ g_hit, int32_t *__restrict__ g_miss,
-                        double w_hit, double w_miss, double thresh)
+grid_merge_tiles_kernel(PeerPlanes pp, PeerSync ps, const uint8_t *all_dirty, int dirty_stride, int nranks_rt,
+                        int rank, uint32_t epoch, int tile_lo, int tile_count, int xw, int yw,
+                        int32_t *__restrict__ g_hit, int32_t *__restrict__ g_miss, double w_hit, double w_miss,
+                        double thresh)
 {
+    const int nranks = NR > 0 ? NR : nranks_rt;
+    if (SYNC) {
+        uint32_t *mine = ps.flags[rank];
+        if ((int)threadIdx.x < nranks) wait_epoch(mine + threadIdx.x, epoch, mine + 3 * nranks + 1);
+        __syncthreads();
+    }
     const int tiles_y = grid_tiles(yw);
     for (int t = blockIdx.x; t < tile_count; t += gridDim.x) {
         const int tile = tile_lo + t;
         unsigned who = 0;
-        for (int r = 0; r < nranks; ++r) who |= (all_dirty[(size_t)r * ntiles + tile] ? 1u : 0u) << r;
+        if (NR > 0) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) who |= (ld_u8_sys(all_dirty + (size_t)r * dirty_stride + tile) ? 1u : 0u) << r;
+        } else {
+            for (int r = 0; r < nranks; ++r) who |= (ld_u8_sys(all_dirty + (size_t)r * dirty_stride + tile) ? 1u : 0u) << r;
+        }
         if (!who) continue;
         const int x0 = (tile / tiles_y) * GRID_TILE, y0 = (tile % tiles_y) * GRID_TILE;
         int32_t *gh = g_hit + (size_t)t * GRID_TILE * GRID_TILE, *gm = g_miss + (size_t)t * GRID_TILE * GRID_TILE;
@@ -132,15 +241,47 @@ grid_merge_tiles_kernel(PeerPlanes pp, const uint8_t *__restrict__ all_dirty, in
             const size_t cell = (size_t)x * yw + y;
             int4 h = *reinterpret_cast<const int4 *>(gh + rx * GRID_TILE + qy);
             int4 m = *reinterpret_cast<const int4 *>(gm + rx * GRID_TILE + qy);
-            for (int r = 0; r < nranks; ++r)
-                if (who & (1u << r)) {
-                    add4(h, ld_stream(pp.hit[r] + cell));
-                    add4(m, ld_stream(pp.miss[r] + cell));
+            if (NR > 0) {
+                int4 dh[NR > 0 ? NR : 1], dm[NR > 0 ? NR : 1];
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    dh[r] = dm[r] = make_int4(0, 0, 0, 0);
+                    if (who & (1u << r)) {
+                        dh[r] = ld_stream(pp.hit[r] + cell);
+                        dm[r] = ld_stream(pp.miss[r] + cell);
+                    }
                 }
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    add4(h, dh[r]);
+                    add4(m, dm[r]);
+                }
+            } else {
+                for (int r = 0; r < nranks; ++r)
+                    if (who & (1u << r)) {
+                        add4(h, ld_stream(pp.hit[r] + cell));
+                        add4(m, ld_stream(pp.miss[r] + cell));
+                    }
+            }
             *reinterpret_cast<int4 *>(gh + rx * GRID_TILE + qy) = h;
             *reinterpret_cast<int4 *>(gm + rx * GRID_TILE + qy) = m;
             const uint32_t occ = occupancy4(h, m, w_hit, w_miss, thresh);
             for (int r = 0; r < nranks; ++r) *reinterpret_cast<uint32_t *>(pp.pmap[r] + cell) = occ;
+        }
+    }
+    if (SYNC) {
+        // the map stores above must be visible system-wide before done[rank] is: fence, count the CTA in, and let
+        // the last one raise the flags
+        __shared__ int last;
+        __threadfence_system();
+        __syncthreads();
+        uint32_t *mine = ps.flags[rank];
+        if (threadIdx.x == 0) last = (atomicAdd(mine + 3 * nranks, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (last) {
+            if (threadIdx.x == 0) mine[3 * nranks] = 0;  // re-armed for the next launch
+            __threadfence_system();
+            if ((int)threadIdx.x < nranks) st_release_sys(ps.flags[threadIdx.x] + nranks + rank, epoch);
         }
     }
 }
@@ -149,19 +290,23 @@ grid_merge_tiles_kernel(PeerPlanes pp, const uint8_t *__restrict__ all_dirty, in
 
 using namespace b2s;
 
-extern "C" int b2s_grid_merge_p2p_tiles(const int32_t *const *delta_hit, const int32_t *const *delta_miss,
-                                        int8_t *const *pmap, const uint8_t *all_dirty, int nranks, int xw, int yw,
-                                        int tile_lo, int tile_hi, int32_t *global_hit_shard,
-                                        int32_t *global_miss_shard, double w_hit, double w_miss, double thresh,
-                                        void *stream)
+namespace b2s {
+static int merge_tiles_launch(const int32_t *const *delta_hit, const int32_t *const *delta_miss, int8_t *const *pmap,
+                              const uint8_t *all_dirty, int dirty_stride, uint32_t *const *flags, int nranks, int rank,
+                              uint32_t epoch, int xw, int yw, int tile_lo, int tile_hi, int32_t *global_hit_shard,
+                              int32_t *global_miss_shard, double w_hit, double w_miss, double thresh, void *stream)
 {
     B2S_REQUIRE(delta_hit && delta_miss && pmap && all_dirty && global_hit_shard && global_miss_shard,
                 "b2s_grid_merge_p2p_tiles: null pointer");
     B2S_REQUIRE(nranks >= 1 && nranks <= MAX_RANKS, "b2s_grid_merge_p2p_tiles: 1..16 ranks");
     B2S_REQUIRE(xw > 0 && yw > 0 && yw % 4 == 0, "b2s_grid_merge_p2p_tiles: yw must be a multiple of 4");
     const int ntiles = grid_tiles(xw) * grid_tiles(yw);
+    B2S_REQUIRE(dirty_stride >= ntiles, "b2s_grid_merge_p2p_tiles: dirty stride smaller than the tile count");
     B2S_REQUIRE(tile_lo >= 0 && tile_lo <= tile_hi && tile_hi <= ntiles, "b2s_grid_merge_p2p_tiles: tile range");
+    B2S_REQUIRE(!flags || (rank >= 0 && rank < nranks), "b2s_grid_merge_p2p_tiles: rank out of range");
     PeerPlanes pp;
+    PeerSync ps;
+    memset(&ps, 0, sizeof(ps));
     for (int r = 0; r < nranks; ++r) {
         B2S_REQUIRE(delta_hit[r] && delta_miss[r] && pmap[r], "b2s_grid_merge_p2p_tiles: null plane");
         B2S_REQUIRE((uintptr_t)delta_hit[r] % 16 == 0 && (uintptr_t)delta_miss[r] % 16 == 0 && (uintptr_t)pmap[r] % 4 == 0,
@@ -169,15 +314,109 @@ extern "C" int b2s_grid_merge_p2p_tiles(const int32_t *const *delta_hit, const i
         pp.hit[r] = delta_hit[r];
         pp.miss[r] = delta_miss[r];
         pp.pmap[r] = pmap[r];
+        if (flags) {
+            B2S_REQUIRE(flags[r], "b2s_grid_merge_p2p_tiles: null flag block");
+            ps.flags[r] = flags[r];
+        }
     }
     const int count = tile_hi - tile_lo;
-    if (count == 0) return B2S_OK;
-    int blocks = count;
-    const int cap = sm_count() * 16;
+    // with flags the kernel is also this rank's "merge done" signal: it runs even when the shard is empty
+    if (count == 0 && !flags) return B2S_OK;
+    int blocks = count > 0 ? count : 1;
+    const int cap = sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    grid_merge_tiles_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pp, all_dirty, nranks, ntiles, tile_lo, count, xw,
-                                                                     yw, global_hit_shard, global_miss_shard, w_hit,
-                                                                     w_miss, thresh);
+    cudaStream_t st = (cudaStream_t)stream;
+#define B2S_TILES(NR, SY)                                                                                          \
+    grid_merge_tiles_kernel<NR, SY><<<blocks, 256, 0, st>>>(pp, ps, all_dirty, dirty_stride, nranks, rank, epoch,  \
+                                                            tile_lo, count, xw, yw, global_hit_shard,             \
+                                                            global_miss_shard, w_hit, w_miss, thresh)
+    if (flags) {
+        switch (nranks) {
+        case 2: B2S_TILES(2, true); break;
+        case 4: B2S_TILES(4, true); break;
+        case 8: B2S_TILES(8, true); break;
+        default: B2S_TILES(0, true); break;
+        }
+    } else {
+        switch (nranks) {
+        case 2: B2S_TILES(2, false); break;
+        case 4: B2S_TILES(4, false); break;
+        case 8: B2S_TILES(8, false); break;
+        default: B2S_TILES(0, false); break;
+        }
+    }
+#undef B2S_TILES
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+}  // namespace b2s
+
+extern "C" int b2s_grid_merge_p2p_tiles(const int32_t *const *delta_hit, const int32_t *const *delta_miss,
+                                        int8_t *const *pmap, const uint8_t *all_dirty, int nranks, int xw, int yw,
+                                        int tile_lo, int tile_hi, int32_t *global_hit_shard,
+                                        int32_t *global_miss_shard, double w_hit, double w_miss, double thresh,
+                                        void *stream)
+{
+    const int ntiles = (xw > 0 && yw > 0) ? grid_tiles(xw) * grid_tiles(yw) : 0;
+    return merge_tiles_launch(delta_hit, delta_miss, pmap, all_dirty, ntiles, nullptr, nranks, 0, 0, xw, yw, tile_lo,
+                              tile_hi, global_hit_shard, global_miss_shard, w_hit, w_miss, thresh, stream);
+}
+
+extern "C" size_t b2s_p2p_flag_bytes(int nranks) { return nranks > 0 ? (size_t)(3 * nranks + 2) * sizeof(uint32_t) : 0; }
+
+extern "C" size_t b2s_p2p_dirty_stride(int xw, int yw) { return (xw > 0 && yw > 0) ? grid_dirty_bytes(xw, yw) : 0; }
+
+extern "C" int b2s_p2p_publish(const void *workspace, const int32_t *counters, uint8_t *const *all_dirty,
+                               uint32_t *const *flags, int nranks, int rank, int xw, int yw, uint32_t epoch, void *stream)
+{
+    B2S_REQUIRE(workspace && all_dirty && flags, "b2s_p2p_publish: null pointer");
+    B2S_REQUIRE(nranks >= 1 && nranks <= MAX_RANKS && rank >= 0 && rank < nranks, "b2s_p2p_publish: bad rank");
+    B2S_REQUIRE(xw > 0 && yw > 0, "b2s_p2p_publish: grid size");
+    PeerSync ps;
+    memset(&ps, 0, sizeof(ps));
+    for (int r = 0; r < nranks; ++r) {
+        B2S_REQUIRE(all_dirty[r] && flags[r] && (uintptr_t)all_dirty[r] % 16 == 0, "b2s_p2p_publish: null / misaligned peer buffer");
+        ps.all_dirty[r] = all_dirty[r];
+        ps.flags[r] = flags[r];
+    }
+    p2p_publish_kernel<<<nranks, 256, 0, (cudaStream_t)stream>>>(ps, (const uint8_t *)workspace + GRID_WS_HEADER, counters,
+                                                                 nranks, rank, (int)grid_dirty_bytes(xw, yw), epoch);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+
+extern "C" int b2s_grid_merge_p2p_tiles_sync(const int32_t *const *delta_hit, const int32_t *const *delta_miss,
+                                             int8_t *const *pmap, const uint8_t *all_dirty, uint32_t *const *flags,
+                                             int nranks, int rank, uint32_t epoch, int xw, int yw, int tile_lo,
+                                             int tile_hi, int32_t *global_hit_shard, int32_t *global_miss_shard,
+                                             double w_hit, double w_miss, double thresh, void *stream)
+{
+    B2S_REQUIRE(flags, "b2s_grid_merge_p2p_tiles_sync: null flag table");
+    const int stride = (xw > 0 && yw > 0) ? (int)grid_dirty_bytes(xw, yw) : 0;
+    return merge_tiles_launch(delta_hit, delta_miss, pmap, all_dirty, stride, flags, nranks, rank, epoch, xw, yw, tile_lo,
+                              tile_hi, global_hit_shard, global_miss_shard, w_hit, w_miss, thresh, stream);
+}
+
+extern "C" int b2s_p2p_status(const uint32_t *my_flags, int nranks, int *timed_out, int64_t *dropped_beams, void *stream)
+{
+    B2S_REQUIRE(my_flags && nranks >= 1 && nranks <= MAX_RANKS, "b2s_p2p_status: bad arguments");
+    uint32_t h[3 * MAX_RANKS + 2];
+    B2S_CUDA(cudaMemcpyAsync(h, my_flags, (size_t)(3 * nranks + 2) * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                             (cudaStream_t)stream));
+    B2S_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (timed_out) *timed_out = (int)h[3 * nranks + 1];
+    if (dropped_beams) {
+        int64_t total = 0;
+        for (int r = 0; r < nranks; ++r) total += h[2 * nranks + r];
+        *dropped_beams = total;
+    }
+    return B2S_OK;
+}
+
+extern "C" int b2s_p2p_wait_done(uint32_t *my_flags, int nranks, uint32_t epoch, void *stream)
+{
+    B2S_REQUIRE(my_flags && nranks >= 1 && nranks <= MAX_RANKS, "b2s_p2p_wait_done: bad arguments");
+    p2p_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(my_flags, nranks, nranks, epoch, 3 * nranks + 1);
     B2S_CUDA(cudaGetLastError());
     return B2S_OK;
 }

@@ -140,11 +140,16 @@ class ShardedMappingP2P(object):
     IPC).  One kernel per rank then sums its shard of all ranks' deltas, adds the sums into its
     shard of the global counts, finalizes that shard and stores the int8 occupancy into every rank's
     map -- reduce-scatter, finalize and all-gather in one pass.  The global counts stay sharded
-    (1/world of the grid per rank); every rank holds the full occupancy map.  Two one-element
-    all-reduces on the same stream fence the kernel against the peers' ray-casts and map writes.
+    (1/world of the grid per rank); every rank holds the full occupancy map.
+
+    fence="flags" (default with sparse=True): no collective in the step.  The ranks push epoch words and their dirty
+    maps into each other's CUDA-IPC-mapped buffers and the merge kernel itself waits for them (b2s_p2p_publish,
+    b2s_grid_merge_p2p_tiles_sync, b2s_p2p_wait_done).  fence="nccl": the round-1 form, an all-gather of the dirty
+    maps before the kernel and a one-element all-reduce after it, kept for comparison and for the dense kernel.
     """
 
-    def __init__(self, xw, yw, xyreso, hit_weight=20.0, miss_weight=0.01, occ_threshold=10.0, sparse=True):
+    def __init__(self, xw, yw, xyreso, hit_weight=20.0, miss_weight=0.01, occ_threshold=10.0, sparse=True,
+                 fence="flags"):
         import ctypes
         from b2slam import _lib, devapi
         self._lib, self._dev, self._ct = _lib, devapi, ctypes
@@ -170,9 +175,16 @@ class ShardedMappingP2P(object):
                 raise ValueError("the dense peer-memory merge needs xw*yw to be a multiple of 4096 cells")
             lo, hi = shard_bounds(blocks, self.rank, self.world)
             self.cell_lo, self.cell_hi = lo * 4096, hi * 4096
+        self.flags_mode = self.sparse and fence == "flags"
+        self.epoch = 0
         self._own = []
         ptrs = []
-        for nbytes in (self.cells * 4, self.cells * 4, self.cells):
+        sizes = [self.cells * 4, self.cells * 4, self.cells]
+        if self.flags_mode:
+            self.dirty_stride = int(L.b2s_p2p_dirty_stride(self.xw, self.yw))
+            self.flag_words = int(L.b2s_p2p_flag_bytes(self.world)) // 4
+            sizes += [self.world * self.dirty_stride, self.flag_words * 4]
+        for nbytes in sizes:
             p = ctypes.c_void_p()
             _lib.check(L.b2s_device_alloc(ctypes.byref(p), nbytes))
             self._own.append(p.value)
@@ -183,6 +195,12 @@ class ShardedMappingP2P(object):
         self.d_hit.zero_()
         self.d_miss.zero_()
         self.pmap_dev.fill_(50)
+        if self.flags_mode:
+            self.all_dirty = devapi.tensor_from_ptr(ptrs[3], (self.world * self.dirty_stride,), torch.uint8)
+            self.flags = devapi.tensor_from_ptr(ptrs[4], (self.flag_words,), torch.int32)
+            self.all_dirty.zero_()
+            self.flags.zero_()
+            self.counters = torch.zeros(_lib.CNT_WORDS, dtype=torch.int32, device="cuda")
         handles = []
         for p in ptrs:
             buf = ctypes.create_string_buffer(64)
@@ -194,9 +212,10 @@ class ShardedMappingP2P(object):
         else:
             everyone[0] = handles
         self._opened = []
-        table = [[0] * self.world for _ in range(3)]
+        nbuf = len(ptrs)
+        table = [[0] * self.world for _ in range(nbuf)]
         for r in range(self.world):
-            for k in range(3):
+            for k in range(nbuf):
                 if r == self.rank:
                     table[k][r] = ptrs[k]
                 else:
@@ -206,6 +225,8 @@ class ShardedMappingP2P(object):
                     table[k][r] = q.value
         arr = ctypes.c_void_p * self.world
         self._hit_ptrs, self._miss_ptrs, self._pmap_ptrs = (arr(*table[k]) for k in range(3))
+        if self.flags_mode:
+            self._dirty_ptrs, self._flag_ptrs = arr(*table[3]), arr(*table[4])
         n = self.cell_hi - self.cell_lo
         self.g_hit = torch.zeros(max(n, 4096), dtype=torch.int32, device="cuda")
         self.g_miss = torch.zeros(max(n, 4096), dtype=torch.int32, device="cuda")
@@ -213,7 +234,8 @@ class ShardedMappingP2P(object):
         if self.sparse:
             dptr = L.b2s_grid_workspace_dirty(ctypes.c_void_p(self.workspace.data_ptr()))
             self.dirty = devapi.tensor_from_ptr(dptr, (self.ntiles,), torch.uint8)
-            self.all_dirty = torch.zeros(self.world * self.ntiles, dtype=torch.uint8, device="cuda")
+            if not self.flags_mode:
+                self.all_dirty = torch.zeros(self.world * self.ntiles, dtype=torch.uint8, device="cuda")
         self.pmap_host = torch.empty((self.xw, self.yw), dtype=torch.int8).pin_memory()
         self._token = torch.zeros(1, dtype=torch.int32, device="cuda")
         self._in = None
@@ -235,6 +257,8 @@ class ShardedMappingP2P(object):
         if self.sparse:
             self._lib.check(L.b2s_grid_clear_dirty(self.d_hit.data_ptr(), self.d_miss.data_ptr(), self.xw, self.yw,
                                                    self.workspace.data_ptr(), stream))
+            if self.flags_mode:
+                self.counters.zero_()
         else:
             self.d_hit.zero_()
             self.d_miss.zero_()
@@ -244,6 +268,19 @@ class ShardedMappingP2P(object):
         L = self._lib.lib()
         stream = torch.cuda.current_stream().cuda_stream
         w_hit, w_miss, thr = self.weights
+        if self.flags_mode:
+            # no collective: publish (dirty map + ready flag to every rank) -> merge (waits for the ready flags itself,
+            # its last CTA raises the done flags) -> wait for every rank's done flag
+            self.epoch += 1
+            ws = self._ct.c_void_p(self.workspace.data_ptr())
+            self._lib.check(L.b2s_p2p_publish(ws, self.counters.data_ptr(), self._dirty_ptrs, self._flag_ptrs, self.world,
+                                              self.rank, self.xw, self.yw, self.epoch, stream))
+            self._lib.check(L.b2s_grid_merge_p2p_tiles_sync(
+                self._hit_ptrs, self._miss_ptrs, self._pmap_ptrs, self.all_dirty.data_ptr(), self._flag_ptrs, self.world,
+                self.rank, self.epoch, self.xw, self.yw, self.tile_lo, self.tile_hi, self.g_hit.data_ptr(),
+                self.g_miss.data_ptr(), w_hit, w_miss, thr, stream))
+            self._lib.check(L.b2s_p2p_wait_done(self.flags.data_ptr(), self.world, self.epoch, stream))
+            return
         if self.sparse:
             if self.world > 1:   # the gather of the dirty maps is also the fence after every rank's ray-cast
                 dist.all_gather_into_tensor(self.all_dirty, self.dirty)
@@ -260,6 +297,25 @@ class ShardedMappingP2P(object):
                 self.g_hit.data_ptr(), self.g_miss.data_ptr(), w_hit, w_miss, thr, stream))
         self._fence()
 
+    def _counters(self):
+        return self.counters if self.flags_mode else None
+
+    def check(self):
+        """Raise on EVERY rank if any rank dropped beams in the last step (NaN / inf coordinates or over-long beams:
+        what Mapping.update_batch raises ValueError / OverflowError for) or if a flag wait timed out.  The counts of
+        all ranks travel with the ready flags, so this is a local read; it synchronizes the stream.  Unlike
+        Mapping.update_batch the step is not rolled back: after an error the object must be rebuilt."""
+        if not self.flags_mode:
+            return
+        t, bad = self._ct.c_int(0), self._ct.c_int64(0)
+        self._lib.check(self._lib.lib().b2s_p2p_status(self.flags.data_ptr(), self.world, self._ct.byref(t),
+                                                       self._ct.byref(bad), torch.cuda.current_stream().cuda_stream))
+        if t.value:
+            raise RuntimeError("a peer did not reach the merge within the time limit (rank %d)" % self.rank)
+        if bad.value:
+            raise ValueError("%d beam(s) with a NaN / inf coordinate or longer than the limit were dropped by some rank; "
+                             "the merged grid of this step is incomplete" % bad.value)
+
     def update_device(self, ox, oy, cx, cy, events=None):
         """Scans already on the device (float32 CUDA tensors).  Leaves the merged map in pmap_dev.
         `events`: optional (start, stop) torch.cuda.Event pair recorded around the ray-cast."""
@@ -267,7 +323,8 @@ class ShardedMappingP2P(object):
         S, Hx, Hy = self.scale
         if events:
             events[0].record()
-        self._dev.grid_raycast(self.d_hit, self.d_miss, S, Hx, Hy, ox, oy, cx, cy, workspace=self.workspace)
+        self._dev.grid_raycast(self.d_hit, self.d_miss, S, Hx, Hy, ox, oy, cx, cy, counters=self._counters(),
+                               workspace=self.workspace)
         if events:
             events[1].record()
         self._merge()
@@ -298,6 +355,7 @@ class ShardedMappingP2P(object):
         self._merge()
         self.pmap_host.copy_(self.pmap_dev, non_blocking=True)
         main.synchronize()
+        self.check()
         return self.pmap_host.numpy()
 
     def update_batch(self, ox, oy, cx, cy):
@@ -310,7 +368,7 @@ class ShardedMappingP2P(object):
 
         def raycast(lo, hi):
             self._dev.grid_raycast(self.d_hit, self.d_miss, S, Hx, Hy, d[0][lo:hi], d[1][lo:hi], d[2][lo:hi], d[3][lo:hi],
-                                   workspace=self.workspace)
+                                   counters=self._counters(), workspace=self.workspace)
         return self._pipeline(host, d, host[0].shape[0], host[0].shape[1], raycast)
 
     def update_scans(self, ranges, poses, angle_min, angle_max, clamp_inf_to=30.0):
@@ -335,7 +393,7 @@ class ShardedMappingP2P(object):
 
         def raycast(lo, hi):
             self._dev.grid_raycast_ranges(self.d_hit, self.d_miss, S, Hx, Hy, d[0][lo:hi], d[1][lo:hi], self._beam_cs,
-                                          clamp_inf_to, workspace=self.workspace)
+                                          clamp_inf_to, counters=self._counters(), workspace=self.workspace)
         return self._pipeline([ranges, pose4], d, K, N, raycast)
 
     def counts(self):

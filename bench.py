@@ -19,6 +19,12 @@ after untimed calls that bring the GPU back to full clocks.  Beside it: `e2e_fus
 raw-scan entry points Mapping.update_scans / ICP.process_scans, half the bytes) and, for the ICP,
 `e2e_pair_form` (ICP.process_batch on explicit pairs, twice the bytes).
 
+With N > 1 ranks the line also carries `merge_bit_identical`: after the timed region a reduced batch per rank goes
+through the same peer-memory merge, every rank ray-casts ALL ranks' scans in one pass by itself, and the merged map
+and its shard of the merged counts are compared byte for byte (all ranks must agree).  `cfg4` / `cfg5` hold the two
+sharded configurations of BASELINE.json (1 M independent 1080-beam ICP pairs; a 16384 x 16384 grid from 8 scan
+streams), strong scaling over the N ranks, each with a parity sample.
+
 `--impl reference` times the reference's own CPU algorithm (the literal Python/NumPy port in
 oracle/pyref.py -- the reference is pure Python, so there is nothing faster to be fair to) on
 all host cores, on a bounded sample of the same workload.
@@ -53,6 +59,24 @@ def measured_peaks():
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_stamp(key):
+    """Figures that only a profiler can give (DRAM bytes, executed-instruction counts), taken from the committed ncu
+    capture of this workload and stamped with the SHA-1 of the kernel sources they were measured on
+    (profiles/r2/ncu_stamps.json, written by profiles/scripts/stamp_ncu.py).  A kernel edited since then makes the
+    stamp stale: the entry is returned as None instead of quoting a number that belongs to other code."""
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2", "ncu_stamps.json")) as fh:
+            ent = json.load(fh)[key]
+        h = hashlib.sha1()
+        for rel in ent["sources"]:
+            with open(os.path.join(ROOT, rel), "rb") as fh:
+                h.update(fh.read())
+        return ent if h.hexdigest() == ent["sha1"] else None
+    except Exception:
+        return None
 
 
 # =============================================================================== clocks
@@ -360,14 +384,13 @@ def bench_grid(args, rank, world, torch, devapi, bdist, synth):
 
     peak, peak_src = measured_peaks()
     achieved = algo_bytes / (ray_avg_ms * 1e-3) / 1e9
-    traffic = None  # DRAM bytes per launch from the committed ncu capture of this exact workload, if there is one
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1", "grid_traffic.json")) as fh:
-            cap = json.load(fh)
-        if cap.get("scans") == K and G == 4096 and N == 1080:
-            traffic = cap["dram__bytes_read.sum"] + cap["dram__bytes_write.sum"]
-    except Exception:
-        pass
+    # DRAM bytes per launch: from the committed ncu capture of this exact workload IF the kernel source is still the
+    # one that was profiled (ncu_stamp), else null
+    stamp = ncu_stamp("grid_raycast")
+    traffic = None
+    if stamp and stamp.get("scans") == K and G == 4096 and N == 1080:
+        traffic = stamp["dram_bytes_per_launch"]
+    merge = merge_check(world, rank, torch, devapi, bdist, synth) if p2p is not None else None
     if p2p is not None:
         p2p.close()
     res = {
@@ -385,7 +408,8 @@ def bench_grid(args, rank, world, torch, devapi, bdist, synth):
                                    "scan streams sharded by rank, int32 count deltas all-reduced (NCCL)")},
         "dtype": "int32 counts (f64 cell / error arithmetic)",
         "roofline": {"bound": "hbm", "kernel": "grid_raycast (+ fold of the transposed scratch plane)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu, profiles/r1/grid_traffic.json)",
+                     "frac": achieved / peak, "traffic": traffic,
+                     "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/r2/ncu_stamps.json; null when the kernel source changed since the capture)",
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": ray_avg_ms,
                      "cell_visits_per_s": visits / (ray_avg_ms * 1e-3)},
         "e2e": {"value": world * K * N * e2e_steps / e2e_s, "unit": "beams/s",
@@ -393,12 +417,61 @@ def bench_grid(args, rank, world, torch, devapi, bdist, synth):
                 "api": ("Mapping.update_batch (b2s_mapping_update)" if world == 1 else
                         "dist.ShardedMappingP2P.update_batch" if p2p is not None else "dist.ShardedMapping.update_batch"),
                 "ms_per_step": e2e_s / e2e_steps * 1e3},
-        "gpu_launches": 3 * args.steps,
+        # own kernels per step: ray-cast + fold + finalize on one GPU; clear-dirty + ray-cast + fold + publish + merge +
+        # wait with the flag-synchronised peer-memory merge
+        "gpu_launches": (6 if p2p is not None else 3) * args.steps,
         "clocks": clocks,
     }
     if fused:
         res["e2e_fused_ingestion"] = fused
+        if world > 1:
+            # N > 1: the raw-scan call is the headline end-to-end path (4 B per beam instead of 8 over the host's memory
+            # system, which eight ranks share); the endpoint form is kept beside it
+            res["e2e_endpoint_form"] = res["e2e"]
+            res["e2e"] = fused
+    if merge is not None:
+        res["merge_bit_identical"] = merge["identical"]
+        res["merge_check"] = merge
     return res
+
+
+def merge_check(world, rank, torch, devapi, bdist, synth, scans=256, steps=2):
+    """Driver-visible multi-GPU correctness (the reference is one process, so 'bit-identical to one GPU' is the
+    contract): `steps` steps of `scans` scans per rank through the peer-memory merge, then EVERY rank ray-casts all
+    ranks' scans in a single pass by itself and compares its copy of the merged occupancy map and its shard of the
+    merged counts byte for byte.  The verdicts are AND-reduced over the ranks."""
+    import torch.distributed as dist
+    G, N = GRID_CELLS, GRID_BEAMS
+    p2p = bdist.ShardedMappingP2P(G, G, GRID_RESO)
+    dev = [torch.from_numpy(a).cuda() for a in synth.grid_scans(22001 + rank, scans, N)]
+    for _ in range(steps):
+        p2p.update_device(*dev)
+    p2p.check()
+    everyone = []
+    for t in dev:
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        everyone.append(torch.cat(parts))
+    S, Hx, Hy = devapi.grid_scale(G, G, GRID_RESO)
+    hit, miss = devapi.new_planes(G, G)
+    ws = devapi.new_workspace(G, G)
+    for _ in range(steps):
+        devapi.grid_raycast(hit, miss, S, Hx, Hy, *everyone, workspace=ws)
+    pm = torch.empty((G, G), dtype=torch.int8, device="cuda")
+    devapi.grid_finalize(hit, miss, pmap=pm)
+    torch.cuda.synchronize()
+    same_map = bool(torch.equal(pm, p2p.pmap_dev))
+    n = (p2p.tile_hi - p2p.tile_lo) * 4096
+    tiles = lambda plane: plane.view(G // 64, 64, G // 64, 64).permute(0, 2, 1, 3).reshape(-1)[p2p.tile_lo * 4096:p2p.tile_hi * 4096]
+    same_counts = bool(torch.equal(tiles(hit), p2p.g_hit[:n]) and torch.equal(tiles(miss), p2p.g_miss[:n]))
+    flag = torch.tensor([int(same_map), int(same_counts)], dtype=torch.int32, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out = {"identical": bool(flag.min().item() == 1), "map_identical_on_every_rank": bool(flag[0].item() == 1),
+           "count_shards_identical": bool(flag[1].item() == 1), "cells": G * G, "scans_per_rank": scans, "steps": steps,
+           "ranks": world, "occupied_cells": int((pm == 100).sum().item()),
+           "against": "one ray-cast pass over all ranks' scans, done by every rank on its own GPU"}
+    p2p.close()
+    return out
 
 
 def bench_icp(args, rank, world, torch, devapi, bdist, synth):
@@ -492,6 +565,128 @@ def bench_icp(args, rank, world, torch, devapi, bdist, synth):
     }
 
 
+def device_pairs(torch, seed, pairs, beams, chunk=65536):
+    """cfg 4 input: the synth.icp_pairs formulae evaluated with torch on the GPU (float32 points; 17.3 GB for 10^6 pairs
+    would not be worth generating on the host)."""
+    import math
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    tar = torch.empty((pairs, 2, beams), dtype=torch.float32, device="cuda")
+    src = torch.empty_like(tar)
+    phi = torch.linspace(-math.pi, math.pi, beams, dtype=torch.float64, device="cuda")[None, :]
+    for s in range(0, pairs, chunk):
+        e = min(pairs, s + chunk)
+        n = e - s
+        u = lambda lo, hi, shape: lo + (hi - lo) * torch.rand(shape, generator=g, dtype=torch.float64, device="cuda")
+        r0, amp, psi = u(3, 8, (n, 1)), u(0.5, 2, (n, 1)), u(0, 2 * math.pi, (n, 1))
+        k = torch.randint(2, 6, (n, 1), generator=g, device="cuda").double()
+        base = r0 + amp * torch.sin(k * phi + psi)
+        noise = lambda: torch.randn((n, beams), generator=g, dtype=torch.float64, device="cuda") * 0.01
+        rt = (base + noise()).clamp(0.10, 30.0)
+        rs = (base + noise()).clamp(0.10, 30.0)
+        tx, ty, th = u(-0.15, 0.15, (n, 1)), u(-0.15, 0.15, (n, 1)), u(-0.08, 0.08, (n, 1))
+        tar[s:e, 0], tar[s:e, 1] = (rt * torch.cos(phi)).float(), (rt * torch.sin(phi)).float()
+        sx, sy = rs * torch.cos(phi), rs * torch.sin(phi)
+        c, sn = torch.cos(th), torch.sin(th)
+        src[s:e, 0], src[s:e, 1] = (c * sx - sn * sy + tx).float(), (sn * sx + c * sy + ty).float()
+    return tar, src
+
+
+def bench_cfg4(args, rank, world, torch, devapi, bdist):
+    """BASELINE.json config 4: 10^6 independent 1080-beam ICP pairs sharded over the ranks (strong scaling, no
+    collective).  Parity: the first 64 pairs of every rank against oracle.c (T to 1e-9, identical iteration counts)."""
+    import torch.distributed as dist
+    total, beams = args.cfg4_pairs, 1080
+    lo, hi = bdist.shard_bounds(total, rank, world)
+    tar, src = device_pairs(torch, 4001 + rank, hi - lo, beams)
+    T = torch.empty((hi - lo, 3, 3), dtype=torch.float64, device="cuda")
+    it = torch.empty(hi - lo, dtype=torch.int32, device="cuda")
+    devapi.icp_batch(tar[:8192], src[:8192], 30, 1e-3)
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(2):
+        bdist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        devapi.icp_batch(tar, src, 30, 1e-3, T, it)
+        b.record()
+        torch.cuda.synchronize()
+        times.append(bdist.max_over_ranks(a.elapsed_time(b)))
+    ms = min(times)
+    from oracle import corc                     # the checker, on a sample; never the thing timed
+    sample = min(64, hi - lo)
+    want_T, want_it = corc.icp_batch(tar[:sample].cpu().numpy(), src[:sample].cpu().numpy(), 30, 1e-3)
+    got_T, got_it = T[:sample].cpu().numpy(), it[:sample].cpu().numpy()
+    ok = bool(np.array_equal(got_it, want_it) and np.abs(got_T - want_T).max() < 1e-9)
+    flag = torch.tensor([int(ok)], dtype=torch.int32, device="cuda")
+    iters = it.sum(dtype=torch.int64).reshape(1).clone()
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        dist.all_reduce(iters)
+    fp64 = ncu_stamp("icp_1080")
+    return {"workload": "cfg4: %d independent 1080-beam ICP pairs sharded over the ranks, max_iter 30, tolerance 1e-3" % total,
+            "value": total / (ms * 1e-3), "unit": "pairs/s", "ms": ms, "n_gpus": world, "scaling": "strong",
+            "pairs_per_gpu": hi - lo, "mean_iterations": float(iters.item()) / total,
+            "parity": {"ok": bool(flag.item() == 1), "pairs_per_rank": sample, "against": "oracle.c (float64)",
+                       "tolerance": "T 1e-9 abs, iteration counts identical"},
+            "fp64_pipe": None if not fp64 else {k: fp64[k] for k in fp64 if k not in ("sources", "sha1")}}
+
+
+def bench_cfg5(args, rank, world, torch, devapi, bdist, synth):
+    """BASELINE.json config 5: one global 16384 x 16384 grid from 8 scan streams; the streams are split over the ranks
+    (strong scaling) and the int32 count deltas merged over peer memory.  Parity: every rank also ray-casts all 8
+    streams alone and compares the merged occupancy map and its shard of the merged counts byte for byte."""
+    import torch.distributed as dist
+    G, streams, K, N = 16384, 8, args.cfg5_scans, GRID_BEAMS
+    lo, hi = bdist.shard_bounds(streams, rank, world)
+    gen = lambda s: synth.grid_scans(5001 + s, K, N, half_extent_m=380.0)
+    mine = [gen(s) for s in range(lo, hi)]
+    dev = [torch.from_numpy(np.concatenate([p[k] for p in mine])).cuda() for k in range(4)] if mine else None
+    sm = bdist.ShardedMappingP2P(G, G, GRID_RESO)
+    empty = [torch.empty((0, N), dtype=torch.float32, device="cuda"), torch.empty((0, N), dtype=torch.float32, device="cuda"),
+             torch.empty(0, dtype=torch.float32, device="cuda"), torch.empty(0, dtype=torch.float32, device="cuda")]
+    batch = dev if dev is not None else empty
+    sm.update_device(*batch)
+    torch.cuda.synchronize()
+    bdist.barrier()
+    reps = 5
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        sm.update_device(*batch)
+    b.record()
+    torch.cuda.synchronize()
+    sm.check()
+    ms = bdist.max_over_ranks(a.elapsed_time(b)) / reps
+    # parity: all 8 streams in one pass on this GPU, (1 + reps) times like the merged object saw them
+    S, Hx, Hy = devapi.grid_scale(G, G, GRID_RESO)
+    hit, miss = devapi.new_planes(G, G)
+    ws = devapi.new_workspace(G, G)
+    for s in range(streams):
+        one = [torch.from_numpy(a_).cuda() for a_ in (mine[s - lo] if lo <= s < hi else gen(s))]
+        for _ in range(1 + reps):
+            devapi.grid_raycast(hit, miss, S, Hx, Hy, *one, workspace=ws)
+        del one
+    pm = torch.empty((G, G), dtype=torch.int8, device="cuda")
+    devapi.grid_finalize(hit, miss, pmap=pm)
+    torch.cuda.synchronize()
+    n = (sm.tile_hi - sm.tile_lo) * 4096
+    tiles = lambda plane: plane.view(G // 64, 64, G // 64, 64).permute(0, 2, 1, 3).reshape(-1)[sm.tile_lo * 4096:sm.tile_hi * 4096]
+    ok = bool(torch.equal(pm, sm.pmap_dev) and torch.equal(tiles(hit), sm.g_hit[:n]) and torch.equal(tiles(miss), sm.g_miss[:n]))
+    flag = torch.tensor([int(ok)], dtype=torch.int32, device="cuda")
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out = {"workload": "cfg5: global 16384x16384 grid @ 0.05 m from 8 scan streams x %d scans x %d beams, streams split over "
+                       "the ranks, count deltas merged over NVLink peer memory" % (K, N),
+           "value": streams * K * N / (ms * 1e-3), "unit": "beams/s", "ms_per_step": ms, "n_gpus": world, "scaling": "strong",
+           "streams_per_gpu": hi - lo, "occupied_cells": int((pm == 100).sum().item()),
+           "counts_checksum": int(hit.sum(dtype=torch.int64).item() * 1000003 + miss.sum(dtype=torch.int64).item()),
+           "parity": {"ok": bool(flag.item() == 1), "against": "one single-GPU ray-cast pass over all 8 streams, done by every rank",
+                      "compared": "int8 occupancy map on every rank + each rank's shard of the int32 counts, byte for byte"}}
+    sm.close()
+    return out
+
+
 def drop_in_latency(torch, synth):
     """Single-call latency of the reference-signature methods (what a ROS node sees per scan)."""
     import b2slam
@@ -556,8 +751,8 @@ def cpu_baselines(args, synth):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100, help="timed steps (100 x 2.5 ms: a quarter-second timed region)")
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b2slam", choices=["b2slam", "reference"])
     ap.add_argument("--workload", default="grid", choices=["grid", "icp"])
     ap.add_argument("--scans", type=int, default=16384, help="grid scans per GPU per step")
@@ -568,6 +763,8 @@ def main():
     ap.add_argument("--merge", default="p2p", choices=["p2p", "nccl"], help="multi-GPU grid merge")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only", default="both", choices=["both", "primary"])
+    ap.add_argument("--cfg4-pairs", type=int, default=1000000, help="BASELINE.json config 4: total ICP pairs (0 skips it)")
+    ap.add_argument("--cfg5-scans", type=int, default=4096, help="BASELINE.json config 5: scans per stream (0 skips it)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b2slam" else args.warmup
 
@@ -599,6 +796,19 @@ def main():
         torch.cuda.synchronize()
         bdist.barrier()
 
+    extra = {}
+    if args.only == "both":
+        if args.cfg4_pairs > 0:
+            extra["cfg4"] = bench_cfg4(args, rank, world, torch, devapi, bdist)
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+            bdist.barrier()
+        if args.cfg5_scans > 0:
+            extra["cfg5"] = bench_cfg5(args, rank, world, torch, devapi, bdist, synth)
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+            bdist.barrier()
+
     cpu = {}
     latency = None
     if rank == 0 and world == 1 and args.only == "both":
@@ -614,10 +824,12 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": prim["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": prim["dtype"],
             "data": "synthetic", "config": prim["config"], "roofline": prim["roofline"], "e2e": prim["e2e"],
-            **{k: prim[k] for k in ("e2e_fused_ingestion", "e2e_pair_form") if k in prim},
+            **{k: prim[k] for k in ("e2e_fused_ingestion", "e2e_pair_form", "e2e_endpoint_form", "merge_bit_identical",
+                                    "merge_check") if k in prim},
             "gpu_launches": sum(r["gpu_launches"] for r in results.values()), "clocks": prim["clocks"],
             "cpu_baseline": cpu.get(order[0]),
         }
+        line.update(extra)
         if latency:
             line["drop_in_latency_ms"] = latency
         if len(order) > 1:

@@ -215,6 +215,34 @@ int b2s_grid_merge_p2p_tiles(const int32_t *const *delta_hit, const int32_t *con
                              int tile_lo, int tile_hi, int32_t *global_hit_shard,
                              int32_t *global_miss_shard, double w_hit, double w_miss, double thresh,
                              void *stream);
+/* The same step without a collective around it (dist.ShardedMappingP2P, the default): the two rendezvous of the step
+ * -- "every rank's ray-cast is done and its dirty map has arrived" before the merge, "every rank's merge is done"
+ * after it -- are epoch words in CUDA-IPC-mapped flag blocks that the ranks push to each other (st.release.sys) and
+ * wait on locally (ld.acquire.sys), inside the kernels.  Per rank: a flag block of b2s_p2p_flag_bytes(nranks) bytes,
+ * zeroed once, and a table all_dirty [nranks][b2s_p2p_dirty_stride(xw, yw)] for the gathered dirty maps, both
+ * cudaMalloc'ed (b2s_device_alloc) and mapped into every peer; flags[r] / all_dirty[r] are rank r's buffers as seen
+ * from this process.  One step, all on one stream, epoch = 1, 2, 3, ... (the same on every rank):
+ *   b2s_grid_clear_dirty -> b2s_grid_raycast_ws / _ranges (private delta planes)
+ *   -> b2s_p2p_publish                 copies this rank's dirty map into every rank's table and raises ready[rank]
+ *                                      there; counters (may be NULL) = the ray-cast's B2S_CNT_* words, whose error
+ *                                      count travels along
+ *   -> b2s_grid_merge_p2p_tiles_sync   waits for every ready flag inside the kernel, merges as above, and its last
+ *                                      CTA raises done[rank] in every rank's block
+ *   -> b2s_p2p_wait_done               returns (on the stream) once every rank's merge is done: this rank's map is
+ *                                      complete and its delta planes may be cleared.
+ * A wait gives up after 20 s and sets an error word instead of hanging the GPU; b2s_p2p_status copies the error
+ * word and the ranks' dropped-beam counts of the last step to the host (it synchronizes the stream). */
+size_t b2s_p2p_flag_bytes(int nranks);
+size_t b2s_p2p_dirty_stride(int xw, int yw);
+int b2s_p2p_publish(const void *workspace, const int32_t *counters, uint8_t *const *all_dirty, uint32_t *const *flags,
+                    int nranks, int rank, int xw, int yw, uint32_t epoch, void *stream);
+int b2s_grid_merge_p2p_tiles_sync(const int32_t *const *delta_hit, const int32_t *const *delta_miss,
+                                  int8_t *const *pmap, const uint8_t *all_dirty, uint32_t *const *flags, int nranks,
+                                  int rank, uint32_t epoch, int xw, int yw, int tile_lo, int tile_hi,
+                                  int32_t *global_hit_shard, int32_t *global_miss_shard, double w_hit, double w_miss,
+                                  double thresh, void *stream);
+int b2s_p2p_wait_done(uint32_t *my_flags, int nranks, uint32_t epoch, void *stream);
+int b2s_p2p_status(const uint32_t *my_flags, int nranks, int *timed_out, int64_t *dropped_beams, void *stream);
 void *b2s_grid_workspace_dirty(void *workspace);
 int b2s_grid_tile_count(int xw, int yw, int *tiles_x, int *tiles_y);
 int b2s_grid_clear_dirty(int32_t *hit, int32_t *miss, int xw, int yw, void *workspace, void *stream);

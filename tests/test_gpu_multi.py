@@ -1,5 +1,6 @@
-"""Multi-GPU path on real devices (skipped with fewer than 2 GPUs): torchrun, NCCL all-reduce of the
-int32 count deltas, rank-sharded ICP pairs.  The single-GPU emulation of the same logic is in
+"""Multi-GPU path on real devices (world sizes 2, 4, 8; skipped where the box has fewer GPUs): torchrun, NCCL all-reduce
+of the int32 count deltas, the peer-memory merge in all its forms (flag-synchronised, NCCL-fenced, dense), rank-sharded
+ICP pairs.  Every merged grid must be bit-identical to ONE pass over all streams (the CPU oracle).  The single-GPU emulation of the same logic is in
 test_gpu_grid.py::test_cfg3_full_size_properties; the gloo version in test_dist_gloo.py."""
 import os
 import subprocess
@@ -31,13 +32,36 @@ for rnd in range(2):
     pm = sm.update_batch(ox, oy, cx, cy)
 hit, miss = sm.counts()
 res = {}
-for tag, sparse in (("2", True), ("3", False)):       # tile-sparse and dense forms of the fused merge
-    p2p = bdist.ShardedMappingP2P(G, G, 0.05, sparse=sparse)
-    for rnd in range(2):
+ROUNDS = 2
+# tile-sparse merge synchronised by flag words in peer memory (default), the same kernel fenced by NCCL, the dense kernel
+for tag, sparse, fence in (("2", True, "flags"), ("3", False, "nccl"), ("4", True, "nccl")):
+    p2p = bdist.ShardedMappingP2P(G, G, 0.05, sparse=sparse, fence=fence)
+    assert p2p.flags_mode == (fence == "flags")
+    for rnd in range(ROUNDS):
         parts = [synth.grid_scans(5001 + s + 100 * rnd, 24, 1080, half_extent_m=40.0) for s in range(lo, hi)]
         ox, oy, cx, cy = (np.concatenate([p[k] for p in parts]) for k in range(4))
         res["pm" + tag] = p2p.update_batch(ox, oy, cx, cy).copy()
     res["hit" + tag], res["miss" + tag] = p2p.counts()
+    if fence == "flags":
+        # many short steps back to back, device-resident inputs: the epochs must keep the ranks in lock step without
+        # any host-side collective (a rank that ran ahead would clear planes a peer still reads)
+        small = [torch.from_numpy(a).cuda() for a in synth.grid_scans(900 + rank, 8, 1080, half_extent_m=40.0)]
+        for k in range(40):
+            p2p.update_device(*small)
+        p2p.check()
+        res["hit5"], res["miss5"] = p2p.counts()
+        torch.cuda.synchronize()
+        res["pm5"] = p2p.pmap_dev.cpu().numpy()
+        # a NaN on ONE rank must raise on EVERY rank (the dropped-beam counts travel with the ready flags)
+        bad = [t.clone() for t in small]
+        if rank == world - 1:
+            bad[1][3, 5] = float("nan")
+        p2p.update_device(*bad)
+        try:
+            p2p.check()
+            res["raised"] = np.array(0)
+        except ValueError:
+            res["raised"] = np.array(1)
     p2p.close()
 # the library's own NCCL plumbing (dlopen'ed libnccl): communicator from a broadcast unique id, in-place all-reduce
 import ctypes
@@ -72,14 +96,15 @@ torch.distributed.destroy_process_group()
 '''
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
-def test_two_gpu_grid_merge_and_icp_sharding(tmp_path):
-    world = 2
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_grid_merge_and_icp_sharding(tmp_path, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs, the box has %d" % (world, torch.cuda.device_count()))
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     env = dict(os.environ, B2S_ROOT=ROOT, B2S_OUT=str(tmp_path))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-           "--master-addr", "127.0.0.1", "--master-port", "29733", str(script)]
+           "--master-addr", "127.0.0.1", "--master-port", str(29733 + world), str(script)]
     subprocess.run(cmd, check=True, env=env, timeout=600)
     from oracle import corc
     import b2slam.synth as synth
@@ -98,9 +123,24 @@ def test_two_gpu_grid_merge_and_icp_sharding(tmp_path):
         assert np.array_equal(z["hit"], oh) and np.array_equal(z["miss"], om)   # bit-identical to one pass
         assert np.array_equal(z["pm"], corc.grid_finalize(oh, om)[1])
         # fused peer-memory merge: same counts (sharded across ranks), same map on every rank
-        for tag in ("2", "3"):
+        for tag in ("2", "3", "4"):
             assert np.array_equal(z["hit" + tag], oh) and np.array_equal(z["miss" + tag], om), tag
             assert np.array_equal(z["pm" + tag], corc.grid_finalize(oh, om)[1]), tag
+        assert int(z["raised"]) == 1, "rank %d did not see the NaN of the last rank" % r
+    # the 40 back-to-back flag-synchronised steps: every rank's 8 scans, 40 times, on top of the two rounds
+    o5h, o5m = oh.copy(), om.copy()
+    for q in range(world):
+        th = np.zeros((G, G), dtype=np.int32)
+        tm = np.zeros((G, G), dtype=np.int32)
+        corc.grid_raycast(th, tm, S, Hx, Hy, *synth.grid_scans(900 + q, 8, 1080, half_extent_m=40.0))
+        o5h += 40 * th
+        o5m += 40 * tm
+    for r in range(world):
+        z = np.load(tmp_path / ("rank%d.npz" % r))
+        assert np.array_equal(z["hit5"], o5h) and np.array_equal(z["miss5"], o5m)
+        assert np.array_equal(z["pm5"], corc.grid_finalize(o5h, o5m)[1])
+    for r in range(world):
+        z = np.load(tmp_path / ("rank%d.npz" % r))
         np.testing.assert_allclose(z["T"], want_T, rtol=0, atol=1e-9)
         assert (z["nccl_hit"] == sum(range(1, world + 1))).all() and (z["nccl_miss"] == 10 * sum(range(1, world + 1))).all()
 
