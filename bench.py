@@ -771,8 +771,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    # keep stdout to the one JSON line: NCCL's version / debug banner goes to stderr
+    # keep stdout to the one JSON line: whatever the libraries print (NCCL's version banner, warnings) goes to
+    # stderr -- at the file-descriptor level, since NCCL writes from C -- until the line itself is printed
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     from b2slam import _lib, devapi, synth
     from b2slam import dist as bdist
@@ -836,7 +840,10 @@ def main():
             sec = results[order[1]]
             sec["cpu_baseline"] = cpu.get(order[1])
             line[order[1]] = sec
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

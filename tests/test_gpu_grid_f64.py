@@ -46,7 +46,7 @@ def test_layer1_float64_raycast_equals_reference(env, tag):
     ox, oy, cx, cy = (torch.from_numpy(np.ascontiguousarray(z[tag + k])).cuda() for k in ("_ox", "_oy", "_cx", "_cy"))
     assert ox.dtype == torch.float64
     ws = env.dev.new_workspace(side, side)
-    variants = (1, 2, 3, 4) if side <= 4096 else (4,)
+    variants = (1, 2, 3, 4, 5) if side <= 4096 else (4, 5)
     try:
         for v in variants:
             assert env.lib.lib().b2s_tune(b"grid_variant", v) == 0
@@ -67,7 +67,7 @@ def test_layer1_float64_raycast_equals_reference(env, tag):
                 assert (pmh[rest] == 50).all()
                 del hit, miss, pm
     finally:
-        env.lib.lib().b2s_tune(b"grid_variant", 4)
+        env.lib.lib().b2s_tune(b"grid_variant", 5)
 
 
 @pytest.mark.parametrize("w_hit,suffix", [(20.0, ""), (4.0, "_w4")])
