@@ -34,6 +34,46 @@ inline int cuda_fail(cudaError_t e, const char *what)
 
 int sm_count();
 
+// Growable device / pinned-host staging buffer.
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return B2S_OK;
+        release();
+        size_t want = bytes + bytes / 4;
+        cudaError_t e = pinned ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            cap = 0;
+            set_error("allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+            return e == cudaErrorMemoryAllocation ? B2S_ERR_NOMEM : B2S_ERR_CUDA;
+        }
+        cap = want;
+        return B2S_OK;
+    }
+    void release()
+    {
+        if (p) {
+            if (pinned) cudaFreeHost(p); else cudaFree(p);
+        }
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// Per-thread, per-device scratch for the small host-buffer calls (pose chain, virtual scan, Bresenham paths): they are
+// made once per scan by a node, so their device buffers are kept and grown instead of cudaMalloc'ed per call.
+// Never freed (the CUDA context may be gone by the time thread-local destructors run).
+struct ScratchPool {
+    int device = -1;
+    Buf a, b, c;
+};
+ScratchPool *scratch_pool();  // bound to the calling thread's current device; nullptr on a CUDA error
+
+
 // Dirty-tile bookkeeping of the ray-cast workspace: one byte per 64 x 64-cell tile of the grid.
 constexpr int GRID_TILE = 64;
 constexpr int GRID_WS_HEADER = 64;

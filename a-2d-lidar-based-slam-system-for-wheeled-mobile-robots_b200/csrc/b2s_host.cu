@@ -45,35 +45,27 @@ constexpr int MAX_CHUNKS = 16;
 int g_tune_gen = 0;    // bumped by every b2s_tune: cached single-pair graphs captured under other settings are stale
 int g_h2d_chunks = 0;  // 0: automatic; 1..MAX_CHUNKS force the pipeline depth of the host-buffer calls (tuning hook)
 
-// Growable device / pinned-host staging buffer.
-struct Buf {
-    void *p = nullptr;
-    size_t cap = 0;
-    bool pinned = false;
-    int reserve(size_t bytes)
-    {
-        if (bytes <= cap) return B2S_OK;
-        release();
-        size_t want = bytes + bytes / 4;
-        cudaError_t e = pinned ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
-        if (e != cudaSuccess) {
-            p = nullptr;
-            cap = 0;
-            set_error("allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
-            return e == cudaErrorMemoryAllocation ? B2S_ERR_NOMEM : B2S_ERR_CUDA;
+ScratchPool *scratch_pool()
+{
+    static thread_local ScratchPool *pool = nullptr;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    if (!pool) pool = new (std::nothrow) ScratchPool();
+    if (!pool) return nullptr;
+    if (pool->device != dev) {  // the thread moved to another GPU: its buffers live on the old one
+        if (pool->device >= 0 && cudaSetDevice(pool->device) == cudaSuccess) {
+            pool->a.release();
+            pool->b.release();
+            pool->c.release();
+            cudaSetDevice(dev);
         }
-        cap = want;
-        return B2S_OK;
+        pool->a = Buf();
+        pool->b = Buf();
+        pool->c = Buf();
+        pool->device = dev;
     }
-    void release()
-    {
-        if (p) {
-            if (pinned) cudaFreeHost(p); else cudaFree(p);
-        }
-        p = nullptr;
-        cap = 0;
-    }
-};
+    return pool;
+}
 
 struct DeviceGuard {
     int prev = -1;
@@ -1072,23 +1064,21 @@ extern "C" int b2s_bresenham_host(const int32_t *segs, int count, const int64_t 
     B2S_REQUIRE(segs && offsets, "b2s_bresenham_host: null pointer");
     const int64_t total = offsets[count];
     B2S_REQUIRE(total >= 0 && (total == 0 || cells_xy), "b2s_bresenham_host: bad offsets");
-    int32_t *d_segs = nullptr, *d_cells = nullptr;
-    int64_t *d_off = nullptr;
-    cudaError_t e = cudaMalloc((void **)&d_segs, (size_t)count * 16);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_off, (size_t)(count + 1) * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_cells, (size_t)(total > 0 ? total : 1) * 8);
-    if (e == cudaSuccess) e = cudaMemcpy(d_segs, segs, (size_t)count * 16, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d_off, offsets, (size_t)(count + 1) * 8, cudaMemcpyHostToDevice);
-    int rc = B2S_OK;
-    if (e == cudaSuccess) rc = b2s_bresenham_paths(d_segs, count, d_off, d_cells, nullptr);
-    if (e == cudaSuccess && rc == B2S_OK) e = cudaDeviceSynchronize();
-    if (e == cudaSuccess && rc == B2S_OK && total > 0)
-        e = cudaMemcpy(cells_xy, d_cells, (size_t)total * 8, cudaMemcpyDeviceToHost);
-    cudaFree(d_segs);
-    cudaFree(d_off);
-    cudaFree(d_cells);
-    if (e != cudaSuccess) return cuda_fail(e, "b2s_bresenham_host");
-    return rc;
+    ScratchPool *sp = scratch_pool();
+    if (!sp) return cuda_fail(cudaErrorUnknown, "b2s_bresenham_host: no device");
+    int rc;
+    if ((rc = sp->a.reserve((size_t)count * 16))) return rc;
+    if ((rc = sp->b.reserve((size_t)(count + 1) * 8))) return rc;
+    if ((rc = sp->c.reserve((size_t)(total > 0 ? total : 1) * 8))) return rc;
+    B2S_CUDA(cudaMemcpyAsync(sp->a.p, segs, (size_t)count * 16, cudaMemcpyHostToDevice, cudaStreamPerThread));
+    B2S_CUDA(cudaMemcpyAsync(sp->b.p, offsets, (size_t)(count + 1) * 8, cudaMemcpyHostToDevice, cudaStreamPerThread));
+    if ((rc = b2s_bresenham_paths((const int32_t *)sp->a.p, count, (const int64_t *)sp->b.p, (int32_t *)sp->c.p,
+                                  cudaStreamPerThread)))
+        return rc;
+    if (total > 0)
+        B2S_CUDA(cudaMemcpyAsync(cells_xy, sp->c.p, (size_t)total * 8, cudaMemcpyDeviceToHost, cudaStreamPerThread));
+    B2S_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
+    return B2S_OK;
 }
 
 // ------------------------------------------------------------------------------ NCCL (dlopen)

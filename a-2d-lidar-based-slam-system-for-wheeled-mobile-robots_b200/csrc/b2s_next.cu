@@ -141,17 +141,16 @@ extern "C" int b2s_virtual_scan(const double *obs_x, const double *obs_y, int co
 extern "C" int b2s_pose_chain_host(const double *T, int pairs, double x0, double y0, double th0, double *traj)
 {
     B2S_REQUIRE(pairs >= 0 && traj && (T || pairs == 0), "b2s_pose_chain_host: bad arguments");
-    double *dT = nullptr, *dtraj = nullptr;
-    cudaError_t e = cudaMalloc((void **)&dT, (size_t)(pairs > 0 ? pairs : 1) * 72);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&dtraj, (size_t)(pairs + 1) * 24);
-    if (e == cudaSuccess && pairs > 0) e = cudaMemcpy(dT, T, (size_t)pairs * 72, cudaMemcpyHostToDevice);
-    int rc = B2S_OK;
-    if (e == cudaSuccess) rc = b2s_pose_chain(dT, pairs, x0, y0, th0, dtraj, nullptr);
-    if (e == cudaSuccess && rc == B2S_OK) e = cudaMemcpy(traj, dtraj, (size_t)(pairs + 1) * 24, cudaMemcpyDeviceToHost);
-    cudaFree(dT);
-    cudaFree(dtraj);
-    if (e != cudaSuccess) return cuda_fail(e, "b2s_pose_chain_host");
-    return rc;
+    ScratchPool *sp = scratch_pool();
+    if (!sp) return cuda_fail(cudaErrorUnknown, "b2s_pose_chain_host: no device");
+    int rc;
+    if ((rc = sp->a.reserve((size_t)(pairs > 0 ? pairs : 1) * 72))) return rc;
+    if ((rc = sp->b.reserve((size_t)(pairs + 1) * 24))) return rc;
+    if (pairs > 0) B2S_CUDA(cudaMemcpyAsync(sp->a.p, T, (size_t)pairs * 72, cudaMemcpyHostToDevice, cudaStreamPerThread));
+    if ((rc = b2s_pose_chain((const double *)sp->a.p, pairs, x0, y0, th0, (double *)sp->b.p, cudaStreamPerThread))) return rc;
+    B2S_CUDA(cudaMemcpyAsync(traj, sp->b.p, (size_t)(pairs + 1) * 24, cudaMemcpyDeviceToHost, cudaStreamPerThread));
+    B2S_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
+    return B2S_OK;
 }
 
 extern "C" int b2s_virtual_scan_host(const double *obs_x, const double *obs_y, int count, double x, double y,
@@ -159,22 +158,23 @@ extern "C" int b2s_virtual_scan_host(const double *obs_x, const double *obs_y, i
                                      double far_range, double *ranges)
 {
     B2S_REQUIRE(count >= 0 && beams > 0 && ranges && (count == 0 || (obs_x && obs_y)), "b2s_virtual_scan_host: bad arguments");
-    double *dx = nullptr, *dy = nullptr, *dr = nullptr;
+    ScratchPool *sp = scratch_pool();
+    if (!sp) return cuda_fail(cudaErrorUnknown, "b2s_virtual_scan_host: no device");
     const size_t ob = (size_t)(count > 0 ? count : 1) * 8;
-    cudaError_t e = cudaMalloc((void **)&dx, ob);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&dy, ob);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&dr, (size_t)beams * 8);
-    if (e == cudaSuccess && count > 0) e = cudaMemcpy(dx, obs_x, (size_t)count * 8, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && count > 0) e = cudaMemcpy(dy, obs_y, (size_t)count * 8, cudaMemcpyHostToDevice);
-    int rc = B2S_OK;
-    if (e == cudaSuccess)
-        rc = b2s_virtual_scan(dx, dy, count, x, y, yaw, angle_min, angle_increment, beams, far_range, dr, nullptr);
-    if (e == cudaSuccess && rc == B2S_OK) e = cudaMemcpy(ranges, dr, (size_t)beams * 8, cudaMemcpyDeviceToHost);
-    cudaFree(dx);
-    cudaFree(dy);
-    cudaFree(dr);
-    if (e != cudaSuccess) return cuda_fail(e, "b2s_virtual_scan_host");
-    return rc;
+    int rc;
+    if ((rc = sp->a.reserve(ob))) return rc;
+    if ((rc = sp->b.reserve(ob))) return rc;
+    if ((rc = sp->c.reserve((size_t)beams * 8))) return rc;
+    if (count > 0) {
+        B2S_CUDA(cudaMemcpyAsync(sp->a.p, obs_x, (size_t)count * 8, cudaMemcpyHostToDevice, cudaStreamPerThread));
+        B2S_CUDA(cudaMemcpyAsync(sp->b.p, obs_y, (size_t)count * 8, cudaMemcpyHostToDevice, cudaStreamPerThread));
+    }
+    if ((rc = b2s_virtual_scan((const double *)sp->a.p, (const double *)sp->b.p, count, x, y, yaw, angle_min, angle_increment,
+                               beams, far_range, (double *)sp->c.p, cudaStreamPerThread)))
+        return rc;
+    B2S_CUDA(cudaMemcpyAsync(ranges, sp->c.p, (size_t)beams * 8, cudaMemcpyDeviceToHost, cudaStreamPerThread));
+    B2S_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
+    return B2S_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -18,11 +18,65 @@ def env_world():
             int(os.environ.get("WORLD_SIZE", 1)))
 
 
+def gpu_numa_node(index):
+    """NUMA node the GPU hangs off (sysfs numa_node of its PCI function), or None when the platform does not say."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(int(index))).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:        # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as fh:
+            node = int(fh.read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def _cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        elif part:
+            cpus.add(int(part))
+    return cpus
+
+
+def bind_to_gpu_numa(index):
+    """Pin this process to the CPUs of its GPU's NUMA node, BEFORE it allocates page-locked staging memory: pages are
+    placed on the node of the thread that first touches them, and a host-to-device copy that has to cross the
+    socket interconnect runs at a fraction of the PCIe rate once several ranks do it at the same time.  Only ever
+    narrows the affinity the launcher gave us; a no-op on single-node hosts, or when sysfs / NVML do not answer,
+    or with B2S_NUMA_BIND=0.  Returns the node, or None."""
+    if os.environ.get("B2S_NUMA_BIND", "1") == "0":
+        return None
+    node = gpu_numa_node(index)
+    if node is None:
+        return None
+    try:
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+            cpus = _cpulist(fh.read())
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def init(backend=None):
-    """Bind this process to its GPU and join the process group (no-op for world size 1)."""
+    """Bind this process to its GPU (and to the CPUs of that GPU's NUMA node) and join the process group (no-op for
+    world size 1)."""
     rank, local_rank, world = env_world()
     if torch.cuda.is_available():
         torch.cuda.set_device(local_rank)
+        if world > 1:
+            bind_to_gpu_numa(local_rank)
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
@@ -133,6 +187,51 @@ class ShardedMapping(object):
         return self.hit.cpu().numpy(), self.miss.cpu().numpy()
 
 
+class _Slot(object):
+    """Buffers of one in-flight host-buffer step of ShardedMappingP2P (there are two)."""
+
+    def __init__(self, xw, yw, flag_words):
+        self.stage = torch.empty((xw, yw), dtype=torch.int8, device="cuda")       # private copy of the merged map
+        self.pmap_host = torch.empty((xw, yw), dtype=torch.int8).pin_memory()
+        self.flags_dev = torch.zeros(max(flag_words, 1), dtype=torch.int32, device="cuda")
+        self.flags_host = torch.zeros(max(flag_words, 1), dtype=torch.int32).pin_memory()
+        self.pose4_host = None
+        self._dev = {}
+        self.inputs_free = None
+        self.done = None
+        self.ticket = None
+
+    def inputs(self, kind, shapes):
+        """Device input buffers of this slot for the given call form and shapes (allocated on first use / on a change)."""
+        have = self._dev.get(kind)
+        if have is None or [tuple(t.shape) for t in have] != [tuple(sh) for sh in shapes]:
+            dt = [torch.float32] * len(shapes) if kind == "xy" else [torch.float32, torch.float64]
+            have = [torch.empty(sh, dtype=d, device="cuda") for sh, d in zip(shapes, dt)]
+            self._dev[kind] = have
+            if kind == "ranges":
+                self.pose4_host = torch.empty(shapes[1], dtype=torch.float64).pin_memory()
+        return have
+
+
+class Ticket(object):
+    """Handle of a submitted step (ShardedMappingP2P.submit_batch / submit_scans)."""
+
+    def __init__(self, owner, slot):
+        self._owner, self._slot = owner, slot
+
+    def wait(self):
+        """Block until this step's merged map is in host memory; raises what check() raises for this step.  The returned
+        int8 (xw, yw) array is a view of a page-locked buffer that the second-next submit overwrites."""
+        slot, owner = self._slot, self._owner
+        if slot.ticket is self:
+            slot.done.synchronize()
+            slot.ticket = None
+            owner.pmap_host = slot.pmap_host
+            if owner.flags_mode:
+                owner._raise_for(slot.flags_host.tolist())
+        return slot.pmap_host.numpy()
+
+
 class ShardedMappingP2P(object):
     """ShardedMapping with the merge fused over NVLink peer memory (b2s_grid_merge_p2p).
 
@@ -236,12 +335,15 @@ class ShardedMappingP2P(object):
             self.dirty = devapi.tensor_from_ptr(dptr, (self.ntiles,), torch.uint8)
             if not self.flags_mode:
                 self.all_dirty = torch.zeros(self.world * self.ntiles, dtype=torch.uint8, device="cuda")
-        self.pmap_host = torch.empty((self.xw, self.yw), dtype=torch.int8).pin_memory()
         self._token = torch.zeros(1, dtype=torch.int32, device="cuda")
-        self._in = None
-        self._in_r = None
+        # two slots of everything a host-buffer call owns (device input buffers, a private device copy of the merged
+        # map, page-locked result buffers), so that call k + 1 can be submitted while call k is still being read back
+        self._slots = [_Slot(self.xw, self.yw, self.flag_words if self.flags_mode else 0) for _ in range(2)]
+        self._calls = 0
+        self.pmap_host = self._slots[0].pmap_host          # the most recent synchronous result
         self._beam_key = None
         self._copy_stream = None
+        self._d2h_stream = None
         self.h2d_chunks = 0   # 0: automatic pipeline depth of the host-buffer calls; > 0 forces it
         torch.cuda.synchronize()
         barrier()
@@ -300,6 +402,16 @@ class ShardedMappingP2P(object):
     def _counters(self):
         return self.counters if self.flags_mode else None
 
+    def _raise_for(self, words):
+        """words: the flag block (host ints) as it stood when a step's merge had finished."""
+        R = self.world
+        if words[3 * R + 1]:
+            raise RuntimeError("a peer did not reach the merge within the time limit (rank %d)" % self.rank)
+        bad = int(sum(int(w) & 0xffffffff for w in words[2 * R:3 * R]))
+        if bad:
+            raise ValueError("%d beam(s) with a NaN / inf coordinate or longer than the limit were dropped by some rank; "
+                             "the merged grid of this step is incomplete" % bad)
+
     def check(self):
         """Raise on EVERY rank if any rank dropped beams in the last step (NaN / inf coordinates or over-long beams:
         what Mapping.update_batch raises ValueError / OverflowError for) or if a flag wait timed out.  The counts of
@@ -329,72 +441,114 @@ class ShardedMappingP2P(object):
             events[1].record()
         self._merge()
 
-    def _pipeline(self, host, dev, scans, beams, raycast):
-        """Chunked H2D on a side stream overlapped with the ray-cast of the previous chunk (the host-buffer calls
-        of Mapping do the same inside the library), then the merge and the read-back of the map."""
+    def _submit(self, kind, host, shapes, scans, beams, make_raycast, prepare=None):
+        """One host-buffer step, enqueued and NOT waited for: chunked H2D on a side stream overlapped with the ray-cast
+        of the previous chunk, the merge, a device-side copy of the merged map into the slot's private buffer, and its
+        read-back on a third stream.  Returns the slot's Ticket.  The next submit may follow immediately: its uploads
+        and ray-casts run while this step's map is still crossing PCIe in the other direction.
+        prepare(lo, hi) builds chunk [lo, hi) of a derived host table right before it is copied."""
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream()
+            self._d2h_stream = torch.cuda.Stream()
         main = torch.cuda.current_stream()
-        nchunk = self.h2d_chunks or max(1, min(8, (scans * beams + (1 << 21) - 1) >> 21))   # ~2M beams per chunk
+        slot = self._slots[self._calls % 2]
+        self._calls += 1
+        if slot.ticket is not None:          # its buffers are about to be reused
+            slot.ticket.wait()
+        dev = slot.inputs(kind, shapes)
+        if slot.inputs_free is not None:     # the ray-casts that last read these device buffers (two submits ago)
+            self._copy_stream.wait_event(slot.inputs_free)
+        raycast = make_raycast(dev)
+        # a step submitted while the previous one is still in flight has its whole upload hidden under that step's
+        # ray-cast, so it goes as ONE launch; a step that starts on an idle device is cut into chunks (~2M beams) so that
+        # the ray-cast can start after the first of them
+        streaming = any(sl.ticket is not None for sl in self._slots if sl is not slot)
+        nchunk = self.h2d_chunks or (1 if streaming else max(1, min(8, (scans * beams + (1 << 21) - 1) >> 21)))
         nchunk = max(1, min(nchunk, scans))
         bounds = [scans * k // nchunk for k in range(nchunk + 1)]
-        self._copy_stream.wait_stream(main)   # the device input buffers are free once earlier work is done
-        ready = []
-        with torch.cuda.stream(self._copy_stream):
-            for k in range(nchunk):
-                lo, hi = bounds[k], bounds[k + 1]
-                for d, h in zip(dev, host):
+        self._begin()
+        for k in range(nchunk):
+            lo, hi = bounds[k], bounds[k + 1]
+            if prepare is not None:
+                prepare(slot, lo, hi)
+            with torch.cuda.stream(self._copy_stream):
+                for d, h in zip(dev, host(slot)):
                     d[lo:hi].copy_(h[lo:hi], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self._copy_stream)
-                ready.append(ev)
-        self._begin()
-        for k in range(nchunk):
-            main.wait_event(ready[k])
-            raycast(bounds[k], bounds[k + 1])
+            main.wait_event(ev)
+            raycast(lo, hi)
+        slot.inputs_free = torch.cuda.Event()
+        slot.inputs_free.record(main)
         self._merge()
-        self.pmap_host.copy_(self.pmap_dev, non_blocking=True)
-        main.synchronize()
-        self.check()
-        return self.pmap_host.numpy()
+        # the merged map is complete here (wait_done); peers overwrite pmap_dev only after this rank's NEXT ready flag,
+        # which is behind this copy in stream order -- so the read-back below never sees a torn map
+        slot.stage.copy_(self.pmap_dev, non_blocking=True)
+        if self.flags_mode:
+            slot.flags_dev.copy_(self.flags, non_blocking=True)
+        merged = torch.cuda.Event()
+        merged.record(main)
+        with torch.cuda.stream(self._d2h_stream):
+            self._d2h_stream.wait_event(merged)
+            slot.pmap_host.copy_(slot.stage, non_blocking=True)
+            if self.flags_mode:
+                slot.flags_host.copy_(slot.flags_dev, non_blocking=True)
+            slot.done = torch.cuda.Event()
+            slot.done.record(self._d2h_stream)
+        slot.ticket = Ticket(self, slot)
+        return slot.ticket
+
+    def submit_batch(self, ox, oy, cx, cy):
+        """update_batch without the wait: returns a Ticket whose wait() gives the merged int8 occupancy of this step.
+        Up to two steps may be in flight; the input arrays must stay untouched until the ticket has been waited for."""
+        host_arrays = [torch.from_numpy(a) if not isinstance(a, torch.Tensor) else a for a in (ox, oy, cx, cy)]
+        K, N = host_arrays[0].shape
+        S, Hx, Hy = self.scale
+
+        def make_raycast(d):
+            def raycast(lo, hi):
+                self._dev.grid_raycast(self.d_hit, self.d_miss, S, Hx, Hy, d[0][lo:hi], d[1][lo:hi], d[2][lo:hi],
+                                       d[3][lo:hi], counters=self._counters(), workspace=self.workspace)
+            return raycast
+        return self._submit("xy", lambda slot: host_arrays, [tuple(h.shape) for h in host_arrays], K, N, make_raycast)
 
     def update_batch(self, ox, oy, cx, cy):
         """ox, oy (K,N), cx, cy (K,) float32 host arrays -> merged int8 occupancy (host, pinned)."""
-        host = [torch.from_numpy(a) if not isinstance(a, torch.Tensor) else a for a in (ox, oy, cx, cy)]
-        if self._in is None or self._in[0].shape != host[0].shape:
-            self._in = [torch.empty(h.shape, dtype=torch.float32, device="cuda") for h in host]
-        d = self._in
-        S, Hx, Hy = self.scale
+        return self.submit_batch(ox, oy, cx, cy).wait()
 
-        def raycast(lo, hi):
-            self._dev.grid_raycast(self.d_hit, self.d_miss, S, Hx, Hy, d[0][lo:hi], d[1][lo:hi], d[2][lo:hi], d[3][lo:hi],
-                                   counters=self._counters(), workspace=self.workspace)
-        return self._pipeline(host, d, host[0].shape[0], host[0].shape[1], raycast)
-
-    def update_scans(self, ranges, poses, angle_min, angle_max, clamp_inf_to=30.0):
-        """Fused ingestion (Mapping.update_scans) for this rank's stream: ranges (K,N) float32 + poses (K,3) instead
-        of world-frame endpoints, half the bytes over PCIe.  Returns the merged int8 occupancy (host, pinned)."""
+    def submit_scans(self, ranges, poses, angle_min, angle_max, clamp_inf_to=30.0):
+        """update_scans without the wait (see submit_batch)."""
         import numpy as np
         from b2slam import scan
         ranges = torch.from_numpy(np.ascontiguousarray(ranges, dtype=np.float32)) if not isinstance(ranges, torch.Tensor) else ranges
-        pose4 = torch.from_numpy(scan.pose_table(poses))
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 3)
         K, N = ranges.shape
-        if pose4.shape[0] != K:
-            raise ValueError("need one pose per scan, got %d poses for %d scans" % (pose4.shape[0], K))
+        if poses.shape[0] != K:
+            raise ValueError("need one pose per scan, got %d poses for %d scans" % (poses.shape[0], K))
         key = (float(angle_min), float(angle_max), N)
         if self._beam_key != key:
             self._beam_cs = torch.from_numpy(scan.beam_table(angle_min, angle_max, N)).cuda()
             self._beam_key = key
-        if self._in_r is None or self._in_r[0].shape != ranges.shape:
-            self._in_r = [torch.empty((K, N), dtype=torch.float32, device="cuda"),
-                          torch.empty((K, 4), dtype=torch.float64, device="cuda")]
-        d = self._in_r
         S, Hx, Hy = self.scale
 
-        def raycast(lo, hi):
-            self._dev.grid_raycast_ranges(self.d_hit, self.d_miss, S, Hx, Hy, d[0][lo:hi], d[1][lo:hi], self._beam_cs,
-                                          clamp_inf_to, counters=self._counters(), workspace=self.workspace)
-        return self._pipeline([ranges, pose4], d, K, N, raycast)
+        def prepare(slot, lo, hi):
+            # u2T's cos / sin of the yaw (slam_ekf.py:130-137) for this chunk, while the previous one is in flight
+            table = slot.pose4_host.numpy()
+            table[lo:hi, 0:2] = poses[lo:hi, 0:2]
+            np.cos(poses[lo:hi, 2], out=table[lo:hi, 2])
+            np.sin(poses[lo:hi, 2], out=table[lo:hi, 3])
+
+        def make_raycast(d):
+            def raycast(lo, hi):
+                self._dev.grid_raycast_ranges(self.d_hit, self.d_miss, S, Hx, Hy, d[0][lo:hi], d[1][lo:hi], self._beam_cs,
+                                              clamp_inf_to, counters=self._counters(), workspace=self.workspace)
+            return raycast
+        return self._submit("ranges", lambda slot: [ranges, slot.pose4_host], [(K, N), (K, 4)], K, N, make_raycast, prepare)
+
+    def update_scans(self, ranges, poses, angle_min, angle_max, clamp_inf_to=30.0):
+        """Fused ingestion (Mapping.update_scans) for this rank's stream: ranges (K,N) float32 + poses (K,3) instead
+        of world-frame endpoints, half the bytes over PCIe.  Returns the merged int8 occupancy (host, pinned)."""
+        return self.submit_scans(ranges, poses, angle_min, angle_max, clamp_inf_to).wait()
 
     def counts(self):
         """Full (hit, miss) planes assembled from the ranks' shards (for checks; not a hot path)."""
@@ -419,6 +573,12 @@ class ShardedMappingP2P(object):
         return out[0], out[1]
 
     def close(self):
+        for slot in self._slots:
+            if slot.ticket is not None:
+                try:
+                    slot.ticket.wait()
+                except Exception:
+                    pass
         torch.cuda.synchronize()
         barrier()
         L = self._lib.lib()

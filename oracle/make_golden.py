@@ -411,6 +411,57 @@ def ingestion_golden():
     print("ingestion: occupied", int((np.array(pm) == 100).sum()))
 
 
+def next_rows_golden():
+    """(viii) the two "next" rows of SURVEY section 8f that had only the oracle behind them:
+    f-2  the odometry chain of ICP.publishResult ([ICP]:181-190): the reference's own method, called T by T on a stream
+         of transforms, sensor_sta read back after every call;
+    f-4  the virtual scan Localization.laserEstimation (W9 localization.py:128-150): the reference's own function on a
+         duck-typed node (obstacle cells, xEst) and scan message."""
+    import math
+    import types as _types
+    rng = np.random.Generator(np.random.PCG64(8701))
+    blob = {}
+    # ---- f-2
+    cls = ref_loader.load_icp_class({"/icp/robot_x": 0.25, "/icp/robot_y": -1.5, "/icp/robot_theta": 0.4})
+    icp = cls()
+    n = 400
+    th = rng.uniform(-0.08, 0.08, n)
+    th[::37] = rng.uniform(-math.pi, math.pi, len(th[::37]))       # a few large turns: the yaw leaves (-pi, pi] and keeps growing
+    tx, ty = rng.uniform(-0.15, 0.15, n), rng.uniform(-0.15, 0.15, n)
+    T = np.zeros((n, 3, 3))
+    T[:, 0, 0], T[:, 0, 1], T[:, 0, 2] = np.cos(th), -np.sin(th), tx
+    T[:, 1, 0], T[:, 1, 1], T[:, 1, 2] = np.sin(th), np.cos(th), ty
+    T[:, 2, 2] = 1.0
+    traj = [list(icp.sensor_sta)]
+    for k in range(n):
+        icp.publishResult(T[k])
+        traj.append([float(v) for v in icp.sensor_sta])
+    blob.update(chain_T=T, chain_start=np.array(traj[0], dtype=np.float64), chain_traj=np.array(traj, dtype=np.float64))
+    # ---- f-4
+    Localization = ref_loader.load_localization_class()
+    cases = []
+    for c, (beams, cells) in enumerate(((120, 900), (360, 4000), (1080, 20000), (90, 0))):
+        amin = -math.pi if c != 1 else -2.0
+        amax = math.pi if c != 1 else 2.5
+        ox = rng.uniform(-12, 12, cells)
+        oy = rng.uniform(-12, 12, cells)
+        if cells:
+            ox[:5], oy[:5] = 100.0, 100.0                       # farther than the 100.0 the empty bins hold
+        pose = np.array([rng.uniform(-3, 3), rng.uniform(-3, 3), rng.uniform(-math.pi, math.pi)])
+        msg = _types.SimpleNamespace(ranges=[1.0] * beams, angle_min=amin, angle_max=amax,
+                                     angle_increment=(amax - amin) / (beams - 1))
+        node = _types.SimpleNamespace(obstacle=[ox, oy], xEst=pose, target_laser=None)
+        out = Localization.laserEstimation(node, msg, pose)
+        cases.append(dict(obs_x=ox, obs_y=oy, pose=pose, angle_min=amin, angle_increment=msg.angle_increment, beams=beams,
+                          ranges=np.array(out.ranges, dtype=np.float64)))
+    blob["vscan_count"] = len(cases)
+    for i, cse in enumerate(cases):
+        for k, v in cse.items():
+            blob["vscan%d_%s" % (i, k)] = v
+    np.savez_compressed(os.path.join(OUT, "next_rows.npz"), **blob)
+    print("next rows: chain of %d transforms, %d virtual scans" % (n, len(cases)))
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference tree not found at %s" % ref_loader.REF_ROOT)
@@ -422,6 +473,7 @@ def main():
         return
     mapping_f64_golden()
     nearest_ties_golden()
+    next_rows_golden()
     ingestion_golden()
     bresenham_golden()
     nearest_and_fit_golden()

@@ -14,6 +14,7 @@ Python 3 / NumPy 2 without editing it we
 bresenham.py and mapping.py import unchanged.
 """
 import importlib.util
+import math
 import os
 import re
 import sys
@@ -71,14 +72,16 @@ def _install_ros_stubs():
     rospy.get_param = get_param
     rospy.Publisher = _Anything
     rospy.Subscriber = _Anything
-    rospy.Time = _Anything
+    rospy.Time = _Anything()          # an instance: rospy.Time.now() is called on the class in the reference
     rospy.init_node = lambda *a, **k: None
     rospy.spin = lambda *a, **k: None
     sys.modules["rospy"] = rospy
 
     tf = types.ModuleType("tf")
     tf.TransformBroadcaster = _Anything
-    tf.transformations = _Anything()
+    tf.transformations = types.SimpleNamespace(
+        # yaw-only quaternion (x, y, z, w): all publishResult needs from tf ([ICP]:195); not on the measured path
+        quaternion_from_euler=lambda roll, pitch, yaw: (0.0, 0.0, math.sin(yaw / 2.0), math.cos(yaw / 2.0)))
     sys.modules["tf"] = tf
 
     for pkg, names in (
@@ -203,3 +206,28 @@ def load_slam_node_class():
                 sys.modules[k] = v
     node.__dict__["print"] = lambda *a, **k: None
     return node.SLAM_EKF, Mapping
+
+
+def load_localization_class():
+    """Localization from W9 localization.py, for laserEstimation (the virtual scan of the static map, :128-150) --
+    called as an unbound function on a duck-typed object.  Its sibling imports are stubbed except `icp` (the real one)."""
+    _install_ros_stubs()
+    ICP = load_icp_class({})
+    stubs = {}
+    for name, attrs in (("icp", {"ICP": ICP}), ("ekf", {"EKF": _Anything})):
+        mod = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(mod, k, v)
+        stubs[name] = mod
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        node = _exec_module("_ref_localization", os.path.join(W9_SCRIPTS, "localization.py"), True)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    node.__dict__["print"] = lambda *a, **k: None
+    return node.Localization

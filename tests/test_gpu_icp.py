@@ -455,3 +455,27 @@ def test_random_icp_shapes_vs_oracle(env):
             assert np.array_equal(it, want_it), "trial %d n %d m %d prune %d" % (trial, n, m, prune)
             np.testing.assert_allclose(T, want_T, rtol=0, atol=1e-9 * max(1.0, scale),
                                        err_msg="trial %d n %d m %d prune %d" % (trial, n, m, prune))
+
+
+def test_pose_chain_matches_reference_publishResult_golden(env):
+    """f-2 pinned: the device prefix scan against sensor_sta of the reference's own publishResult after every one of
+    400 transforms (tests/golden/next_rows.npz).  The parallel prefix re-associates the sums: 1e-12 absolute."""
+    from b2slam import scan
+    z = load_golden("next_rows.npz")
+    traj = scan.compose_odometry_gpu(tuple(z["chain_start"]), z["chain_T"])
+    np.testing.assert_allclose(traj, z["chain_traj"], rtol=0, atol=1e-12)
+    assert np.array_equal(traj[0], z["chain_start"])
+
+
+def test_virtual_scan_matches_reference_laserEstimation_golden(env):
+    """f-4 pinned: same bearing bins as the reference's own laserEstimation, ranges to 1e-13 relative (hypot on the
+    device vs libm), incl. an empty map and obstacles beyond the 100.0 the empty bins hold."""
+    from b2slam import scan
+    z = load_golden("next_rows.npz")
+    for i in range(int(z["vscan_count"])):
+        g = lambda k: z["vscan%d_%s" % (i, k)]
+        got = scan.virtual_scan(np.stack([g("obs_x"), g("obs_y")]), g("pose"), float(g("angle_min")),
+                                float(g("angle_increment")), int(g("beams")))
+        want = g("ranges")
+        assert np.array_equal(got == 100.0, want == 100.0), i       # the same bins were hit
+        np.testing.assert_allclose(got, want, rtol=1e-13, atol=0)

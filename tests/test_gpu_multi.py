@@ -187,3 +187,47 @@ def test_p2p_merge_single_rank_degenerates_to_finalize():
         assert np.array_equal(h, oh) and np.array_equal(m, om), (xw, yw, sparse, "pipelined")
         assert np.array_equal(pm, corc.grid_finalize(oh, om)[1]), (xw, yw, sparse, "pipelined")
         sm.close()
+
+
+def test_streamed_submit_wait_equals_blocking_calls():
+    """submit_scans / submit_batch + Ticket.wait with two steps in flight: every step's map equals the oracle's map of
+    the scans up to and including that step (the read-back of step k overlaps step k + 1 but must never see it), the
+    counts at the end are the sum of all steps, and an error on a step surfaces at ITS ticket."""
+    import math
+    import b2slam.dist as bdist
+    import b2slam.synth as synth
+    from b2slam import scan
+    from oracle import corc
+    G = 1024
+    S, Hx, Hy = 20.0, G * 0.05 / 2.0, G * 0.05 / 2.0
+    sm = bdist.ShardedMappingP2P(G, G, 0.05)
+    oh = np.zeros((G, G), dtype=np.int32)
+    om = np.zeros((G, G), dtype=np.int32)
+    beams = scan.beam_table(-math.pi, math.pi, 360)
+    want, tickets = [], []
+    for k in range(7):
+        if k % 2:
+            ox, oy, cx, cy = synth.grid_scans(300 + k, 64, 360, half_extent_m=20.0)
+            tickets.append(sm.submit_batch(ox, oy, cx, cy))
+            corc.grid_raycast(oh, om, S, Hx, Hy, ox, oy, cx, cy)
+        else:
+            ranges, poses = synth.grid_scan_ranges(300 + k, 64, 360, half_extent_m=20.0)
+            tickets.append(sm.submit_scans(ranges, poses, -math.pi, math.pi))
+            corc.grid_raycast_ranges(oh, om, S, Hx, Hy, ranges, scan.pose_table(poses), beams, 30.0)
+        want.append(corc.grid_finalize(oh, om)[1].copy())
+        if k >= 1:                                   # two in flight: wait for the previous one only now
+            got = tickets[k - 1].wait()
+            assert np.array_equal(got, want[k - 1]), "step %d" % (k - 1)
+    assert np.array_equal(tickets[-1].wait(), want[-1])
+    h, m = sm.counts()
+    assert np.array_equal(h, oh) and np.array_equal(m, om)
+    # a bad step raises at its own ticket, the following step does not
+    ox, oy, cx, cy = synth.grid_scans(999, 8, 360, half_extent_m=20.0)
+    bad = oy.copy()
+    bad[3, 5] = np.nan
+    t_bad = sm.submit_batch(ox, bad, cx, cy)
+    t_ok = sm.submit_batch(ox, oy, cx, cy)
+    with pytest.raises(ValueError):
+        t_bad.wait()
+    t_ok.wait()
+    sm.close()

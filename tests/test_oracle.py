@@ -267,3 +267,29 @@ def test_ingestion_oracle_matches_reference_node():
     score, pmap = corc.grid_finalize(hit, miss)
     np.testing.assert_allclose(score, z["datamap"], rtol=1e-12, atol=0)
     assert np.array_equal(pmap, z["pmap"])
+
+
+# ----------------------------------------------------------------------------- next rows: f-2 pose chain, f-4 virtual scan
+
+def test_pose_chain_oracle_matches_reference_publishResult():
+    """pyref.compose_pose and the host form scan.compose_odometry against sensor_sta after every call of the
+    reference's own ICP.publishResult ([ICP]:181-190) on a 400-transform stream (golden)."""
+    import b2slam.scan as scan
+    z = load_golden("next_rows.npz")
+    T, want = z["chain_T"], z["chain_traj"]
+    st = tuple(z["chain_start"])
+    assert st == (0.25, -1.5, 0.4)
+    for k in range(T.shape[0]):
+        st = pyref.compose_pose(st, T[k])
+        assert st == tuple(want[k + 1]), k                    # the literal port is bit-identical, step by step
+    traj = scan.compose_odometry(tuple(z["chain_start"]), T)
+    assert np.array_equal(traj, want)
+
+
+def test_virtual_scan_oracle_matches_reference_laserEstimation():
+    z = load_golden("next_rows.npz")
+    for i in range(int(z["vscan_count"])):
+        g = lambda k: z["vscan%d_%s" % (i, k)]
+        got = pyref.virtual_scan([g("obs_x"), g("obs_y")], g("pose"), float(g("angle_min")), float(g("angle_increment")),
+                                 int(g("beams")))
+        assert np.array_equal(got, g("ranges")), i
