@@ -402,7 +402,8 @@ template <int MODE>
 __device__ __forceinline__ void load_beam(const ScanInput &in, long long i, int beams, double &fox, double &foy,
                                           double &fcx, double &fcy)
 {
-    const int s = (int)(i / beams);
+    // (a 64-bit division costs ~70 instructions; every launch of a realistic size fits 32 bits)
+    const int s = (i >> 32) == 0 ? (int)((unsigned)i / (unsigned)beams) : (int)(i / beams);
     if (MODE == IN_F32) {
         fox = (double)__ldg((const float *)in.ox + i);
         foy = (double)__ldg((const float *)in.oy + i);
@@ -449,9 +450,8 @@ grid_raycast_v4(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int32_t *
     }
     const bool live = (st == BEAM_OK);
     const int span = live ? b.span : -1;
-    int tmax = span;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    // (warp reductions are single REDUX instructions: the set-up of a warp used to spend 45 shuffles on them)
+    const int tmax = __reduce_max_sync(0xffffffffu, span);
     if (tmax < 0) return;
 
     if (live && (unsigned)b.hx < (unsigned)xw && (unsigned)b.hy < (unsigned)yw)
@@ -469,18 +469,16 @@ grid_raycast_v4(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int32_t *
             ny0 = -max(0, min(b.sy, b.hy));
             y1 = min(yw - 1, max(b.sy, b.hy));
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            nx0 = max(nx0, __shfl_xor_sync(0xffffffffu, nx0, o));
-            x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
-            ny0 = max(ny0, __shfl_xor_sync(0xffffffffu, ny0, o));
-            y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
-        }
-        if (__any_sync(0xffffffffu, live && b.steep) && lane == 0) {
-            atomicMax(&ws->bbox[0], nx0);
-            atomicMax(&ws->bbox[1], x1);
-            atomicMax(&ws->bbox[2], ny0);
-            atomicMax(&ws->bbox[3], y1);
+        nx0 = __reduce_max_sync(0xffffffffu, nx0);
+        x1 = __reduce_max_sync(0xffffffffu, x1);
+        ny0 = __reduce_max_sync(0xffffffffu, ny0);
+        y1 = __reduce_max_sync(0xffffffffu, y1);
+        if (__any_sync(0xffffffffu, live && b.steep) && lane < 4) {
+            // lane k widens bound k, and only when it actually does: after the first few warps of a launch almost
+            // none does, and half a million warps no longer queue up on the same four words (a stale read only
+            // costs a redundant atomic)
+            const int mine = lane == 0 ? nx0 : lane == 1 ? x1 : lane == 2 ? ny0 : y1;
+            if (mine > *reinterpret_cast<volatile int *>(&ws->bbox[lane])) atomicMax(&ws->bbox[lane], mine);
         }
         const int tx0 = (-nx0) / GRID_TILE, tx1 = x1 / GRID_TILE, ty0 = (-ny0) / GRID_TILE, ty1 = y1 / GRID_TILE;
         const int ny = ty1 - ty0 + 1, cnt = (tx1 - tx0 + 1) * ny, tiles_y = grid_tiles(yw);
@@ -494,9 +492,7 @@ grid_raycast_v4(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int32_t *
     const unsigned pitch2 = 2u * wmin;
     const unsigned long long plane_base = (unsigned long long)(uintptr_t)(b.steep ? scratch_t : miss) - 2ull * steep_bit;
     const int delay = (live && b.hit_k == 0) ? (tmax - span) : 0;
-    int dmax = delay;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    const int dmax = __reduce_max_sync(0xffffffffu, delay);
     int k_lo = max(0, -b.major0), k_hi = min(span, wmaj - 1 - b.major0);
     if (b.hit_k == 0) k_lo = max(k_lo, 1); else k_hi = min(k_hi, span - 1);
     const bool any = live && k_hi >= k_lo;
@@ -520,12 +516,8 @@ grid_raycast_v4(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int32_t *
     if (CORE_PHASE) {
         const bool unclipped = live && min(b.sx, b.hx) >= 0 && max(b.sx, b.hx) < xw && min(b.sy, b.hy) >= 0 &&
                                max(b.sy, b.hy) < yw;
-        int lo = any ? t_em : 0x3fffffff, hi = any ? t_em + (int)em_len : -1;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo = max(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-            hi = min(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-        }
+        const int lo = __reduce_max_sync(0xffffffffu, any ? t_em : 0x3fffffff);
+        const int hi = __reduce_min_sync(0xffffffffu, any ? t_em + (int)em_len : -1);
         if (__all_sync(0xffffffffu, unclipped && any)) {
             c_lo = max(lo, dmax);
             c_hi = hi;

@@ -232,12 +232,15 @@ static __device__ __noinline__ int warp_careful_nearest(double px, double py, co
 
 // Register cap: 80 per thread keeps 6 CTAs of 128 threads (360 beams) / 2 CTAs of 384 threads (1080 beams)
 // resident per SM; without it the allocation of some instances drifts above that step from build to build.
+// The small-scan instances (NN_BLK = 8, i.e. up to 600 targets: CTAs of 128 threads) fit 72 registers without a spill,
+// which makes room for a 7th CTA per SM: measured 0.789 -> 0.765 ms on cfg 2; at 384 threads 72 registers buy no
+// extra CTA and cost 1.4 %, and 64 registers (8 CTAs) spill 56 bytes and are slower than 72 on both shapes.
 //
 // RANGES = true is the fused-ingestion form: tar_xy / src_xy hold raw ranges (one float per beam, n == m)
 // and the points are formed here exactly as laserToNumpy does ([ICP]:216-229, [SLAM]:115-123): float64
 // (cos a * r, sin a * r) with the beam table computed by the host's NumPy, +inf -> clamp when clamp > 0.
 template <typename TIn, int R, int PRUNE, int NN_BLK, bool RANGES = false>
-__global__ void __maxnreg__(R <= 3 ? 80 : 104) icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__restrict__ src_xy, int n,
+__global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__restrict__ src_xy, int n,
                                  int m, int max_iter, double tol, double *__restrict__ T_out,
                                  int32_t *__restrict__ iters_out, int use_bulk,
                                  const double2 *__restrict__ beam_cs = nullptr, double clamp = 0.0)

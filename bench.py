@@ -581,9 +581,11 @@ def bench_icp(args, rank, world, torch, devapi, bdist, synth):
                      "brute_force_equivalent_fp64_tflops": flops / step_s / 1e12,
                      "fp64_peak_tflops_nominal": FP64_PEAK_TFLOPS,
                      "fp64_peak_tflops_measured_same_run": fp64_peak.value,
-                     "fp64_note": "the pruned search executes a fraction of the brute-force evaluations, so the equivalent "
-                                  "rate may exceed the peak; executed-instruction utilisation is in profiles/r1/"
-                                  "icp_batch_warp_pruned_360_ncu_full.txt (ncu: FP64 pipe 52 %, issue slots 70 %)"},
+                     "fp64_pipe_executed": (lambda st: None if not st else {k: st[k] for k in st if k not in ("sources", "sha1")})(ncu_stamp("icp_360")),
+                     "fp64_note": "the pruned search executes a fraction of the brute-force evaluations, so the brute-force-"
+                                  "equivalent rate is not a utilisation; fp64_pipe_executed is: the share of the FP64 pipe and "
+                                  "the executed warp instructions of this kernel from the committed ncu capture "
+                                  "(profiles/r2/ncu_stamps.json, null when the kernel source changed since)"},
         "e2e": {"value": world * P * e2e_steps / e2e_s, "unit": "pairs/s",
                 "h2d_bytes_per_step": int(h_seq.nbytes), "d2h_bytes_per_step": P * 76,
                 "api": "ICP.process_sequence (b2s_icp_process_sequence)", "ms_per_step": e2e_s / e2e_steps * 1e3},
