@@ -13,11 +13,14 @@ A step is one pass of the hot path over one batch of synthetic scans resident in
         over NVLink peer memory, or all-reduce them over NCCL with --merge nccl), finalize to the
         int8 occupancy map
   icp : ICP.process over the whole batch of pairs (one CTA per pair)
-`e2e` is the same step through the host-buffer API (Mapping.update_batch; ICP.process_sequence,
-cfg 2 being a scan stream): pinned host arrays in, host arrays out, copies inside the timed region,
-after untimed calls that bring the GPU back to full clocks.  Beside it: `e2e_fused_ingestion` (the
-raw-scan entry points Mapping.update_scans / ICP.process_scans, half the bytes) and, for the ICP,
-`e2e_pair_form` (ICP.process_batch on explicit pairs, twice the bytes).
+`e2e` is the same step through the host-buffer API with pinned host arrays in and the int8 occupancy map out, every
+copy inside the timed region, after untimed calls that bring the GPU back to full clocks.  For the grid the headline is
+the streaming form of the raw-scan call (dist.ShardedMappingP2P.submit_scans + Ticket.wait, two steps in flight: the
+upload of step k+1 overlaps the read-back of step k; ranges + poses, 4 B per beam); beside it `e2e_blocking_call`
+(Mapping.update_batch on world-frame endpoints, one call at a time; N > 1: ShardedMappingP2P.update_batch) and
+`e2e_fused_ingestion` (the blocking raw-scan call Mapping.update_scans / ShardedMappingP2P.update_scans).  For the ICP
+`e2e` is ICP.process_sequence (cfg 2 is a scan stream), with `e2e_fused_ingestion` (ICP.process_scans, raw ranges)
+and `e2e_pair_form` (ICP.process_batch on explicit pairs, twice the bytes).
 
 With N > 1 ranks the line also carries `merge_bit_identical`: after the timed region a reduced batch per rank goes
 through the same peer-memory merge, every rank ray-casts ALL ranks' scans in one pass by itself, and the merged map
@@ -768,13 +771,13 @@ def cpu_baselines(args, synth):
     ctx = mp.get_context("fork")
     out = {}
     with ctx.Pool(cores) as pool:
-        scans = 32 * cores
+        scans = 256 * cores   # ~10 s of wall time on all cores (the literal port does ~30 k beams/s per core)
         data = synth.grid_scans(12001, scans, GRID_BEAMS)
         rate, dt, _ = cpu_grid_rate(pool, cores, scans, data)
         out["grid"] = {"value": rate, "unit": "beams/s", "cores": cores, "kind": "port",
                        "sample": "first %d cfg-3 scans x %d beams, literal Python port (oracle/pyref.py) over %d "
                                  "processes, %.1f s wall" % (scans, GRID_BEAMS, cores, dt)}
-        pairs = max(cores, min(32, 2 * cores))
+        pairs = 8 * cores     # ~15 s of wall time on all cores (~0.6 pairs/s per core at 360 beams)
         xy, _ = synth.room_sequence(9001, 513, ICP_BEAMS)
         rate, dt, _ = cpu_icp_rate(pool, cores, pairs, xy[:-1], xy[1:])
         out["icp"] = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",
