@@ -544,6 +544,8 @@ grid_raycast_v4(int32_t *__restrict__ hit, int32_t *__restrict__ miss, int32_t *
 }
 
 // miss[x][y] += scratch_t[y][x] over the recorded bounding box, scratch_t cleared on the way.
+// A fixed-size grid walks the 32 x 32-cell tiles INSIDE the box (a 16384^2 plane has 262 144 such tiles, a step
+// touches a few thousand of them: launching one CTA per tile of the plane cost more than the fold itself).
 __global__ void __launch_bounds__(256)
 grid_fold_kernel(int32_t *__restrict__ miss, int32_t *__restrict__ scratch_t, const GridWorkspace *__restrict__ ws,
                  int xw, int yw)
@@ -551,28 +553,33 @@ grid_fold_kernel(int32_t *__restrict__ miss, int32_t *__restrict__ scratch_t, co
     __shared__ int tile[32][33];
     const int xmin = -ws->bbox[0], xmax = ws->bbox[1], ymin = -ws->bbox[2], ymax = ws->bbox[3];
     if (xmax < 0 || ymax < 0) return;  // no y-major beam in this launch
-    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
-    if (x0 > xmax || x0 + 31 < xmin || y0 > ymax || y0 + 31 < ymin) return;
+    const int bx0 = xmin >> 5, by0 = ymin >> 5;
+    const int nbx = (xmax >> 5) - bx0 + 1, nby = (ymax >> 5) - by0 + 1;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-    int any_nz = 0;
+    for (int t = blockIdx.x; t < nbx * nby; t += gridDim.x) {
+        const int x0 = (bx0 + t / nby) * 32, y0 = (by0 + t % nby) * 32;
+        int any_nz = 0;
 #pragma unroll
-    for (int r = ty; r < 32; r += 8) {
-        const int y = y0 + r, x = x0 + tx;
-        int v = 0;
-        if (y < yw && x < xw) {
-            const size_t at = (size_t)y * xw + x;
-            v = scratch_t[at];
-            if (v) scratch_t[at] = 0;
+        for (int r = ty; r < 32; r += 8) {
+            const int y = y0 + r, x = x0 + tx;
+            int v = 0;
+            if (y < yw && x < xw) {
+                const size_t at = (size_t)y * xw + x;
+                v = scratch_t[at];
+                if (v) scratch_t[at] = 0;
+            }
+            tile[r][tx] = v;
+            any_nz |= v;
         }
-        tile[r][tx] = v;
-        any_nz |= v;
-    }
-    if (!__syncthreads_or(any_nz)) return;
+        if (__syncthreads_or(any_nz)) {
 #pragma unroll
-    for (int r = ty; r < 32; r += 8) {
-        const int x = x0 + r, y = y0 + tx;
-        const int v = tile[tx][r];
-        if (v && x < xw && y < yw) miss[(size_t)x * yw + y] += v;
+            for (int r = ty; r < 32; r += 8) {
+                const int x = x0 + r, y = y0 + tx;
+                const int v = tile[tx][r];
+                if (v && x < xw && y < yw) miss[(size_t)x * yw + y] += v;
+            }
+        }
+        __syncthreads();  // the tile buffer is reused by the next iteration
     }
 }
 
@@ -804,8 +811,10 @@ static int raycast_v4_launch(int32_t *hit, int32_t *miss, int xw, int yw, double
 #undef B2S_V4
     B2S_CUDA(cudaGetLastError());
     if (!fold) return B2S_OK;
-    dim3 fgrid((xw + 31) / 32, (yw + 31) / 32);
-    grid_fold_kernel<<<fgrid, 256, 0, st>>>(miss, scratch_t, ws, xw, yw);
+    long long ftiles = (long long)((xw + 31) / 32) * ((yw + 31) / 32);
+    const long long fcap = (long long)sm_count() * 16;
+    if (ftiles > fcap) ftiles = fcap;
+    grid_fold_kernel<<<(unsigned)ftiles, 256, 0, st>>>(miss, scratch_t, ws, xw, yw);
     B2S_CUDA(cudaGetLastError());
     B2S_CUDA(cudaMemsetAsync(ws, 0x80, GRID_WS_HEADER, st));
     return B2S_OK;
@@ -873,22 +882,23 @@ namespace b2s {
 // planes back to all-zero at a cost proportional to what the last ray-casts touched.
 __global__ void __launch_bounds__(256)
 grid_clear_dirty_kernel(int32_t *__restrict__ hit, int32_t *__restrict__ miss, uint8_t *__restrict__ dirty, int xw,
-                        int yw)
+                        int yw, int ntiles)
 {
     const int tiles_y = grid_tiles(yw);
-    const int tile = blockIdx.x;
-    if (!dirty[tile]) return;
-    const int x0 = (tile / tiles_y) * GRID_TILE, y0 = (tile % tiles_y) * GRID_TILE;
-    for (int k = threadIdx.x; k < GRID_TILE * GRID_TILE; k += blockDim.x) {
-        const int x = x0 + k / GRID_TILE, y = y0 + k % GRID_TILE;
-        if (x < xw && y < yw) {
-            const size_t at = (size_t)x * yw + y;
-            hit[at] = 0;
-            miss[at] = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {   // (fixed-size grid: a 16384^2 map has 65 536 tiles)
+        if (!dirty[tile]) continue;
+        const int x0 = (tile / tiles_y) * GRID_TILE, y0 = (tile % tiles_y) * GRID_TILE;
+        for (int k = threadIdx.x; k < GRID_TILE * GRID_TILE; k += blockDim.x) {
+            const int x = x0 + k / GRID_TILE, y = y0 + k % GRID_TILE;
+            if (x < xw && y < yw) {
+                const size_t at = (size_t)x * yw + y;
+                hit[at] = 0;
+                miss[at] = 0;
+            }
         }
+        __syncthreads();
+        if (threadIdx.x == 0) dirty[tile] = 0;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) dirty[tile] = 0;
 }
 }  // namespace b2s
 
@@ -901,28 +911,30 @@ __global__ void __launch_bounds__(256)
 grid_finalize_dirty_kernel(const int32_t *__restrict__ hit, const int32_t *__restrict__ miss, int xw, int yw,
                            double w_hit, double w_miss, double thresh, const uint8_t *__restrict__ dirty,
                            int8_t *__restrict__ pmap, int8_t *__restrict__ packed, int32_t *__restrict__ tile_ids,
-                           int32_t *__restrict__ counter, int cap)
+                           int32_t *__restrict__ counter, int cap, int ntiles)
 {
     __shared__ int slot_s;
-    const int tile = blockIdx.x;
-    if (!dirty[tile]) return;
-    if (threadIdx.x == 0) slot_s = atomicAdd(counter, 1);
-    __syncthreads();
-    const int slot = slot_s;
-    if (slot < cap && threadIdx.x == 0) tile_ids[slot] = tile;
     const int tiles_y = grid_tiles(yw);
-    const int x0 = (tile / tiles_y) * GRID_TILE, y0 = (tile % tiles_y) * GRID_TILE;
-    for (int k = threadIdx.x; k < GRID_TILE * GRID_TILE; k += blockDim.x) {
-        const int x = x0 + k / GRID_TILE, y = y0 + k % GRID_TILE;
-        int8_t v = 0;
-        if (x < xw && y < yw) {
-            const size_t at = (size_t)x * yw + y;
-            const int h = hit[at], m = miss[at];
-            const double sc = __dadd_rn(__dmul_rn(w_miss, (double)m), __dmul_rn(w_hit, (double)h));
-            v = (h == 0 && m == 0) ? 50 : (sc > thresh ? 100 : 0);
-            pmap[at] = v;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {  // fixed-size grid (65 536 tiles at 16384^2)
+        if (!dirty[tile]) continue;
+        if (threadIdx.x == 0) slot_s = atomicAdd(counter, 1);
+        __syncthreads();
+        const int slot = slot_s;
+        if (slot < cap && threadIdx.x == 0) tile_ids[slot] = tile;
+        const int x0 = (tile / tiles_y) * GRID_TILE, y0 = (tile % tiles_y) * GRID_TILE;
+        for (int k = threadIdx.x; k < GRID_TILE * GRID_TILE; k += blockDim.x) {
+            const int x = x0 + k / GRID_TILE, y = y0 + k % GRID_TILE;
+            int8_t v = 0;
+            if (x < xw && y < yw) {
+                const size_t at = (size_t)x * yw + y;
+                const int h = hit[at], m = miss[at];
+                const double sc = __dadd_rn(__dmul_rn(w_miss, (double)m), __dmul_rn(w_hit, (double)h));
+                v = (h == 0 && m == 0) ? 50 : (sc > thresh ? 100 : 0);
+                pmap[at] = v;
+            }
+            if (slot < cap) packed[(size_t)slot * GRID_TILE * GRID_TILE + k] = v;
         }
-        if (slot < cap) packed[(size_t)slot * GRID_TILE * GRID_TILE + k] = v;
+        __syncthreads();  // slot_s is rewritten by the next dirty tile of this CTA
     }
 }
 
@@ -931,9 +943,10 @@ int grid_finalize_dirty(const int32_t *hit, const int32_t *miss, int xw, int yw,
                         int32_t *counter, int cap, void *stream)
 {
     const int tiles = grid_tiles(xw) * grid_tiles(yw);
-    grid_finalize_dirty_kernel<<<tiles, 256, 0, (cudaStream_t)stream>>>(
+    const int gcap = sm_count() * 16;
+    grid_finalize_dirty_kernel<<<tiles < gcap ? tiles : gcap, 256, 0, (cudaStream_t)stream>>>(
         hit, miss, xw, yw, w_hit, w_miss, thresh, (const uint8_t *)workspace + GRID_WS_HEADER, pmap, packed, tile_ids,
-        counter, cap);
+        counter, cap, tiles);
     B2S_CUDA(cudaGetLastError());
     return B2S_OK;
 }
@@ -956,8 +969,9 @@ extern "C" int b2s_grid_clear_dirty(int32_t *hit, int32_t *miss, int xw, int yw,
 {
     B2S_REQUIRE(hit && miss && workspace && xw > 0 && yw > 0, "b2s_grid_clear_dirty: bad arguments");
     const int tiles = grid_tiles(xw) * grid_tiles(yw);
-    grid_clear_dirty_kernel<<<tiles, 256, 0, (cudaStream_t)stream>>>(hit, miss, (uint8_t *)workspace + GRID_WS_HEADER,
-                                                                    xw, yw);
+    const int cap = sm_count() * 16;
+    grid_clear_dirty_kernel<<<tiles < cap ? tiles : cap, 256, 0, (cudaStream_t)stream>>>(
+        hit, miss, (uint8_t *)workspace + GRID_WS_HEADER, xw, yw, tiles);
     B2S_CUDA(cudaGetLastError());
     return B2S_OK;
 }
