@@ -319,11 +319,18 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_ke
     const double sax = shift(first[0], n), say = shift(first[1], n);
     const double sbx = shift(first[2], m), sby = shift(first[3], m);
 
-    // ---- pruning bounds: the target scan is cut into blocks of NN_BLK consecutive points, each with the
-    // centre of its bounding box and a radius that covers it (inflated by 1e-9 so rounding can only make
-    // the test below more conservative).  The staging area is free again and holds them: [nblk][4] doubles.
+    // ---- pruning bounds: the target scan is cut into blocks of NN_BLK consecutive points, each with a centre and a
+    // radius that covers it.  The bounds only decide which blocks are LOOKED AT, never the result, so they live in
+    // float32 (half the issue slots of the float64 tests they replace), made conservative as follows.  The centre is
+    // the float32 rounding of the bounding-box centre -- any point serves as a centre as long as the radius is measured
+    // from it, so the radius is taken in float64 from that float32 point and rounded UP.  A source point p enters the
+    // test as pf = float(p), off by at most 2^-24 (|px| + |py|); the float32 distance computation adds at most 2^-22
+    // relative.  A block is skipped iff  |pf - c|^2 (float)  >  ((rad + su + E) (1 + 2^-19))^2  rounded up, with
+    // E = 2^-22 (|pfx| + |pfy|): then the true |p - c| exceeds rad + su, i.e. every point of the block is farther than
+    // the upper bound su >= sqrt(ub) (1 + 2^-23) on the nearest distance.  NaN / inf anywhere make the comparison false:
+    // nothing is skipped.  The staging area is free again and holds the bounds: [nblk] float4.
     const int nblk = (m + NN_BLK - 1) / NN_BLK;
-    double4 *bnd = reinterpret_cast<double4 *>(stage);
+    float4 *bnd = reinterpret_cast<float4 *>(stage);
     if (PRUNE) {
         for (int b = tid; b < nblk; b += blockDim.x) {
             const int j0 = b * NN_BLK, j1 = min(m, j0 + NN_BLK);
@@ -332,7 +339,8 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_ke
                 x0 = fmin(x0, tar[j].x); x1 = fmax(x1, tar[j].x);
                 y0 = fmin(y0, tar[j].y); y1 = fmax(y1, tar[j].y);
             }
-            const double cx = 0.5 * (x0 + x1), cy = 0.5 * (y0 + y1);
+            const float cfx = __double2float_rn(0.5 * (x0 + x1)), cfy = __double2float_rn(0.5 * (y0 + y1));
+            const double cx = (double)cfx, cy = (double)cfy;
             double rad2 = 0.0;
             bool finite = true;
             for (int j = j0; j < j1; ++j) {
@@ -343,7 +351,7 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_ke
             }
             // a block with a NaN / inf point gets an infinite radius: it is never skipped
             const double rad = finite ? sqrt(rad2) * 1.000000001 + 1e-300 : INFINITY;
-            bnd[b] = make_double4(cx, cy, rad, 0.0);
+            bnd[b] = make_float4(cfx, cfy, __fmul_ru(__double2float_ru(rad), 1.000002f), 0.0f);  // (1 + 2^-19) folded in
         }
         __syncthreads();
     }
@@ -419,7 +427,10 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_ke
                 // upper bound is all the tests need.  NaN stays NaN, overflow gives inf: then nothing is skipped.
                 // The factor (> 1 + 2^-23) covers the rounding of the double-precision tests below.
                 const float suf = __fmul_ru(__fsqrt_ru(__double2float_ru(ub)), 1.0000002f);
-                const double su = (double)suf;
+                // the point in float32 for the block tests, its rounding allowance E, and su + E with the (1 + 2^-19)
+                const float pxf = __double2float_rn(px), pyf = __double2float_rn(py);
+                const float suE = __fmul_ru(__fadd_ru(suf, __fmul_ru(__fadd_ru(fabsf(pxf), fabsf(pyf)), 2.3841858e-7f)),
+                                            1.000002f);
                 // NN_CHAINS independent running minima (target j feeds chain j % NN_CHAINS) shorten the serial
                 // compare-select dependency; they are merged below with the lower index winning ties, which is
                 // what one ascending strict '<' scan gives.
@@ -451,11 +462,11 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_ke
                     }
                 };
                 auto lane_skips = [&](int b) -> bool {
-                    const double4 c = bnd[b];
-                    const double cxd = px - c.x, cyd = py - c.y;
-                    const double dc2 = fma(cyd, cyd, cxd * cxd);
-                    const double reach = c.z + su;
-                    return !real || (dc2 > reach * reach);
+                    const float4 c = bnd[b];
+                    const float cxd = pxf - c.x, cyd = pyf - c.y;
+                    const float dc2 = fmaf(cyd, cyd, cxd * cxd);
+                    const float reach = __fadd_ru(c.z, suE);
+                    return !real || (dc2 > __fmul_ru(reach, reach));
                 };
                 if (PRUNE >= 2) {
                     // common centre: the middle lane's point (any point works; the bound is computed from the actual points)
@@ -464,16 +475,20 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_ke
                     const double ex = px - wx, ey = py - wy;
                     const float ef = real ? __fadd_ru(__fsqrt_ru(__double2float_ru(fma(ey, ey, ex * ex))), suf) * 1.000001f
                                           : 0.0f;  // every step rounds up; NaN bits compare above all
-                    const double gmax = (double)__uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(ef)));
+                    const float gmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(ef)));
+                    // the same float32 test as lane_skips, for the common centre w and the warp's bound gmax
+                    const float wxf = __double2float_rn(wx), wyf = __double2float_rn(wy);
+                    const float gE = __fmul_ru(__fadd_ru(gmax, __fmul_ru(__fadd_ru(fabsf(wxf), fabsf(wyf)), 2.3841858e-7f)),
+                                               1.000002f);
                     const int lane = tid & 31;
                     for (int base = 0; base < nblk; base += 32) {
                         bool keep = false;
                         if (base + lane < nblk) {
-                            const double4 c = bnd[base + lane];
-                            const double cxd = wx - c.x, cyd = wy - c.y;
-                            const double dc2 = fma(cyd, cyd, cxd * cxd);
-                            const double reach = c.z + gmax;
-                            keep = !(dc2 > reach * reach);
+                            const float4 c = bnd[base + lane];
+                            const float cxd = wxf - c.x, cyd = wyf - c.y;
+                            const float dc2 = fmaf(cyd, cyd, cxd * cxd);
+                            const float reach = __fadd_ru(c.z, gE);
+                            keep = !(dc2 > __fmul_ru(reach, reach));
                         }
                         unsigned todo = __ballot_sync(0xffffffffu, keep);
                         while (todo) {
@@ -580,10 +595,10 @@ template <typename TIn, int R>
 static int launch_icp_r(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_src, int n_tar, int max_iter,
                         double tol, double *T_out, int32_t *iters_out, void *stream)
 {
-    // the block bounds live in the staging area: [ceil(m/blk)][4] doubles must fit in 2*m*sizeof(TIn)
+    // the block bounds live in the staging area: [ceil(m/blk)] float4 must fit in 2*m*sizeof(TIn)
     const int blk = (g_icp_block == 8 || g_icp_block == 16 || g_icp_block == 32) ? g_icp_block
                     : (g_icp_prune >= 2 ? (n_tar <= 600 ? 8 : 16) : (n_tar <= 600 ? 16 : 32));  // measured best per mode
-    const bool fits = (size_t)((n_tar + blk - 1) / blk) * 32 <= (size_t)2 * n_tar * sizeof(TIn);
+    const bool fits = (size_t)((n_tar + blk - 1) / blk) * 16 <= (size_t)2 * n_tar * sizeof(TIn);
 #define B2S_ICP_GO(P, B) \
     return launch_icp_rp<TIn, R, P, B>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream)
     if (g_icp_prune && fits) {
