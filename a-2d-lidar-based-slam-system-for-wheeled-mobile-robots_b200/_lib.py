@@ -99,6 +99,9 @@ SIGNATURES = {
                                               ctypes.POINTER(_i32)]),
     "b2s_mapping_update_ranges": (_i32, [_vp, _vp, _vp, _vp, _dbl, _i32, _i32, _vp]),
     "b2s_mapping_update_scans": (_i32, [_vp, _vp, _vp, _vp, _dbl, _i32, _i32, _vp]),
+    "b2s_mapping_submit": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, ctypes.POINTER(_i32)]),
+    "b2s_mapping_submit_scans": (_i32, [_vp, _vp, _vp, _vp, _dbl, _i32, _i32, _i32, _vp, ctypes.POINTER(_i32)]),
+    "b2s_mapping_wait": (_i32, [_vp, _i32]),
     "b2s_mapping_read": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "b2s_mapping_write": (_i32, [_vp, _vp, _vp]),
     "b2s_mapping_planes": (_i32, [_vp, _pp, _pp, _pp]),

@@ -178,6 +178,19 @@ struct b2s_mapping {
     bool pmap_valid;  // d_pmap holds the occupancy of the current counts
     int8_t *h_packed;  // pinned staging for the dirty tiles
     int32_t *h_ids;
+    // Streaming calls (b2s_mapping_submit* / b2s_mapping_wait): two slots of everything a step owns, so that step
+    // k + 1 can be uploaded and ray-cast while the map of step k is still on its way back to the host.
+    struct Slot {
+        Buf d_in, d_map, h_pose;          // device inputs, device copy of this step's occupancy, pinned pose table
+        int32_t *d_cnt, *h_cnt;           // the ray-cast's B2S_CNT_* words of this step (device / pinned host)
+        cudaEvent_t inputs_free, done;    // last ray-cast of the step enqueued / results on the host
+        bool in_flight, fused;
+        int ticket, scans, beams;
+        double clamp;
+    } slot[2];
+    cudaStream_t d2h_stream;
+    cudaEvent_t finalized;
+    int submitted;
 };
 
 extern "C" int b2s_version(void) { return 100; }
@@ -668,9 +681,16 @@ extern "C" int b2s_mapping_create(b2s_mapping **out, int xw, int yw, double xyre
     m->pmap_valid = false;
     m->h_packed = nullptr;
     m->h_ids = nullptr;
-    m->stream = m->stream2 = m->copy_stream = nullptr;
+    m->stream = m->stream2 = m->copy_stream = m->d2h_stream = nullptr;
     for (int k = 0; k < MAX_CHUNKS; ++k) m->chunk_ready[k] = nullptr;
-    m->begun = m->joined = nullptr;
+    m->begun = m->joined = m->finalized = nullptr;
+    m->submitted = 0;
+    for (int k = 0; k < 2; ++k) {
+        m->slot[k].d_cnt = m->slot[k].h_cnt = nullptr;
+        m->slot[k].inputs_free = m->slot[k].done = nullptr;
+        m->slot[k].in_flight = false;
+        m->slot[k].h_pose.pinned = true;
+    }
     const size_t plane = (size_t)xw * yw * sizeof(int32_t);
     cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking);
@@ -678,6 +698,14 @@ extern "C" int b2s_mapping_create(b2s_mapping **out, int xw, int yw, double xyre
     for (int k = 0; k < MAX_CHUNKS && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&m->chunk_ready[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->begun, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->joined, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->finalized, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->d2h_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+        e = cudaEventCreateWithFlags(&m->slot[k].inputs_free, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->slot[k].done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&m->slot[k].d_cnt, B2S_CNT_WORDS * sizeof(int32_t));
+        if (e == cudaSuccess) e = cudaMallocHost((void **)&m->slot[k].h_cnt, B2S_CNT_WORDS * sizeof(int32_t));
+    }
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->hit, plane);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->miss, plane);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->counters, 2 * B2S_CNT_WORDS * sizeof(int32_t));
@@ -711,6 +739,17 @@ extern "C" int b2s_mapping_destroy(b2s_mapping *m)
     m->d_packed.release();
     m->d_in.release(); m->d_datamap.release(); m->d_pmap.release();
     m->h_pose.release();
+    if (m->d2h_stream) cudaStreamSynchronize(m->d2h_stream);
+    for (int k = 0; k < 2; ++k) {
+        b2s_mapping::Slot &sl = m->slot[k];
+        sl.d_in.release(); sl.d_map.release(); sl.h_pose.release();
+        if (sl.d_cnt) cudaFree(sl.d_cnt);
+        if (sl.h_cnt) cudaFreeHost(sl.h_cnt);
+        if (sl.inputs_free) cudaEventDestroy(sl.inputs_free);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
+    if (m->finalized) cudaEventDestroy(m->finalized);
+    if (m->d2h_stream) cudaStreamDestroy(m->d2h_stream);
     for (int k = 0; k < MAX_CHUNKS; ++k)
         if (m->chunk_ready[k]) cudaEventDestroy(m->chunk_ready[k]);
     if (m->begun) cudaEventDestroy(m->begun);
@@ -759,6 +798,8 @@ int mapping_update_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beam
                         int *tiles_count = nullptr)
 {
     DeviceGuard g(m->device);
+    for (int k = 0; k < 2; ++k)  // streamed steps still in flight land first (their verdicts belong to their tickets)
+        if (m->slot[k].in_flight) B2S_CUDA(cudaEventSynchronize(m->slot[k].done));
     Trace tr(m->stream);
     const size_t total = (size_t)scans * beams;
     int rc;
@@ -1010,6 +1051,178 @@ extern "C" int b2s_mapping_update_scans(b2s_mapping *m, const float *ranges, con
     B2S_REQUIRE((size_t)scans * beams == 0 || (ranges && poses3 && beam_cs), "b2s_mapping_update_scans: null pointer");
     HostBatch hb = {true, false, nullptr, nullptr, nullptr, nullptr, ranges, nullptr, beam_cs, clamp_inf_to, poses3};
     return mapping_update_impl(m, hb, scans, beams, pmap_out);
+}
+
+// ------------------------------------------------------------------------------ streaming Mapping calls
+//
+// b2s_mapping_update* are blocking: upload, ray-cast, finalize, read the map back, return.  Back to back they leave
+// the copy engines idle while the kernels run and the SMs idle while the 16.8 MB map crosses PCIe.  The submit / wait
+// pair keeps two steps in flight instead: submit enqueues a whole step (its own device input buffers, counters and
+// device copy of the occupancy) and returns; the upload of step k + 1 then overlaps the ray-cast of step k and the
+// read-back of step k - ... on a third stream.  wait(ticket) blocks until that step's map is in pmap_out and gives the
+// step's verdict; a batch the reference would raise on is taken back out of the counts there (sign -1 kernels on the
+// slot's still-resident inputs: exact), but maps of steps submitted in between were finalized with it still applied.
+namespace {
+int mapping_wait_slot(b2s_mapping *m, b2s_mapping::Slot &sl)
+{
+    if (!sl.in_flight) return B2S_OK;
+    B2S_CUDA(cudaEventSynchronize(sl.done));
+    sl.in_flight = false;
+    const int32_t *cnt = sl.h_cnt;
+    const int saw_nan = cnt[B2S_CNT_NONFINITE], saw_inf = cnt[B2S_CNT_OVERFLOW], too_long = cnt[B2S_CNT_TOO_LONG];
+    if (!(saw_nan || saw_inf || too_long > 0)) return B2S_OK;
+    // roll the step back: the inputs are still in the slot's device buffers (the slot is not reused before its wait)
+    const size_t total = (size_t)sl.scans * sl.beams, a_pts = (total * sizeof(float) + 15) & ~(size_t)15;
+    char *base = (char *)sl.d_in.p;
+    int rc;
+    if (sl.fused) {
+        const size_t poses = (size_t)sl.scans * 4 * sizeof(double);
+        rc = grid_raycast_ranges_signed(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y, (const float *)base,
+                                        (const double *)(base + a_pts), (const double *)(base + a_pts + poses), sl.clamp,
+                                        sl.scans, sl.beams, nullptr, m->workspace, -1, m->stream, true);
+    } else {
+        const size_t a_ctr = ((size_t)sl.scans * sizeof(float) + 15) & ~(size_t)15;
+        rc = grid_raycast_signed(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y, base, base + a_pts,
+                                 base + 2 * a_pts, base + 2 * a_pts + a_ctr, false, sl.scans, sl.beams, nullptr,
+                                 m->workspace, -1, m->stream, true);
+    }
+    if (rc) return rc;
+    B2S_CUDA(cudaStreamSynchronize(m->stream));
+    if (saw_nan || saw_inf) {
+        set_error(saw_nan ? "cannot convert float NaN to integer" : "cannot convert float infinity to integer");
+        return B2S_ERR_NONFINITE;
+    }
+    set_error("%d beam(s) longer than %d cells: batch rejected", too_long, B2S_MAX_PATH_CELLS);
+    return B2S_ERR_TOO_LONG;
+}
+
+int mapping_submit_impl(b2s_mapping *m, const HostBatch &hb, int scans, int beams, int zero_first, int8_t *pmap_out,
+                        int *ticket_out)
+{
+    DeviceGuard g(m->device);
+    const int ticket = m->submitted;
+    b2s_mapping::Slot &sl = m->slot[ticket & 1];
+    b2s_mapping::Slot &other = m->slot[(ticket & 1) ^ 1];
+    int rc;
+    if (sl.in_flight && (rc = mapping_wait_slot(m, sl))) return rc;  // its buffers are about to be reused
+    const size_t total = (size_t)scans * beams, cells = (size_t)m->xw * m->yw;
+    const size_t a_pts = (total * sizeof(float) + 15) & ~(size_t)15;
+    const size_t poses = (size_t)scans * 4 * sizeof(double), table = (size_t)beams * 2 * sizeof(double);
+    const size_t a_ctr = ((size_t)scans * sizeof(float) + 15) & ~(size_t)15;
+    if ((rc = sl.d_in.reserve(hb.fused ? a_pts + poses + table : 2 * a_pts + 2 * a_ctr))) return rc;
+    if ((rc = sl.d_map.reserve(cells))) return rc;
+    if (hb.fused && hb.poses3 && (rc = sl.h_pose.reserve(poses ? poses : 16))) return rc;
+    char *base = (char *)sl.d_in.p;
+    float *d_a = (float *)base;
+    double *d_pose = (double *)(base + a_pts), *d_cs = (double *)(base + a_pts + poses);
+    char *d_b = base + a_pts, *d_c = base + 2 * a_pts, *d_d = base + 2 * a_pts + a_ctr;
+    cudaStream_t cs = m->copy_stream;
+    // the copy stream may overwrite the slot's inputs once the ray-casts that last read them are done
+    B2S_CUDA(cudaStreamWaitEvent(cs, sl.inputs_free, 0));
+    B2S_CUDA(cudaMemsetAsync(sl.d_cnt, 0, B2S_CNT_WORDS * sizeof(int32_t), m->stream));
+    if (zero_first) {
+        const size_t plane = cells * sizeof(int32_t);
+        B2S_CUDA(cudaMemsetAsync(m->hit, 0, plane, m->stream));
+        B2S_CUDA(cudaMemsetAsync(m->miss, 0, plane, m->stream));
+    }
+    if (total > 0) {
+        // a step submitted while the other slot is in flight has its upload hidden under that step's ray-cast and
+        // goes as one launch; a step that starts on an idle device is cut into ~1 M-beam chunks (see the blocking call)
+        int nchunk = other.in_flight ? 1 : (int)((total + (1u << 20) - 1) >> 20);
+        if (nchunk > MAX_CHUNKS) nchunk = MAX_CHUNKS;
+        if (g_h2d_chunks > 0) nchunk = g_h2d_chunks;
+        if (nchunk > scans) nchunk = scans;
+        if (nchunk < 1) nchunk = 1;
+        if (hb.fused) B2S_CUDA(cudaMemcpyAsync(d_cs, hb.beam_cs, table, cudaMemcpyHostToDevice, cs));
+        double *tab = hb.fused && hb.poses3 ? (double *)sl.h_pose.p : nullptr;
+        const double *pose4 = tab ? tab : hb.pose4;
+        for (int k = 0; k < nchunk; ++k) {
+            const size_t s0 = (size_t)scans * k / nchunk, s1 = (size_t)scans * (k + 1) / nchunk, ns = s1 - s0;
+            if (hb.fused) {
+                if (tab)
+                    for (size_t s = s0; s < s1; ++s) {
+                        tab[4 * s] = hb.poses3[3 * s];
+                        tab[4 * s + 1] = hb.poses3[3 * s + 1];
+                        tab[4 * s + 2] = cos(hb.poses3[3 * s + 2]);
+                        tab[4 * s + 3] = sin(hb.poses3[3 * s + 2]);
+                    }
+                B2S_CUDA(cudaMemcpyAsync(d_a + s0 * beams, hb.ranges + s0 * beams, ns * beams * sizeof(float), cudaMemcpyHostToDevice, cs));
+                B2S_CUDA(cudaMemcpyAsync(d_pose + 4 * s0, pose4 + 4 * s0, ns * 4 * sizeof(double), cudaMemcpyHostToDevice, cs));
+            } else {
+                const size_t el = sizeof(float);
+                B2S_CUDA(cudaMemcpyAsync((char *)d_a + s0 * beams * el, (const char *)hb.ox + s0 * beams * el, ns * beams * el, cudaMemcpyHostToDevice, cs));
+                B2S_CUDA(cudaMemcpyAsync(d_b + s0 * beams * el, (const char *)hb.oy + s0 * beams * el, ns * beams * el, cudaMemcpyHostToDevice, cs));
+                B2S_CUDA(cudaMemcpyAsync(d_c + s0 * el, (const char *)hb.cx + s0 * el, ns * el, cudaMemcpyHostToDevice, cs));
+                B2S_CUDA(cudaMemcpyAsync(d_d + s0 * el, (const char *)hb.cy + s0 * el, ns * el, cudaMemcpyHostToDevice, cs));
+            }
+            B2S_CUDA(cudaEventRecord(m->chunk_ready[k], cs));
+            B2S_CUDA(cudaStreamWaitEvent(m->stream, m->chunk_ready[k], 0));
+            const bool fold = (k == nchunk - 1);
+            if (hb.fused)
+                rc = grid_raycast_ranges_signed(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y,
+                                                d_a + s0 * beams, d_pose + 4 * s0, d_cs, hb.clamp, (int)ns, beams, sl.d_cnt,
+                                                m->workspace, +1, m->stream, fold);
+            else
+                rc = grid_raycast_signed(m->hit, m->miss, m->xw, m->yw, m->cells_per_m, m->off_x, m->off_y,
+                                         (char *)d_a + s0 * beams * sizeof(float), d_b + s0 * beams * sizeof(float),
+                                         d_c + s0 * sizeof(float), d_d + s0 * sizeof(float), false, (int)ns, beams, sl.d_cnt,
+                                         m->workspace, +1, m->stream, fold);
+            if (rc) return rc;
+        }
+    }
+    B2S_CUDA(cudaEventRecord(sl.inputs_free, m->stream));
+    if (pmap_out) {
+        rc = b2s_grid_finalize(m->hit, m->miss, m->xw, m->yw, m->w_hit, m->w_miss, m->thresh, nullptr, (int8_t *)sl.d_map.p,
+                               m->stream);
+        if (rc) return rc;
+    }
+    B2S_CUDA(cudaEventRecord(m->finalized, m->stream));
+    B2S_CUDA(cudaStreamWaitEvent(m->d2h_stream, m->finalized, 0));
+    if (pmap_out) B2S_CUDA(cudaMemcpyAsync(pmap_out, sl.d_map.p, cells, cudaMemcpyDeviceToHost, m->d2h_stream));
+    B2S_CUDA(cudaMemcpyAsync(sl.h_cnt, sl.d_cnt, B2S_CNT_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost, m->d2h_stream));
+    B2S_CUDA(cudaEventRecord(sl.done, m->d2h_stream));
+    sl.in_flight = true;
+    sl.fused = hb.fused;
+    sl.ticket = ticket;
+    sl.scans = scans;
+    sl.beams = beams;
+    sl.clamp = hb.clamp;
+    m->pmap_valid = false;  // the incremental read-back of update() starts over after streamed steps
+    m->submitted = ticket + 1;
+    if (ticket_out) *ticket_out = ticket;
+    return B2S_OK;
+}
+}  // namespace
+
+extern "C" int b2s_mapping_submit(b2s_mapping *m, const float *ox, const float *oy, const float *cx, const float *cy,
+                                  int scans, int beams, int zero_first, int8_t *pmap_out, int *ticket_out)
+{
+    B2S_REQUIRE(m && ticket_out, "b2s_mapping_submit: null pointer");
+    B2S_REQUIRE(scans >= 0 && beams >= 0, "b2s_mapping_submit: negative count");
+    B2S_REQUIRE((size_t)scans * beams == 0 || (ox && oy && cx && cy), "b2s_mapping_submit: null pointer");
+    HostBatch hb = {false, false, ox, oy, cx, cy, nullptr, nullptr, nullptr, 0.0, nullptr};
+    return mapping_submit_impl(m, hb, scans, beams, zero_first, pmap_out, ticket_out);
+}
+
+extern "C" int b2s_mapping_submit_scans(b2s_mapping *m, const float *ranges, const double *poses3, const double *beam_cs,
+                                        double clamp_inf_to, int scans, int beams, int zero_first, int8_t *pmap_out,
+                                        int *ticket_out)
+{
+    B2S_REQUIRE(m && ticket_out, "b2s_mapping_submit_scans: null pointer");
+    B2S_REQUIRE(scans >= 0 && beams >= 0, "b2s_mapping_submit_scans: negative count");
+    B2S_REQUIRE((size_t)scans * beams == 0 || (ranges && poses3 && beam_cs), "b2s_mapping_submit_scans: null pointer");
+    HostBatch hb = {true, false, nullptr, nullptr, nullptr, nullptr, ranges, nullptr, beam_cs, clamp_inf_to, poses3};
+    return mapping_submit_impl(m, hb, scans, beams, zero_first, pmap_out, ticket_out);
+}
+
+extern "C" int b2s_mapping_wait(b2s_mapping *m, int ticket)
+{
+    B2S_REQUIRE(m, "b2s_mapping_wait: null handle");
+    B2S_REQUIRE(ticket >= 0 && ticket < m->submitted, "b2s_mapping_wait: unknown ticket");
+    DeviceGuard g(m->device);
+    b2s_mapping::Slot &sl = m->slot[ticket & 1];
+    if (!sl.in_flight || sl.ticket != ticket) return B2S_OK;  // already waited for (or superseded and waited implicitly)
+    return mapping_wait_slot(m, sl);
 }
 
 extern "C" int b2s_mapping_read(b2s_mapping *m, int32_t *hit, int32_t *miss, float *datamap, int8_t *pmap)

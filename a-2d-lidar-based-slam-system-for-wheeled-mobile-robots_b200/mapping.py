@@ -11,6 +11,24 @@ import numpy as np
 from b2slam import _lib
 
 
+class MapTicket(object):
+    """Handle of a step submitted with Mapping.submit_scans / submit_batch."""
+
+    def __init__(self, owner, ticket, out):
+        self._owner, self._ticket, self._out = owner, ticket, out
+
+    def wait(self):
+        """Block until the step's occupancy is in host memory and return it (int8 (xw, yw), page-locked, overwritten
+        by the second-next submit).  A step holding a coordinate the reference's int() raises on raises here
+        (ValueError / OverflowError) and has been taken back out of the counts."""
+        m = self._owner
+        rc = m._L.b2s_mapping_wait(m._h, self._ticket)
+        m._raise_nonfinite(rc)
+        _lib.check(rc)
+        m._host_map_blank = False
+        return self._out
+
+
 class Mapping(object):
     """[MAP]:7-51.  Mapping(xw, yw, xyreso) as in the reference, plus keyword weights:
 
@@ -174,6 +192,63 @@ class Mapping(object):
         if want_pmap:
             self._host_map_blank = False
         return self._pmap8 if want_pmap else None
+
+    # ------------------------------------------------------------------ streaming calls (two steps in flight)
+
+    def _stream_slot(self):
+        if getattr(self, "_stream_maps", None) is None:
+            self._stream_maps = [_lib.pinned_empty((self.xw, self.yw), np.int8) for _ in range(2)]
+            self._stream_keep = [None, None]
+        return self._stream_maps
+
+    def submit_scans(self, ranges, poses, angle_min, angle_max, clamp_inf_to=30.0, zero_first=False):
+        """update_scans without the wait (b2s_mapping_submit_scans): the step is enqueued -- upload, ray-cast, finalize,
+        read-back of the map on a third stream -- and a MapTicket is returned at once.  Up to two steps are in flight, so
+        the upload and ray-cast of the next step run while this step's 16.8 MB map (at 4096^2) crosses PCIe the other
+        way.  ticket.wait() returns this step's int8 occupancy (a page-locked buffer that the second-next submit
+        overwrites) or raises what update_scans would have raised for it.  zero_first: clear the counts before the step.
+        The arrays must stay untouched until the ticket has been waited for."""
+        from b2slam import scan
+        ranges = np.ascontiguousarray(ranges, dtype=np.float32)
+        if ranges.ndim == 1:
+            ranges = ranges.reshape(1, -1)
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 3)
+        if poses.shape[0] != ranges.shape[0]:
+            raise ValueError("need one pose per scan, got %d poses for %d scans" % (poses.shape[0], ranges.shape[0]))
+        key = (float(angle_min), float(angle_max), ranges.shape[1])
+        if getattr(self, "_beam_key", None) != key:
+            self._beam_cs = scan.beam_table(angle_min, angle_max, ranges.shape[1])
+            self._beam_key = key
+        maps = self._stream_slot()
+        t = ctypes.c_int(-1)
+        n = getattr(self, "_submitted", 0)
+        out = maps[n % 2]
+        self._pmap64 = None
+        _lib.check(self._L.b2s_mapping_submit_scans(self._h, _lib.ptr(ranges), _lib.ptr(poses), _lib.ptr(self._beam_cs),
+                                                    float(clamp_inf_to or 0.0), ranges.shape[0], ranges.shape[1],
+                                                    1 if zero_first else 0, _lib.ptr(out), ctypes.byref(t)))
+        self._submitted = n + 1
+        self._stream_keep[n % 2] = (ranges, poses)       # keep the inputs alive while the device reads them
+        return MapTicket(self, t.value, out)
+
+    def submit_batch(self, ox, oy, cx, cy, zero_first=False):
+        """update_batch (float32 endpoints) without the wait; see submit_scans."""
+        ox = np.ascontiguousarray(ox, dtype=np.float32)
+        oy = np.ascontiguousarray(oy, dtype=np.float32)
+        cx = np.ascontiguousarray(cx, dtype=np.float32).reshape(-1)
+        cy = np.ascontiguousarray(cy, dtype=np.float32).reshape(-1)
+        if ox.ndim != 2 or ox.shape != oy.shape or cx.shape[0] != ox.shape[0] or cy.shape[0] != ox.shape[0]:
+            raise ValueError("expected ox, oy (K,N) and cx, cy (K,), got %s %s %s %s" % (ox.shape, oy.shape, cx.shape, cy.shape))
+        maps = self._stream_slot()
+        t = ctypes.c_int(-1)
+        n = getattr(self, "_submitted", 0)
+        out = maps[n % 2]
+        self._pmap64 = None
+        _lib.check(self._L.b2s_mapping_submit(self._h, _lib.ptr(ox), _lib.ptr(oy), _lib.ptr(cx), _lib.ptr(cy), ox.shape[0],
+                                              ox.shape[1], 1 if zero_first else 0, _lib.ptr(out), ctypes.byref(t)))
+        self._submitted = n + 1
+        self._stream_keep[n % 2] = (ox, oy, cx, cy)
+        return MapTicket(self, t.value, out)
 
     def counts(self):
         """(hit, miss) int32 (xw, yw) snapshots of the device planes."""

@@ -408,16 +408,21 @@ def bench_grid(args, rank, world, torch, devapi, bdist, synth):
         fs = time_host_calls(fused_step, e2e_steps, bdist, torch, lockstep=world > 1)
         fused = {"value": world * K * N * e2e_steps / fs, "unit": "beams/s", "h2d_bytes_per_step": 4 * K * N + 32 * K,
                  "d2h_bytes_per_step": G * G, "api": api, "ms_per_step": fs / e2e_steps * 1e3}
-        # the same steps through the streaming form of the API: submit step k + 1, then wait for step k
-        sm_stream = p2p if p2p is not None else bdist.ShardedMappingP2P(G, G, GRID_RESO)
+        # the same steps through the streaming form of the call: submit step k + 1, then wait for step k
         stream_steps = max(10, min(args.steps, 40))
-        ss = time_host_stream(lambda: sm_stream.submit_scans(keep_r, poses, -math.pi, math.pi), stream_steps, bdist, torch)
-        streamed = {"value": world * K * N * stream_steps / ss, "unit": "beams/s", "h2d_bytes_per_step": 4 * K * N + 32 * K,
-                    "d2h_bytes_per_step": G * G, "ms_per_step": ss / stream_steps * 1e3,
-                    "api": "dist.ShardedMappingP2P.submit_scans + Ticket.wait, two steps in flight (raw ranges + poses in, "
-                           "merged int8 map out, every step)"}
-        if p2p is None:
-            sm_stream.close()
+        if world == 1:
+            # one GPU: the C-ABI host-buffer call itself (b2s_mapping_submit_scans / b2s_mapping_wait); every step clears
+            # the counts first, like the device-timed step
+            ss = time_host_stream(lambda: m.submit_scans(h_ranges, poses, -math.pi, math.pi, zero_first=True),
+                                  stream_steps, bdist, torch)
+            sapi = ("Mapping.submit_scans + MapTicket.wait (b2s_mapping_submit_scans / b2s_mapping_wait), two steps in "
+                    "flight: raw ranges + poses in, int8 map out, every step")
+        else:
+            ss = time_host_stream(lambda: p2p.submit_scans(keep_r, poses, -math.pi, math.pi), stream_steps, bdist, torch)
+            sapi = ("dist.ShardedMappingP2P.submit_scans + Ticket.wait, two steps in flight: raw ranges + poses in, merged "
+                    "int8 map out, every step and rank")
+        streamed = {"value": world * K * N * stream_steps / ss, "unit": "beams/s", "h2d_bytes_per_step": 4 * K * N + 24 * K,
+                    "d2h_bytes_per_step": G * G, "ms_per_step": ss / stream_steps * 1e3, "api": sapi}
 
     peak, peak_src = measured_peaks()
     achieved = algo_bytes / (ray_avg_ms * 1e-3) / 1e9

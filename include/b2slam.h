@@ -334,6 +334,20 @@ int b2s_mapping_update_ranges(b2s_mapping *map, const float *ranges, const doubl
  * math.sin) are evaluated with libm inside the call, one pipeline chunk ahead of the device. */
 int b2s_mapping_update_scans(b2s_mapping *m, const float *ranges, const double *poses3, const double *beam_cs,
                              double clamp_inf_to, int scans, int beams, int8_t *pmap_out);
+/* Streaming forms of b2s_mapping_update / b2s_mapping_update_scans: submit enqueues the whole step -- chunked upload,
+ * ray-cast, finalize into the step's own device map, read-back into pmap_out on a third stream -- and returns a
+ * ticket at once; up to two steps are in flight, so the upload and ray-cast of step k + 1 run while the map of step k
+ * is still crossing PCIe the other way.  zero_first != 0 clears the counts before the step.  pmap_out [xw][yw]
+ * (page-locked for a truly asynchronous copy; may be NULL) and the input arrays must stay valid and untouched until
+ * b2s_mapping_wait(ticket) has returned; submitting a third step first waits for the first one implicitly.
+ * b2s_mapping_wait returns the step's verdict: B2S_ERR_NONFINITE / B2S_ERR_TOO_LONG mean the batch held a coordinate the
+ * reference's int() raises on ([MAP]:33-36) / an over-long beam and has been taken back out of the counts (exact, sign -1
+ * kernels); maps of steps submitted after it and before the wait were finalized with it still applied. */
+int b2s_mapping_submit(b2s_mapping *map, const float *ox, const float *oy, const float *cx, const float *cy, int scans,
+                       int beams, int zero_first, int8_t *pmap_out, int *ticket_out);
+int b2s_mapping_submit_scans(b2s_mapping *map, const float *ranges, const double *poses3, const double *beam_cs,
+                             double clamp_inf_to, int scans, int beams, int zero_first, int8_t *pmap_out, int *ticket_out);
+int b2s_mapping_wait(b2s_mapping *map, int ticket);
 /* Snapshot to host; any pointer may be NULL. */
 int b2s_mapping_read(b2s_mapping *map, int32_t *hit, int32_t *miss, float *datamap, int8_t *pmap);
 /* Overwrite the count planes from host arrays [xw][yw] (checkpoint restore; the reference has none). */

@@ -502,3 +502,56 @@ def test_layer1_validate_flags(env):
     assert run(a, oy, cx, cy) == [1, 0]
     c = cx.copy(); c[0] = -np.inf
     assert run(ox, oy, c, cy) == [0, 1]
+
+
+def test_streamed_mapping_calls_equal_blocking_calls(env):
+    """Mapping.submit_scans / submit_batch + MapTicket.wait (b2s_mapping_submit* / b2s_mapping_wait), two steps in flight:
+    every step's map equals the oracle's after that step, the counts at the end are the sum of all steps, a step the
+    reference would raise on raises at ITS ticket and is taken back out exactly, and zero_first starts over."""
+    import math
+    from b2slam import scan
+    G = 1024
+    S, Hx, Hy = env.dev.grid_scale(G, G, 0.05)
+    m = env.b2slam.Mapping(G, G, 0.05)
+    oh = np.zeros((G, G), dtype=np.int32)
+    om = np.zeros((G, G), dtype=np.int32)
+    beams = scan.beam_table(-math.pi, math.pi, 360)
+    want, tickets = [], []
+    for k in range(7):
+        if k % 2:
+            ox, oy, cx, cy = env.synth.grid_scans(400 + k, 96, 360, half_extent_m=20.0)
+            tickets.append(m.submit_batch(ox, oy, cx, cy))
+            env.corc.grid_raycast(oh, om, S, Hx, Hy, ox, oy, cx, cy)
+        else:
+            ranges, poses = env.synth.grid_scan_ranges(400 + k, 96, 360, half_extent_m=20.0)
+            tickets.append(m.submit_scans(ranges, poses, -math.pi, math.pi))
+            env.corc.grid_raycast_ranges(oh, om, S, Hx, Hy, ranges, scan.pose_table(poses), beams, 30.0)
+        want.append(env.corc.grid_finalize(oh, om)[1].copy())
+        if k >= 1:
+            assert np.array_equal(tickets[k - 1].wait(), want[k - 1]), "step %d" % (k - 1)
+    assert np.array_equal(tickets[-1].wait(), want[-1])
+    h, ms = m.counts()
+    assert np.array_equal(h, oh) and np.array_equal(ms, om)
+    # a bad step: raises at its own ticket, is rolled back exactly; the good step submitted behind it stays applied
+    ox, oy, cx, cy = env.synth.grid_scans(999, 16, 360, half_extent_m=20.0)
+    bad = oy.copy()
+    bad[3, 5] = np.nan
+    t_bad = m.submit_batch(ox, bad, cx, cy)
+    t_ok = m.submit_batch(ox, oy, cx, cy)
+    with pytest.raises(ValueError):
+        t_bad.wait()
+    t_ok.wait()
+    env.corc.grid_raycast(oh, om, S, Hx, Hy, ox, oy, cx, cy)
+    h, ms = m.counts()
+    assert np.array_equal(h, oh) and np.array_equal(ms, om)
+    # the blocking call after streamed steps, and zero_first
+    pm = m.update_batch(ox, oy, cx, cy)
+    env.corc.grid_raycast(oh, om, S, Hx, Hy, ox, oy, cx, cy)
+    assert np.array_equal(pm, env.corc.grid_finalize(oh, om)[1])
+    t = m.submit_batch(ox, oy, cx, cy, zero_first=True)
+    oh[:] = 0
+    om[:] = 0
+    env.corc.grid_raycast(oh, om, S, Hx, Hy, ox, oy, cx, cy)
+    assert np.array_equal(t.wait(), env.corc.grid_finalize(oh, om)[1])
+    h, ms = m.counts()
+    assert np.array_equal(h, oh) and np.array_equal(ms, om)
