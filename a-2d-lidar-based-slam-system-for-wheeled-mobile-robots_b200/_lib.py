@@ -86,6 +86,9 @@ SIGNATURES = {
     "b2s_icp_process_sequence": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _dbl, _vp, _vp]),
     "b2s_icp_odometry": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _dbl, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
     "b2s_icp_process_scans": (_i32, [_vp, _vp, _vp, _dbl, _i32, _i32, _i32, _dbl, _vp, _vp, _vp, _vp]),
+    "b2s_icp_submit_sequence": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _dbl, _vp, _vp, ctypes.POINTER(_i32)]),
+    "b2s_icp_submit_scans": (_i32, [_vp, _vp, _vp, _dbl, _i32, _i32, _i32, _dbl, _vp, _vp, ctypes.POINTER(_i32)]),
+    "b2s_icp_wait": (_i32, [_vp, _i32]),
     "b2s_icp_find_nearest": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _vp]),
     "b2s_icp_get_transform": (_i32, [_vp, _vp, _vp, _i32, _vp]),
     "b2s_mapping_create": (_i32, [_pp, _i32, _i32, _dbl, _dbl, _dbl, _dbl, _i32]),

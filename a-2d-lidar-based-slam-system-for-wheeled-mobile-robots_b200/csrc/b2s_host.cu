@@ -159,6 +159,17 @@ struct b2s_icp {
         double tol;
         void *d_tar, *d_src, *d_T, *d_iters, *h;
     } one_key;
+    // Streaming sequence calls (b2s_icp_submit_sequence / _scans, b2s_icp_wait): two slots of device buffers, so the
+    // scans of call k + 1 cross PCIe while call k is being solved and its transforms are read back.
+    struct Slot {
+        Buf d_scans, d_T, d_iters, d_cs;
+        cudaEvent_t inputs_free, done;
+        bool in_flight;
+        int ticket;
+    } slot[2];
+    cudaStream_t d2h_stream;
+    cudaEvent_t solved;
+    int submitted;
 };
 
 struct b2s_mapping {
@@ -296,8 +307,13 @@ extern "C" int b2s_icp_create(b2s_icp **out, int device)
     b2s_icp *c = new (std::nothrow) b2s_icp();
     if (!c) return B2S_ERR_NOMEM;
     c->device = device;
-    c->stream = c->stream2 = c->copy_stream = nullptr;
-    c->joined = nullptr;
+    c->stream = c->stream2 = c->copy_stream = c->d2h_stream = nullptr;
+    c->joined = c->solved = nullptr;
+    c->submitted = 0;
+    for (int k = 0; k < 2; ++k) {
+        c->slot[k].inputs_free = c->slot[k].done = nullptr;
+        c->slot[k].in_flight = false;
+    }
     c->one_exec = nullptr;
     memset(&c->one_key, 0, sizeof(c->one_key));
     c->h_one.pinned = true;
@@ -306,6 +322,12 @@ extern "C" int b2s_icp_create(b2s_icp **out, int device)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->joined, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->solved, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+        e = cudaEventCreateWithFlags(&c->slot[k].inputs_free, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->slot[k].done, cudaEventDisableTiming);
+    }
     for (int k = 0; k < MAX_CHUNKS && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&c->chunk_ready[k], cudaEventDisableTiming);
     if (e != cudaSuccess) {
         int rc = cuda_fail(e, "b2s_icp_create");
@@ -326,6 +348,15 @@ extern "C" int b2s_icp_destroy(b2s_icp *c)
     if (c->one_exec) cudaGraphExecDestroy(c->one_exec);
     c->d_tar.release(); c->d_src.release(); c->d_T.release(); c->d_iters.release(); c->d_aux.release();
     c->h_one.release();
+    if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
+    for (int k = 0; k < 2; ++k) {
+        b2s_icp::Slot &sl = c->slot[k];
+        sl.d_scans.release(); sl.d_T.release(); sl.d_iters.release(); sl.d_cs.release();
+        if (sl.inputs_free) cudaEventDestroy(sl.inputs_free);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
+    if (c->solved) cudaEventDestroy(c->solved);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     for (int k = 0; k < MAX_CHUNKS; ++k)
         if (c->chunk_ready[k]) cudaEventDestroy(c->chunk_ready[k]);
     if (c->joined) cudaEventDestroy(c->joined);
@@ -471,22 +502,27 @@ extern "C" int b2s_icp_process(b2s_icp *c, const void *tar_xy, const void *src_x
 // results stay in c->d_T / c->d_iters for the caller to read back or chain.
 // `beam_cs` != NULL selects the raw-scan form: scans_xy holds one float range per beam and the kernel forms the
 // points itself (b2s_icp_batch_ranges), a quarter of the bytes of the float64 pair form.
+struct IcpBufs {
+    Buf &scans, &T, &iters, &cs;
+};
+
 static int icp_sequence_enqueue(b2s_icp *c, Trace &tr, const void *scans_xy, int is_f64, int scans, int n, int max_iter,
-                                double tol, const double *beam_cs = nullptr, double clamp = 0.0)
+                                double tol, const double *beam_cs, double clamp, IcpBufs bufs, int force_chunks = 0)
 {
     const size_t el = is_f64 ? 8 : 4, scan_bytes = (beam_cs ? (size_t)1 : (size_t)2) * n * el;
     const int pairs = scans - 1;
     int rc;
-    if ((rc = c->d_tar.reserve((size_t)scans * scan_bytes))) return rc;
-    if ((rc = c->d_T.reserve((size_t)pairs * 9 * sizeof(double)))) return rc;
-    if ((rc = c->d_iters.reserve((size_t)pairs * sizeof(int32_t)))) return rc;
+    if ((rc = bufs.scans.reserve((size_t)scans * scan_bytes))) return rc;
+    if ((rc = bufs.T.reserve((size_t)pairs * 9 * sizeof(double)))) return rc;
+    if ((rc = bufs.iters.reserve((size_t)pairs * sizeof(int32_t)))) return rc;
     if (beam_cs) {
-        if ((rc = c->d_src.reserve((size_t)n * 2 * sizeof(double)))) return rc;
-        B2S_CUDA(cudaMemcpyAsync(c->d_src.p, beam_cs, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+        if ((rc = bufs.cs.reserve((size_t)n * 2 * sizeof(double)))) return rc;
+        B2S_CUDA(cudaMemcpyAsync(bufs.cs.p, beam_cs, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
     }
     int nchunk = (int)(((size_t)scans * scan_bytes + (8u << 20) - 1) / (8u << 20));  // ~8 MB of points per chunk
     if (beam_cs && nchunk < 4 && pairs >= 4096) nchunk = 4;  // (raw scans are half the bytes: keep the pipeline depth)
     if (nchunk > 8) nchunk = 8;
+    if (force_chunks > 0) nchunk = force_chunks;
     if (g_h2d_chunks > 0) nchunk = g_h2d_chunks;
     if (nchunk > pairs) nchunk = pairs;
     if (nchunk < 1) nchunk = 1;
@@ -494,7 +530,7 @@ static int icp_sequence_enqueue(b2s_icp *c, Trace &tr, const void *scans_xy, int
     for (int k = 0; k < nchunk; ++k) {
         const size_t p0 = (size_t)pairs * k / nchunk, p1 = (size_t)pairs * (k + 1) / nchunk;
         const size_t s0 = k == 0 ? 0 : p0 + 1, s1 = p1 + 1;
-        B2S_CUDA(cudaMemcpyAsync((char *)c->d_tar.p + s0 * scan_bytes, (const char *)scans_xy + s0 * scan_bytes,
+        B2S_CUDA(cudaMemcpyAsync((char *)bufs.scans.p + s0 * scan_bytes, (const char *)scans_xy + s0 * scan_bytes,
                                  (s1 - s0) * scan_bytes, cudaMemcpyHostToDevice, c->copy_stream));
         B2S_CUDA(cudaEventRecord(c->chunk_ready[k], c->copy_stream));
         tr.mark("h2d chunk done", k, c->copy_stream);
@@ -503,11 +539,11 @@ static int icp_sequence_enqueue(b2s_icp *c, Trace &tr, const void *scans_xy, int
         const size_t p0 = (size_t)pairs * k / nchunk, p1 = (size_t)pairs * (k + 1) / nchunk;
         cudaStream_t ks = (k & 1) ? c->stream2 : c->stream;
         B2S_CUDA(cudaStreamWaitEvent(ks, c->chunk_ready[k], 0));
-        const char *tar = (const char *)c->d_tar.p + p0 * scan_bytes;
-        double *dT = (double *)c->d_T.p + p0 * 9;
-        int32_t *dI = (int32_t *)c->d_iters.p + p0;
+        const char *tar = (const char *)bufs.scans.p + p0 * scan_bytes;
+        double *dT = (double *)bufs.T.p + p0 * 9;
+        int32_t *dI = (int32_t *)bufs.iters.p + p0;
         if (beam_cs)
-            rc = b2s_icp_batch_ranges((const float *)tar, (const float *)(tar + scan_bytes), (const double *)c->d_src.p, clamp,
+            rc = b2s_icp_batch_ranges((const float *)tar, (const float *)(tar + scan_bytes), (const double *)bufs.cs.p, clamp,
                                       (int)(p1 - p0), n, max_iter, tol, dT, dI, ks);
         else if (is_f64)
             rc = b2s_icp_batch_f64((const double *)tar, (const double *)(tar + scan_bytes), (int)(p1 - p0), n, n, max_iter, tol,
@@ -558,7 +594,8 @@ extern "C" int b2s_icp_process_sequence(b2s_icp *c, const void *scans_xy, int is
     B2S_REQUIRE(scans_xy && T_out, "b2s_icp_process_sequence: null pointer");
     DeviceGuard g(c->device);
     Trace tr(c->stream);
-    int rc = icp_sequence_enqueue(c, tr, scans_xy, is_f64, scans, n, max_iter, tol);
+    IcpBufs own = {c->d_tar, c->d_T, c->d_iters, c->d_src};
+    int rc = icp_sequence_enqueue(c, tr, scans_xy, is_f64, scans, n, max_iter, tol, nullptr, 0.0, own);
     if (rc) return rc;
     return icp_sequence_finish(c, tr, scans, nullptr, nullptr, T_out, iters_out);
 }
@@ -576,7 +613,8 @@ extern "C" int b2s_icp_odometry(b2s_icp *c, const void *scans_xy, int is_f64, in
     DeviceGuard g(c->device);
     Trace tr(c->stream);
     int rc;
-    if (scans > 1 && (rc = icp_sequence_enqueue(c, tr, scans_xy, is_f64, scans, n, max_iter, tol))) return rc;
+    IcpBufs own = {c->d_tar, c->d_T, c->d_iters, c->d_src};
+    if (scans > 1 && (rc = icp_sequence_enqueue(c, tr, scans_xy, is_f64, scans, n, max_iter, tol, nullptr, 0.0, own))) return rc;
     const double state[3] = {x0, y0, th0};
     return icp_sequence_finish(c, tr, scans, state, traj_out, T_out, iters_out);
 }
@@ -598,8 +636,79 @@ extern "C" int b2s_icp_process_scans(b2s_icp *c, const float *ranges, const doub
     DeviceGuard g(c->device);
     Trace tr(c->stream);
     int rc;
-    if (scans > 1 && (rc = icp_sequence_enqueue(c, tr, ranges, 0, scans, n, max_iter, tol, beam_cs, clamp_inf_to))) return rc;
+    IcpBufs own = {c->d_tar, c->d_T, c->d_iters, c->d_src};
+    if (scans > 1 && (rc = icp_sequence_enqueue(c, tr, ranges, 0, scans, n, max_iter, tol, beam_cs, clamp_inf_to, own))) return rc;
     return icp_sequence_finish(c, tr, scans, state3, traj_out, T_out, iters_out);
+}
+
+// Streaming forms of b2s_icp_process_sequence / b2s_icp_process_scans: submit enqueues the uploads and the solves of a
+// scan stream on the slot's own device buffers and the read-back of its transforms on a third stream, and returns a
+// ticket; two calls may be in flight, so the scans of call k + 1 cross PCIe while call k is being solved.
+static int icp_submit(b2s_icp *c, const void *scans_data, int is_f64, const double *beam_cs, double clamp, int scans, int n,
+                      int max_iter, double tol, double *T_out, int32_t *iters_out, int *ticket_out)
+{
+    DeviceGuard g(c->device);
+    const int ticket = c->submitted;
+    b2s_icp::Slot &sl = c->slot[ticket & 1];
+    b2s_icp::Slot &other = c->slot[(ticket & 1) ^ 1];
+    if (sl.in_flight) {
+        B2S_CUDA(cudaEventSynchronize(sl.done));
+        sl.in_flight = false;
+    }
+    const int pairs = scans - 1;
+    Trace tr(c->stream);
+    B2S_CUDA(cudaStreamWaitEvent(c->copy_stream, sl.inputs_free, 0));
+    IcpBufs bufs = {sl.d_scans, sl.d_T, sl.d_iters, sl.d_cs};
+    int rc;
+    // while the other slot is being solved this call's upload is hidden anyway: fewer, larger chunks
+    if (pairs > 0 && (rc = icp_sequence_enqueue(c, tr, scans_data, is_f64, scans, n, max_iter, tol, beam_cs, clamp, bufs,
+                                                other.in_flight ? 2 : 0)))
+        return rc;
+    B2S_CUDA(cudaEventRecord(sl.inputs_free, c->stream));
+    B2S_CUDA(cudaEventRecord(c->solved, c->stream));
+    B2S_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->solved, 0));
+    if (pairs > 0) {
+        B2S_CUDA(cudaMemcpyAsync(T_out, sl.d_T.p, (size_t)pairs * 9 * sizeof(double), cudaMemcpyDeviceToHost, c->d2h_stream));
+        if (iters_out)
+            B2S_CUDA(cudaMemcpyAsync(iters_out, sl.d_iters.p, (size_t)pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, c->d2h_stream));
+    }
+    B2S_CUDA(cudaEventRecord(sl.done, c->d2h_stream));
+    sl.in_flight = true;
+    sl.ticket = ticket;
+    c->submitted = ticket + 1;
+    *ticket_out = ticket;
+    return B2S_OK;
+}
+
+extern "C" int b2s_icp_submit_sequence(b2s_icp *c, const void *scans_xy, int is_f64, int scans, int n, int max_iter,
+                                       double tol, double *T_out, int32_t *iters_out, int *ticket_out)
+{
+    B2S_REQUIRE(c && ticket_out, "b2s_icp_submit_sequence: null pointer");
+    B2S_REQUIRE(scans >= 0 && n > 0 && max_iter >= 0, "b2s_icp_submit_sequence: bad sizes");
+    B2S_REQUIRE(scans <= 1 || (scans_xy && T_out), "b2s_icp_submit_sequence: null pointer");
+    return icp_submit(c, scans_xy, is_f64, nullptr, 0.0, scans < 1 ? 1 : scans, n, max_iter, tol, T_out, iters_out, ticket_out);
+}
+
+extern "C" int b2s_icp_submit_scans(b2s_icp *c, const float *ranges, const double *beam_cs, double clamp_inf_to, int scans,
+                                    int n, int max_iter, double tol, double *T_out, int32_t *iters_out, int *ticket_out)
+{
+    B2S_REQUIRE(c && ticket_out, "b2s_icp_submit_scans: null pointer");
+    B2S_REQUIRE(scans >= 0 && n > 0 && max_iter >= 0, "b2s_icp_submit_scans: bad sizes");
+    B2S_REQUIRE(scans <= 1 || (ranges && beam_cs && T_out), "b2s_icp_submit_scans: null pointer");
+    B2S_REQUIRE(clamp_inf_to == clamp_inf_to, "b2s_icp_submit_scans: NaN clamp");
+    return icp_submit(c, ranges, 0, beam_cs, clamp_inf_to, scans < 1 ? 1 : scans, n, max_iter, tol, T_out, iters_out, ticket_out);
+}
+
+extern "C" int b2s_icp_wait(b2s_icp *c, int ticket)
+{
+    B2S_REQUIRE(c, "b2s_icp_wait: null handle");
+    B2S_REQUIRE(ticket >= 0 && ticket < c->submitted, "b2s_icp_wait: unknown ticket");
+    DeviceGuard g(c->device);
+    b2s_icp::Slot &sl = c->slot[ticket & 1];
+    if (!sl.in_flight || sl.ticket != ticket) return B2S_OK;
+    B2S_CUDA(cudaEventSynchronize(sl.done));
+    sl.in_flight = false;
+    return B2S_OK;
 }
 
 extern "C" int b2s_icp_find_nearest(b2s_icp *c, const double *src_xy, int n, const double *tar_xy,

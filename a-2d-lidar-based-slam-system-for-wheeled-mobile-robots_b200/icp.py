@@ -20,6 +20,19 @@ def _ros_param(name, default):
         return default
 
 
+class IcpTicket(object):
+    """Handle of a stream submitted with ICP.submit_sequence / submit_scans."""
+
+    def __init__(self, owner, ticket, T, iters, pairs):
+        self._owner, self._ticket, self._T, self._iters, self._pairs = owner, ticket, T, iters, pairs
+
+    def wait(self):
+        """Block until the transforms are in host memory: (T (P,3,3) float64, iterations (P,) int32)."""
+        _lib.check(self._owner._L.b2s_icp_wait(self._owner._h, self._ticket))
+        P = self._pairs
+        return self._T[:P].reshape(P, 3, 3), self._iters[:P]
+
+
 class ICP(object):
     """[ICP]:10-36.  max_iter / dis_th / tolerance default to the reference's 30 / 5 / 0.001.
 
@@ -146,6 +159,63 @@ class ICP(object):
                 self.tolerance if tolerance is None else float(tolerance),
                 _lib.ptr(T), _lib.ptr(iters)))
         return T.reshape(P, 3, 3), iters
+
+    # ------------------------------------------------------------------ streaming calls (two in flight)
+
+    def _stream_out(self, pairs):
+        """Page-locked result buffers of the next streamed call (two slots, re-allocated when the size grows)."""
+        slots = getattr(self, "_stream_slots", None)
+        if slots is None:
+            slots = self._stream_slots = [None, None]
+            self._stream_n = 0
+            self._stream_keep = [None, None]
+        k = self._stream_n % 2
+        if slots[k] is None or slots[k][0].shape[0] < max(pairs, 1):
+            slots[k] = (_lib.pinned_empty((max(pairs, 1), 9), np.float64), _lib.pinned_empty((max(pairs, 1),), np.int32))
+        return k, slots[k]
+
+    def submit_sequence(self, scans, max_iter=None, tolerance=None):
+        """process_sequence without the wait (b2s_icp_submit_sequence): the uploads and solves are enqueued and an
+        IcpTicket is returned at once; with two calls in flight the scans of the next stream cross PCIe while this one
+        is being solved.  ticket.wait() -> (T (K-1,3,3), iterations (K-1,)), views of page-locked buffers that the
+        second-next submit overwrites.  `scans` must stay untouched until then."""
+        scans = np.asarray(scans)
+        if scans.ndim != 3 or scans.shape[1] != 2 or scans.shape[2] < 1:
+            raise ValueError("expected scans (K,2,N), got %s" % (scans.shape,))
+        f64 = scans.dtype != np.float32
+        scans = np.ascontiguousarray(scans, dtype=np.float64 if f64 else np.float32)
+        K, N = scans.shape[0], scans.shape[2]
+        P = max(K - 1, 0)
+        k, (T, iters) = self._stream_out(P)
+        t = ctypes.c_int(-1)
+        _lib.check(self._L.b2s_icp_submit_sequence(
+            self._h, _lib.ptr(scans), 1 if f64 else 0, K, N, self.max_iter if max_iter is None else int(max_iter),
+            self.tolerance if tolerance is None else float(tolerance), _lib.ptr(T), _lib.ptr(iters), ctypes.byref(t)))
+        self._stream_n += 1
+        self._stream_keep[k] = scans
+        return IcpTicket(self, t.value, T, iters, P)
+
+    def submit_scans(self, ranges, angle_min, angle_max, clamp_inf_to=None, max_iter=None, tolerance=None):
+        """process_scans (raw ranges, no pose chain) without the wait; see submit_sequence."""
+        from b2slam import scan
+        ranges = np.ascontiguousarray(ranges, dtype=np.float32)
+        if ranges.ndim != 2 or ranges.shape[1] < 1:
+            raise ValueError("expected ranges (K,N) with N >= 1, got %s" % (ranges.shape,))
+        K, N = ranges.shape
+        key = (float(angle_min), float(angle_max), N)
+        if getattr(self, "_beam_key", None) != key:
+            self._beam_cs = scan.beam_table(angle_min, angle_max, N)
+            self._beam_key = key
+        P = max(K - 1, 0)
+        k, (T, iters) = self._stream_out(P)
+        t = ctypes.c_int(-1)
+        _lib.check(self._L.b2s_icp_submit_scans(
+            self._h, _lib.ptr(ranges), _lib.ptr(self._beam_cs), float(clamp_inf_to or 0.0), K, N,
+            self.max_iter if max_iter is None else int(max_iter),
+            self.tolerance if tolerance is None else float(tolerance), _lib.ptr(T), _lib.ptr(iters), ctypes.byref(t)))
+        self._stream_n += 1
+        self._stream_keep[k] = ranges
+        return IcpTicket(self, t.value, T, iters, P)
 
     def odometry(self, scans, state=(0.0, 0.0, 0.0), max_iter=None, tolerance=None):
         """The LiDAR-odometry loop of localization.py:66-83 for a recorded stream: process_sequence(scans) followed

@@ -291,6 +291,15 @@ int b2s_icp_odometry(b2s_icp *icp, const void *scans_xy, int is_f64, int scans, 
 int b2s_icp_process_scans(b2s_icp *icp, const float *ranges, const double *beam_cs, double clamp_inf_to, int scans,
                           int n, int max_iter, double tol, const double *state3, double *traj_out, double *T_out,
                           int32_t *iters_out);
+/* Streaming forms of b2s_icp_process_sequence / b2s_icp_process_scans (transforms only): submit enqueues the uploads, the
+ * solves and the read-back of T_out [scans-1][9] / iters_out [scans-1] (may be NULL) and returns a ticket; two calls may be
+ * in flight, so the scans of the next stream cross PCIe while this one is being solved.  The input array and the output
+ * buffers (page-locked for truly asynchronous copies) must stay valid and untouched until b2s_icp_wait(ticket) returns. */
+int b2s_icp_submit_sequence(b2s_icp *icp, const void *scans_xy, int is_f64, int scans, int n, int max_iter, double tol,
+                            double *T_out, int32_t *iters_out, int *ticket_out);
+int b2s_icp_submit_scans(b2s_icp *icp, const float *ranges, const double *beam_cs, double clamp_inf_to, int scans, int n,
+                         int max_iter, double tol, double *T_out, int32_t *iters_out, int *ticket_out);
+int b2s_icp_wait(b2s_icp *icp, int ticket);
 int b2s_icp_find_nearest(b2s_icp *icp, const double *src_xy, int n, const double *tar_xy, int m,
                          double *dist_out, int64_t *idx_out);
 int b2s_icp_get_transform(b2s_icp *icp, const double *src_xy, const double *tar_xy, int n,

@@ -479,3 +479,30 @@ def test_virtual_scan_matches_reference_laserEstimation_golden(env):
         want = g("ranges")
         assert np.array_equal(got == 100.0, want == 100.0), i       # the same bins were hit
         np.testing.assert_allclose(got, want, rtol=1e-13, atol=0)
+
+
+def test_streamed_sequence_calls_equal_blocking_calls(env):
+    """ICP.submit_sequence / submit_scans + IcpTicket.wait (two in flight) give exactly what process_sequence /
+    process_scans give, call by call, also when the streams differ in length."""
+    import math
+    xy, _ = env.synth.room_sequence(515, 700, 360)
+    chunks = [xy[0:300], xy[250:700], xy[100:101], xy[400:520]]
+    want = [env.icp.process_sequence(c) for c in chunks]
+    tickets, got = [], []
+    for k, c in enumerate(chunks):
+        tickets.append(env.icp.submit_sequence(c))
+        if k >= 1:
+            T, it = tickets[k - 1].wait()
+            got.append((T.copy(), it.copy()))
+    T, it = tickets[-1].wait()
+    got.append((T.copy(), it.copy()))
+    for (T, it), (wT, wit) in zip(got, want):
+        assert np.array_equal(T, wT) and np.array_equal(it, wit)
+    rng = np.hypot(xy[:200, 0], xy[:200, 1]).astype(np.float32)
+    wT, wit = env.icp.process_scans(rng, -math.pi, math.pi)
+    t1 = env.icp.submit_scans(rng, -math.pi, math.pi)
+    t2 = env.icp.submit_scans(rng[:50], -math.pi, math.pi)
+    T, it = t1.wait()
+    assert np.array_equal(T, wT) and np.array_equal(it, wit)
+    T2, it2 = t2.wait()
+    assert np.array_equal(T2, wT[:49]) and np.array_equal(it2, wit[:49])
