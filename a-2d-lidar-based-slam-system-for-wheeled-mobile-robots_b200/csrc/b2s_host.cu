@@ -40,6 +40,7 @@ extern int g_grid_variant;
 extern int g_icp_src_per_thread;
 extern int g_icp_prune;
 extern int g_icp_block;
+extern int g_icp_layout;
 int g_icp_graph = 1;  // 1: single-pair ICP calls replay a captured CUDA graph (default); 0: plain stream calls (tuning hook)
 constexpr int MAX_CHUNKS = 16;
 int g_tune_gen = 0;    // bumped by every b2s_tune: cached single-pair graphs captured under other settings are stale
@@ -255,8 +256,13 @@ extern "C" int b2s_tune(const char *key, int value)
         g_icp_graph = value;
         return B2S_OK;
     }
+    if (strcmp(key, "icp_layout") == 0) {
+        B2S_REQUIRE(value >= 0 && value <= 2, "b2s_tune: icp_layout must be 0, 1 or 2");
+        g_icp_layout = value;
+        return B2S_OK;
+    }
     if (strcmp(key, "icp_prune") == 0) {
-        B2S_REQUIRE(value >= 0 && value <= 3, "b2s_tune: icp_prune must be 0..3");
+        B2S_REQUIRE(value >= 0 && value <= 4, "b2s_tune: icp_prune must be 0..4");
         g_icp_prune = value;
         return B2S_OK;
     }

@@ -79,8 +79,10 @@ rigid_fit_kernel(const double *__restrict__ src_xy, const double *__restrict__ t
 }
 
 int g_icp_src_per_thread = 0;  // 0: choose per problem size; 2..4 force (tuning hook)
-int g_icp_prune = 2;           // 2: exact search, warp-level + per-lane block pruning (default); 1: per-lane only; 0: plain brute force
-int g_icp_block = 0;           // 0: 16 targets per pruning block up to 600 targets, 32 above; 8 / 16 / 32 force
+int g_icp_layout = 2;          // point groups per warp: 2 balanced when that takes no extra group (default); 1 balanced; 0 strided (tuning hook)
+int g_icp_prune = 4;           // exact search: 4 queued (default: both pruning tests, the surviving point x block pairs spread over the lanes);
+                               // 2 collective, warp-level + per-lane pruning; 3 warp-level only; 1 per-lane only; 0 plain brute force
+int g_icp_block = 0;           // targets per pruning block: 0 chooses per mode and scan size (8 up to 600 targets, 16 above); 8 / 16 / 32 force
 
 }  // namespace b2s
 

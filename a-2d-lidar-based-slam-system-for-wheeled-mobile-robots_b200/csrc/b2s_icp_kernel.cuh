@@ -27,10 +27,31 @@
 
 namespace b2s {
 
+#ifndef B2S_ICP_REGS_BLK8
+#define B2S_ICP_REGS_BLK8 72
+#endif
+#ifndef B2S_ICP_REGS_BLK16
+#define B2S_ICP_REGS_BLK16 80
+#endif
+
 constexpr int FIT_SUMS = 9;
 constexpr int NN_CHAINS = 4;
 constexpr int SUM_PAD = 10;                          // doubles per warp slot (9 sums, padded for 16-byte loads)
-constexpr int SCRATCH_DOUBLES = 2 * 32 * SUM_PAD;    // two buffers (alternating calls) x 32 warps
+// Bytes of the staging area: the input rows as they come (`in_bytes`), later reused for the block bounds (a float4
+// per block); rounded to 16.
+__host__ __device__ inline size_t icp_stage_bytes(size_t in_bytes, int nblk)
+{
+    const size_t b = (size_t)nblk * 16;
+    return ((in_bytes > b ? in_bytes : b) + 15) & ~(size_t)15;
+}
+
+// Reduction scratch of a CTA of `nwarps` warps, in doubles: two buffers (alternating calls) of nwarps x SUM_PAD for
+// cta_sum9, and 4 x 32 for the block_sum<4> of the set-up.
+__host__ __device__ inline int icp_scratch_doubles(int nwarps)
+{
+    const int a = 2 * nwarps * SUM_PAD;
+    return a > 128 ? a : 128;
+}
 
 // Sum of 8 values over the warp with 9 shuffles instead of 40: at offsets 16, 8, 4 every lane hands the half of
 // its values it is not responsible for to its partner and keeps the other half, so the value count halves while
@@ -64,7 +85,7 @@ __device__ __forceinline__ void cta_sum9(double (&v)[FIT_SUMS], double *scratch,
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwarps = (blockDim.x + 31) >> 5;
-    double *buf = scratch + phase * (32 * SUM_PAD);
+    double *buf = scratch + phase * (nwarps * SUM_PAD);
     phase ^= 1;
     const double v8[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
     const double t = warp_sum8_transposed(v8, lane);
@@ -171,6 +192,17 @@ __device__ __forceinline__ void cta_rigid_fit(const double (&ax)[R], const doubl
     extra = v[8];
 }
 
+// An upper bound of sqrt(x) for the pruning radii, x >= 0 in float32: the approximate square root (one MUFU, relative
+// error <= 2^-22 by the PTX ISA, subnormal inputs flushed to zero) times 1 + 2^-20, plus more than the root of the
+// largest flushed input.  Like the rounded-up exact root it replaces (a range check, a branch and six instructions),
+// this only widens what the search looks at; inf stays inf and NaN stays NaN, which make every skip test false.
+__device__ __forceinline__ float sqrt_up(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, 1.000001f, 2e-19f);
+}
+
 // ---------------------------------------------------------------- the reference's distance and its ties
 //
 // findNearest orders candidates by np.linalg.norm(src[i] - tar[j]) with a strict '<' in ascending j ([ICP]:99-106).
@@ -193,12 +225,14 @@ __device__ __forceinline__ double ref_dist(double dx, double dy)
 
 // Exhaustive search for ONE source point (px, py: warp-uniform) over all m targets by the reference's rule; the 32
 // lanes take every 32nd target and the partial winners are merged with "smaller distance, then lower index".
+// PAD_BLK > 0: the target array has one unused slot after every PAD_BLK points (queued search, see below).
+template <int PAD_BLK>
 static __device__ __noinline__ int warp_careful_nearest(double px, double py, const double2 *tar, int m, int lane)
 {
     double bd = INFINITY;
     int bj = 0;
     for (int j = lane; j < m; j += 32) {
-        const double2 t = tar[j];
+        const double2 t = tar[PAD_BLK ? j + j / PAD_BLK : j];
         const double d = ref_dist(px - t.x, py - t.y);
         if (d < bd) {
             bd = d;
@@ -227,6 +261,84 @@ static __device__ __noinline__ int warp_careful_nearest(double px, double py, co
         }                                                   \
     } while (0)
 
+// ---------------------------------------------------------------- the queued search (PRUNE == 4)
+//
+// The collective search (PRUNE 1..3) evaluates a block with the whole warp as soon as ONE of its 32 source points needs
+// it: 32 consecutive points need the union of ~5 blocks, each point only 1-2 of them, so two thirds of the distance
+// evaluations are spent on blocks the lane's own bound already excludes.  The queued search keeps the two pruning tests
+// (same bounds, same proof) but only RECORDS what survives them: every (source point, block) pair that passes the
+// per-lane test becomes one 4-byte item in a per-warp queue in shared memory, the items of a warp's R x 32 points are
+// then spread evenly over the 32 lanes (lane l takes items l, l + 32, ...: one block of NN_BLK targets against one
+// point each, so every evaluation is one some point needs), the per-item winners go to fixed result slots, and each
+// point merges its own <= QK results in ascending block order with the same compare as everything else.  A point that
+// needs more than QK blocks (a loose first-iteration bound, NaN coordinates) sends its whole group of 32 through the
+// collective search instead.  For the items' loads to be conflict-free the target array carries one unused slot after
+// every NN_BLK points (block stride NN_BLK + 1: neighbouring blocks start 4 banks apart), filled with NaN like the
+// tail of a ragged last block -- NaN never wins and never raises the near-tie flag.
+constexpr int QK = 3;                     // queued items (= result slots) per source point
+constexpr int QCAND = 12;                 // candidate blocks of a group of 32 points beyond which it goes collective
+constexpr unsigned NAN_HI = 0x7ff80000u;  // high word of the padding NaN
+
+// Collective search of one group of 32 points on the padded target layout: the PRUNE == 2 algorithm (warp-level test,
+// per-lane test, whole-warp visits).  Returns the winner's index, bit 31 = near-tie flag.
+template <int NN_BLK>
+static __device__ __noinline__ unsigned collective_nearest_padded(double px, double py, bool real, int arg_prev,
+                                                                   const double2 *tar, const float4 *bnd, int nblk,
+                                                                   int lane)
+{
+    const double2 g = tar[arg_prev + arg_prev / NN_BLK];
+    const double gx = px - g.x, gy = py - g.y;
+    const double ub = fma(gy, gy, gx * gx);
+    const float suf = sqrt_up(__double2float_ru(ub));
+    const float pxf = __double2float_rn(px), pyf = __double2float_rn(py);
+    const float suE = __fmul_ru(__fadd_ru(suf, __fmul_ru(__fadd_ru(fabsf(pxf), fabsf(pyf)), 2.3841858e-7f)), 1.000002f);
+    const int mid = __popc(__ballot_sync(0xffffffffu, real)) >> 1;
+    const double wx = __shfl_sync(0xffffffffu, px, mid), wy = __shfl_sync(0xffffffffu, py, mid);
+    const double ex = px - wx, ey = py - wy;
+    const float ef = real ? __fadd_ru(sqrt_up(__double2float_ru(fma(ey, ey, ex * ex))), suf) * 1.000001f : 0.0f;
+    const float gmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(ef)));
+    const float wxf = __double2float_rn(wx), wyf = __double2float_rn(wy);
+    const float gE = __fmul_ru(__fadd_ru(gmax, __fmul_ru(__fadd_ru(fabsf(wxf), fabsf(wyf)), 2.3841858e-7f)), 1.000002f);
+    unsigned bh[NN_CHAINS];
+    int bj[NN_CHAINS];
+    bool near = false;
+#pragma unroll
+    for (int q = 0; q < NN_CHAINS; ++q) {
+        bh[q] = 0x7ff00000u;
+        bj[q] = 0;
+    }
+    for (int base = 0; base < nblk; base += 32) {
+        bool keep = false;
+        if (base + lane < nblk) {
+            const float4 c = bnd[base + lane];
+            const float cxd = wxf - c.x, cyd = wyf - c.y;
+            const float reach = __fadd_ru(c.z, gE);
+            keep = !(fmaf(cyd, cyd, cxd * cxd) > __fmul_ru(reach, reach));
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, keep);
+        while (todo) {
+            const int b = base + __ffs(todo) - 1;
+            todo &= todo - 1;
+            const float4 c = bnd[b];
+            const float cxd = pxf - c.x, cyd = pyf - c.y;
+            const float reach = __fadd_ru(c.z, suE);
+            const bool skip = !real || (fmaf(cyd, cyd, cxd * cxd) > __fmul_ru(reach, reach));
+            if (__all_sync(0xffffffffu, skip)) continue;
+            const double2 *blk = tar + b * (NN_BLK + 1);
+#pragma unroll
+            for (int jj = 0; jj < NN_BLK; ++jj) {
+                const double2 t = blk[jj];
+                const double dx = px - t.x, dy = py - t.y;
+                const unsigned fh = (unsigned)__double2hiint(fma(dy, dy, dx * dx));
+                B2S_NN_STEP(fh, bh[jj % NN_CHAINS], bj[jj % NN_CHAINS], b * NN_BLK + jj, near);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 1; q < NN_CHAINS; ++q) B2S_NN_STEP(bh[q], bh[0], bj[0], bj[q], near);
+    return (unsigned)bj[0] | (near ? 0x80000000u : 0u);
+}
+
 // Targets per pruning block (NN_BLK): 8 is fastest at 360 beams, 16 at 1080 with the warp-level test in front
 // (16 / 32 with the per-lane test alone); chosen per launch, see launch_icp_r.
 
@@ -240,7 +352,7 @@ static __device__ __noinline__ int warp_careful_nearest(double px, double py, co
 // and the points are formed here exactly as laserToNumpy does ([ICP]:216-229, [SLAM]:115-123): float64
 // (cos a * r, sin a * r) with the beam table computed by the host's NumPy, +inf -> clamp when clamp > 0.
 template <typename TIn, int R, int PRUNE, int NN_BLK, bool RANGES = false>
-__global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__restrict__ src_xy, int n,
+__global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? B2S_ICP_REGS_BLK8 : B2S_ICP_REGS_BLK16) : 104) icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__restrict__ src_xy, int n,
                                  int m, int max_iter, double tol, double *__restrict__ T_out,
                                  int32_t *__restrict__ iters_out, int use_bulk,
                                  const double2 *__restrict__ beam_cs = nullptr, double clamp = 0.0)
@@ -258,12 +370,26 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_ke
             y = (double)scan[count + i];
         }
     };
+    constexpr bool QUEUED = PRUNE == 4;
+    constexpr int PAD_BLK = QUEUED ? NN_BLK : 0;      // one unused slot after every PAD_BLK targets (queued search)
+    // Per warp: QCAP queue entries (4 bytes) directly followed by QCAP result slots (8 bytes).  A group that turns out
+    // to need the collective search may have queued up to QCAND x 32 entries before it is rolled back; they spill into
+    // the result slots, which nothing reads before phase B has rewritten them.
+    constexpr int QCAP = R * QK * 32;
+    static_assert(!QUEUED || QCAND * 32 <= QK * 32 + 2 * QCAP, "queue overrun must stay inside the warp's result slots");
+    const int nblk = (m + NN_BLK - 1) / NN_BLK;
+    auto TI = [](int j) { return PAD_BLK ? j + j / (PAD_BLK ? PAD_BLK : 1) : j; };  // index into tar[]
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [mbarrier 16 B][scratch][tar double2 * m][staging TIn * 2m]
+    // layout: [mbarrier 16 B][scratch][tar double2 * m (queued: nblk * (NN_BLK + 1))][staging TIn * 2m, 16-byte rounded]
+    //         queued search only: [moved source double2 * R * threads][per warp: queue u32 * QCAP, results uint2 * QCAP]
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     double *scratch = reinterpret_cast<double *>(smem_raw + 16);
-    double2 *tar = reinterpret_cast<double2 *>(smem_raw + 16 + SCRATCH_DOUBLES * sizeof(double));
-    TIn *stage = reinterpret_cast<TIn *>(tar + m);
+    double2 *tar = reinterpret_cast<double2 *>(smem_raw + 16 + icp_scratch_doubles(blockDim.x >> 5) * sizeof(double));
+    const int tar_slots = QUEUED ? nblk * (NN_BLK + 1) : m;
+    TIn *stage = reinterpret_cast<TIn *>(tar + tar_slots);
+    double2 *srcm = reinterpret_cast<double2 *>(reinterpret_cast<unsigned char *>(stage) +
+                                               icp_stage_bytes((size_t)ROWS * m * sizeof(TIn), nblk));
+    unsigned *queue_all = reinterpret_cast<unsigned *>(srcm + (QUEUED ? R * blockDim.x : 0));  // 3 * QCAP words per warp
 
     const int pair = blockIdx.x;
     const int tid = threadIdx.x;
@@ -271,7 +397,7 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_ke
     const TIn *src_g = src_xy + (size_t)pair * ROWS * n;
 
     // ---- stage the target scan: global -> shared via the bulk-copy engine when alignment allows
-    if (use_bulk) {
+    if (use_bulk & 1) {
         if (tid == 0) {
             mbar_init(bar, 1);
             fence_mbar_init();
@@ -287,14 +413,29 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_ke
     }
 
     // ---- this thread's source points (registers for the whole solve); overlaps the copy
+    // The scan is cut into groups of `gs` consecutive points, the same number of groups for every warp (round r of warp
+    // w holds group r * nwarps + w in its low lanes): 360 and 1080 beams both give groups of 30, so the warps reach the
+    // one barrier of an iteration together instead of the last warp carrying a short tail group.
+    const int nwarps_ = blockDim.x >> 5;
+    const int rounds = ((n + 31) / 32 + nwarps_ - 1) / nwarps_;  // <= R by the launch geometry
+    const int gs = (n + nwarps_ * rounds - 1) / (nwarps_ * rounds);
+    // ... unless that takes more groups than the strided layout (point tid + r * threads, a short tail group), which
+    // costs more than the imbalance (1080 beams on 12 warps: 36 against 34); use_bulk bits 1-2: 0 strided, 1 balanced, 2 auto
+    const int layout = (use_bulk >> 1) & 3;
+    const bool balanced = layout == 1 || (layout == 2 && nwarps_ * rounds <= (n + 31) / 32);
+    auto point_index = [&](int r) -> int {  // -1: no point in this slot
+        if (!balanced) return tid + r * (int)blockDim.x < n ? tid + r * (int)blockDim.x : -1;
+        const int i = (r * nwarps_ + (tid >> 5)) * gs + (tid & 31);
+        return (r < rounds && (tid & 31) < gs && i < n) ? i : -1;
+    };
     double sx[R], sy[R];  // moved by every iteration; the originals are read again for the final fit
     int count = 0;
     double first[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const int i = tid + r * blockDim.x;
+        const int i = point_index(r);
         sx[r] = sy[r] = 0.0;
-        if (i < n) {
+        if (i >= 0) {
             point(src_g, n, i, sx[r], sy[r]);
             count = r + 1;
             first[0] += sx[r];
@@ -302,14 +443,19 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_ke
         }
     }
 
-    if (use_bulk) mbar_wait(bar, 0);
+    if (use_bulk & 1) mbar_wait(bar, 0);
     else __syncthreads();
     for (int j = tid; j < m; j += blockDim.x) {
         double2 t;
         point(stage, m, j, t.x, t.y);
-        tar[j] = t;
+        tar[TI(j)] = t;
         first[2] += t.x;
         first[3] += t.y;
+    }
+    if (QUEUED) {  // the unused slot of every block and the tail of a ragged last block: NaN never wins, never ties
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+        for (int b = tid; b < nblk; b += blockDim.x) tar[b * (NN_BLK + 1) + NN_BLK] = make_double2(qnan, qnan);
+        for (int j = m + tid; j < nblk * NN_BLK; j += blockDim.x) tar[TI(j)] = make_double2(qnan, qnan);
     }
     // fixed shifts for the one-pass fits: centroid of the original source, centroid of the target scan
     block_sum<4>(first, scratch);  // its barriers also publish tar[]
@@ -329,22 +475,22 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_ke
     // E = 2^-22 (|pfx| + |pfy|): then the true |p - c| exceeds rad + su, i.e. every point of the block is farther than
     // the upper bound su >= sqrt(ub) (1 + 2^-23) on the nearest distance.  NaN / inf anywhere make the comparison false:
     // nothing is skipped.  The staging area is free again and holds the bounds: [nblk] float4.
-    const int nblk = (m + NN_BLK - 1) / NN_BLK;
     float4 *bnd = reinterpret_cast<float4 *>(stage);
     if (PRUNE) {
         for (int b = tid; b < nblk; b += blockDim.x) {
             const int j0 = b * NN_BLK, j1 = min(m, j0 + NN_BLK);
-            double x0 = tar[j0].x, x1 = x0, y0 = tar[j0].y, y1 = y0;
+            const double2 *tb = tar + TI(j0) - j0;  // (a block is contiguous in both layouts)
+            double x0 = tb[j0].x, x1 = x0, y0 = tb[j0].y, y1 = y0;
             for (int j = j0 + 1; j < j1; ++j) {
-                x0 = fmin(x0, tar[j].x); x1 = fmax(x1, tar[j].x);
-                y0 = fmin(y0, tar[j].y); y1 = fmax(y1, tar[j].y);
+                x0 = fmin(x0, tb[j].x); x1 = fmax(x1, tb[j].x);
+                y0 = fmin(y0, tb[j].y); y1 = fmax(y1, tb[j].y);
             }
             const float cfx = __double2float_rn(0.5 * (x0 + x1)), cfy = __double2float_rn(0.5 * (y0 + y1));
             const double cx = (double)cfx, cy = (double)cfy;
             double rad2 = 0.0;
             bool finite = true;
             for (int j = j0; j < j1; ++j) {
-                const double dx = tar[j].x - cx, dy = tar[j].y - cy;
+                const double dx = tb[j].x - cx, dy = tb[j].y - cy;
                 const double d2 = fma(dy, dy, dx * dx);
                 finite = finite && (d2 == d2) && (d2 < INFINITY);
                 rad2 = fmax(rad2, d2);
@@ -361,8 +507,13 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_ke
     int arg[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const long long i = tid + r * blockDim.x;
+        const long long i = max(0, point_index(r));
         arg[r] = (int)min((long long)(m - 1), i * m / n);
+    }
+
+    if (QUEUED) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) srcm[tid + r * blockDim.x] = make_double2(sx[r], sy[r]);
     }
 
     double prev_err = 0.0;
@@ -377,7 +528,7 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_ke
                 const int src_lane = __ffs(need) - 1;
                 need &= need - 1;
                 const double qx = __shfl_sync(0xffffffffu, px, src_lane), qy = __shfl_sync(0xffffffffu, py, src_lane);
-                const int j = warp_careful_nearest(qx, qy, tar, m, lane_id);
+                const int j = warp_careful_nearest<PAD_BLK>(qx, qy, tar, m, lane_id);
                 if (lane_id == src_lane) winner = j;
             }
         };
@@ -402,6 +553,151 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_ke
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) settle(near[r] && r < count, sx[r], sy[r], arg[r]);
+        } else if (QUEUED) {
+            const int lane = tid & 31;
+            unsigned *q = queue_all + (tid >> 5) * (3 * QCAP);
+            uint2 *res = reinterpret_cast<uint2 *>(q + QCAP);
+            const unsigned lt = (1u << lane) - 1u;
+            unsigned total = 0;       // items queued by this warp (warp-uniform)
+            unsigned collective = 0;  // bit r: group r goes through the collective search
+            int cnt[R];
+            // ---- phase A: the two pruning tests; what survives is queued, one candidate block after the other
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const bool real = r < count;
+                const double px = sx[r], py = sy[r];
+                const double2 g = tar[TI(arg[r])];
+                const double gx = px - g.x, gy = py - g.y;
+                const double ub = fma(gy, gy, gx * gx);
+                const float suf = sqrt_up(__double2float_ru(ub));
+                const float pxf = __double2float_rn(px), pyf = __double2float_rn(py);
+                const float suE = __fmul_ru(__fadd_ru(suf, __fmul_ru(__fadd_ru(fabsf(pxf), fabsf(pyf)), 2.3841858e-7f)),
+                                            1.000002f);
+                const int mid = __popc(__ballot_sync(0xffffffffu, real)) >> 1;
+                const double wx = __shfl_sync(0xffffffffu, px, mid), wy = __shfl_sync(0xffffffffu, py, mid);
+                const double ex = px - wx, ey = py - wy;
+                const float ef = real ? __fadd_ru(sqrt_up(__double2float_ru(fma(ey, ey, ex * ex))), suf) * 1.000001f
+                                      : 0.0f;
+                const float gmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(ef)));
+                const float wxf = __double2float_rn(wx), wyf = __double2float_rn(wy);
+                const float gE = __fmul_ru(__fadd_ru(gmax, __fmul_ru(__fadd_ru(fabsf(wxf), fabsf(wyf)), 2.3841858e-7f)),
+                                           1.000002f);
+                const unsigned start = total;
+                // item: point slot (12 bits) | block (10 bits) << 12 | result slot r * QK + k (5 bits) << 22
+                const unsigned item0 = (unsigned)(tid + r * blockDim.x) | ((unsigned)(r * QK) << 22);
+                unsigned item = item0;
+                int ncand = 0;
+                for (int base = 0; base < nblk; base += 32) {
+                    bool keep = false;
+                    if (base + lane < nblk) {
+                        const float4 cb = bnd[base + lane];
+                        const float cxd = wxf - cb.x, cyd = wyf - cb.y;
+                        const float reach = __fadd_ru(cb.z, gE);
+                        keep = !(fmaf(cyd, cyd, cxd * cxd) > __fmul_ru(reach, reach));
+                    }
+                    unsigned todo = __ballot_sync(0xffffffffu, keep);
+                    ncand += __popc(todo);
+                    if (ncand > QCAND) break;  // (the queue has room for QCAND candidate blocks x 32 points per group)
+                    while (todo) {  // two candidate blocks per pass (independent loads and tests)
+                        const int b0 = base + __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const bool two = todo != 0;
+                        const int b1 = two ? base + __ffs(todo) - 1 : b0;
+                        todo &= todo - 1;
+                        const float4 c0 = bnd[b0], c1 = bnd[b1];
+                        const float x0 = pxf - c0.x, y0 = pyf - c0.y, x1 = pxf - c1.x, y1 = pyf - c1.y;
+                        const float reach0 = __fadd_ru(c0.z, suE), reach1 = __fadd_ru(c1.z, suE);
+                        const bool need0 = real && !(fmaf(y0, y0, x0 * x0) > __fmul_ru(reach0, reach0));
+                        const bool need1 = real && two && !(fmaf(y1, y1, x1 * x1) > __fmul_ru(reach1, reach1));
+                        const unsigned m0 = __ballot_sync(0xffffffffu, need0), m1 = __ballot_sync(0xffffffffu, need1);
+                        if (need0) q[total + __popc(m0 & lt)] = item + ((unsigned)b0 << 12);
+                        item += need0 ? (1u << 22) : 0u;
+                        total += __popc(m0);
+                        if (need1) q[total + __popc(m1 & lt)] = item + ((unsigned)b1 << 12);
+                        item += need1 ? (1u << 22) : 0u;
+                        total += __popc(m1);
+                    }
+                }
+                const int c = (int)((item - item0) >> 22);
+                // too many candidate blocks, or a point that needs more blocks than it has result slots
+                if (ncand > QCAND || __any_sync(0xffffffffu, c > QK)) {
+                    total = start;
+                    collective |= 1u << r;
+                }
+                cnt[r] = c;
+            }
+            __syncwarp();
+            // ---- phase B: one item per lane and pass, NN_BLK targets against one point.  The block-local index rides in
+            // the low bits of the key (high word of the squared distance, low bits masked), so the smallest and the
+            // second smallest key of the block come out of a min / max tournament; two keys less than two mask units
+            // apart raise the near-tie flag (the exhaustive careful search then decides).
+            constexpr unsigned KMASK = NN_BLK - 1;  // NN_BLK is a power of two
+            for (unsigned t0 = 0; t0 < total; t0 += 32) {
+                const unsigned t = t0 + lane;
+                const bool valid = t < total;
+                const unsigned e = q[valid ? t : 0u];  // (an idle lane repeats item 0 and drops the result)
+                const double2 p = srcm[e & 0xfffu];
+                const unsigned b = (e >> 12) & 0x3ffu;
+                const double2 *blk = tar + b * (NN_BLK + 1);
+                unsigned lo[NN_BLK], hi[NN_BLK];
+#pragma unroll
+                for (int jj = 0; jj < NN_BLK; ++jj) {
+                    const double2 tg = blk[jj];
+                    const double dx = p.x - tg.x, dy = p.y - tg.y;
+                    lo[jj] = ((unsigned)__double2hiint(fma(dy, dy, dx * dx)) & ~KMASK) | (unsigned)jj;
+                }
+#pragma unroll
+                for (int jj = 0; jj < NN_BLK; jj += 2) {
+                    const unsigned x = lo[jj], y = lo[jj + 1];
+                    lo[jj] = min(x, y);
+                    hi[jj] = max(x, y);
+                }
+#pragma unroll
+                for (int w = 2; w < NN_BLK; w *= 2)
+#pragma unroll
+                    for (int jj = 0; jj < NN_BLK; jj += 2 * w) {
+                        const unsigned la = lo[jj], lb = lo[jj + w];
+                        hi[jj] = min(min(hi[jj], hi[jj + w]), max(la, lb));
+                        lo[jj] = min(la, lb);
+                    }
+                const bool near = ((hi[0] & ~KMASK) - (lo[0] & ~KMASK)) <= NN_BLK;
+                if (valid) res[(e >> 22) * 32 + (e & 31u)] = make_uint2(lo[0], b | (near ? 0x80000000u : 0u));
+            }
+            __syncwarp();
+            // ---- phase C: every point merges its own results, blocks ascending
+            unsigned flagged = 0;  // bit r: point r of this lane is a near tie
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                bool near = false;
+                if (collective & (1u << r)) {
+                    const unsigned w = collective_nearest_padded<NN_BLK>(sx[r], sy[r], r < count, arg[r], tar, bnd, nblk, lane);
+                    arg[r] = (int)(w & 0x7fffffffu);
+                    near = (w >> 31) != 0;
+                } else if (__all_sync(0xffffffffu, cnt[r] <= 1)) {  // the usual case: one block per point
+                    const uint2 v = res[(r * QK) * 32 + lane];
+                    const bool any = cnt[r] != 0;
+                    arg[r] = any ? (int)((v.y & 0x3ffu) * NN_BLK + (v.x & KMASK)) : 0;
+                    near = any && ((v.y >> 31) != 0 || v.x >= 0x7ff00000u);  // (nothing finite in the block: let the careful search decide)
+                } else {
+                    unsigned bh = 0x7ff00000u;
+                    int bj = 0;
+                    for (int k = 0; k < cnt[r]; ++k) {
+                        const uint2 v = res[(r * QK + k) * 32 + lane];
+                        const unsigned fh = v.x & ~KMASK;
+                        near |= (v.y >> 31) != 0 || (fh - bh + NN_BLK) <= 2u * NN_BLK;
+                        if (fh < bh) {
+                            bh = fh;
+                            bj = (int)((v.y & 0x3ffu) * NN_BLK + (v.x & KMASK));
+                        }
+                    }
+                    arg[r] = bj;
+                }
+                flagged |= (near && r < count) ? (1u << r) : 0u;
+            }
+            if (__any_sync(0xffffffffu, flagged != 0)) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) settle((flagged >> r) & 1u, sx[r], sy[r], arg[r]);
+            }
         } else {
             // Exact search with pruning.  ANY target gives an upper bound ub on the nearest distance; a block
             // whose every point is provably farther than sqrt(ub) cannot contain the nearest point nor tie
@@ -420,13 +716,13 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_ke
             for (int r = 0; r < R; ++r) {
                 const bool real = r < count;
                 const double px = sx[r], py = sy[r];
-                const double2 g = tar[arg[r]];
+                const double2 g = tar[TI(arg[r])];
                 const double gx = px - g.x, gy = py - g.y;
                 const double ub = fma(gy, gy, gx * gx);
                 // sqrt(ub) rounded UP in float (two instructions instead of a double-precision square root); an
                 // upper bound is all the tests need.  NaN stays NaN, overflow gives inf: then nothing is skipped.
                 // The factor (> 1 + 2^-23) covers the rounding of the double-precision tests below.
-                const float suf = __fmul_ru(__fsqrt_ru(__double2float_ru(ub)), 1.0000002f);
+                const float suf = sqrt_up(__double2float_ru(ub));
                 // the point in float32 for the block tests, its rounding allowance E, and su + E with the (1 + 2^-19)
                 const float pxf = __double2float_rn(px), pyf = __double2float_rn(py);
                 const float suE = __fmul_ru(__fadd_ru(suf, __fmul_ru(__fadd_ru(fabsf(pxf), fabsf(pyf)), 2.3841858e-7f)),
@@ -473,7 +769,7 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_ke
                     const int mid = __popc(__ballot_sync(0xffffffffu, real)) >> 1;  // real lanes are the low ones
                     const double wx = __shfl_sync(0xffffffffu, px, mid), wy = __shfl_sync(0xffffffffu, py, mid);
                     const double ex = px - wx, ey = py - wy;
-                    const float ef = real ? __fadd_ru(__fsqrt_ru(__double2float_ru(fma(ey, ey, ex * ex))), suf) * 1.000001f
+                    const float ef = real ? __fadd_ru(sqrt_up(__double2float_ru(fma(ey, ey, ex * ex))), suf) * 1.000001f
                                           : 0.0f;  // every step rounds up; NaN bits compare above all
                     const float gmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(ef)));
                     // the same float32 test as lane_skips, for the common centre w and the warp's bound gmax
@@ -516,7 +812,7 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_ke
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (PRUNE && r >= count) arg[r] = 0;  // idle slot: keep the index in range
-            const double2 t = tar[arg[r]];
+            const double2 t = tar[TI(arg[r])];
             bx[r] = t.x;
             by[r] = t.y;
             if (r < count) {
@@ -532,6 +828,7 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_ke
             const double x = sx[r], y = sy[r];
             sx[r] = T[0] * x + T[1] * y + T[2];
             sy[r] = T[3] * x + T[4] * y + T[5];
+            if (QUEUED) srcm[tid + r * blockDim.x] = make_double2(sx[r], sy[r]);
         }
         ++iters;
         const double err = dsum / (double)n;
@@ -544,9 +841,9 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_ke
     double ox_[R], oy_[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const int i = tid + r * blockDim.x;
+        const int i = point_index(r);
         ox_[r] = oy_[r] = 0.0;
-        if (i < n) point(src_g, n, i, ox_[r], oy_[r]);
+        if (i >= 0) point(src_g, n, i, ox_[r], oy_[r]);
     }
     cta_rigid_fit<R>(ox_, oy_, sx, sy, count, n, sax, say, sax, say, unused, scratch, phase, T);  // [ICP]:81
     if (tid == 0) {
@@ -561,6 +858,23 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? 72 : 80) : 104) icp_batch_ke
 extern int g_icp_src_per_thread;
 extern int g_icp_prune;
 extern int g_icp_block;
+extern int g_icp_layout;
+
+// Dynamic shared memory of one CTA (the layout at the top of the kernel); in_bytes = bytes of the staged input rows.
+template <int PRUNE, int NN_BLK, int R>
+static size_t icp_smem_bytes(int n_tar, size_t in_bytes, int threads)
+{
+    const size_t nblk = ((size_t)n_tar + NN_BLK - 1) / NN_BLK;
+    size_t bytes = 16 + icp_scratch_doubles(threads / 32) * sizeof(double) + icp_stage_bytes(in_bytes, (int)nblk);
+    if (PRUNE == 4) {
+        bytes += nblk * (NN_BLK + 1) * sizeof(double2);                       // padded targets
+        bytes += (size_t)R * threads * sizeof(double2);                       // moved source points
+        bytes += (size_t)(threads / 32) * (size_t)(R * QK * 32) * (sizeof(unsigned) + sizeof(uint2));  // queues + results
+    } else {
+        bytes += (size_t)n_tar * sizeof(double2);
+    }
+    return bytes;
+}
 
 template <typename TIn, int R, int PRUNE, int NN_BLK>
 static int launch_icp_rp(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_src, int n_tar, int max_iter,
@@ -570,8 +884,7 @@ static int launch_icp_rp(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_
     threads = ((threads + 31) / 32) * 32;
     if (threads < 64) threads = 64;
     B2S_REQUIRE(threads <= 1024, "b2s_icp_batch: too many source points per scan");
-    const size_t smem = 16 + SCRATCH_DOUBLES * sizeof(double) + (size_t)n_tar * sizeof(double2) +
-                        (size_t)n_tar * 2 * sizeof(TIn);
+    const size_t smem = icp_smem_bytes<PRUNE, NN_BLK, R>(n_tar, (size_t)n_tar * 2 * sizeof(TIn), threads);
     B2S_REQUIRE(smem <= 227 * 1024, "b2s_icp_batch: n_tar too large for shared memory");
     // opt-in above 48 KB; the attribute is per device and per function, and setting it is cheap
     if (smem > 48 * 1024)
@@ -579,7 +892,7 @@ static int launch_icp_rp(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_
                                       (int)smem));
     // bulk copy needs 16-byte aligned source and size: every pair's target block must qualify
     const size_t pair_bytes = (size_t)2 * n_tar * sizeof(TIn);
-    const int use_bulk = ((uintptr_t)tar_xy % 16 == 0) && (pair_bytes % 16 == 0);
+    const int use_bulk = (((uintptr_t)tar_xy % 16 == 0) && (pair_bytes % 16 == 0) ? 1 : 0) | (g_icp_layout << 1);
     if (threads > 512) {  // (large scans only: the query is not free)
         cudaFuncAttributes fa;
         B2S_CUDA(cudaFuncGetAttributes(&fa, icp_batch_kernel<TIn, R, PRUNE, NN_BLK>));
@@ -597,11 +910,15 @@ static int launch_icp_r(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_s
 {
     // the block bounds live in the staging area: [ceil(m/blk)] float4 must fit in 2*m*sizeof(TIn)
     const int blk = (g_icp_block == 8 || g_icp_block == 16 || g_icp_block == 32) ? g_icp_block
-                    : (g_icp_prune >= 2 ? (n_tar <= 600 ? 8 : 16) : (n_tar <= 600 ? 16 : 32));  // measured best per mode
+                    : (g_icp_prune == 4 ? 8 : g_icp_prune >= 2 ? (n_tar <= 600 ? 8 : 16) : (n_tar <= 600 ? 16 : 32));  // measured best per mode
     const bool fits = (size_t)((n_tar + blk - 1) / blk) * 16 <= (size_t)2 * n_tar * sizeof(TIn);
 #define B2S_ICP_GO(P, B) \
     return launch_icp_rp<TIn, R, P, B>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream)
     if (g_icp_prune && fits) {
+        if (g_icp_prune == 4) {
+            if (blk == 8) B2S_ICP_GO(4, 8);
+            B2S_ICP_GO(4, 16);
+        }
         if (g_icp_prune == 3) {
             if (blk == 8) B2S_ICP_GO(3, 8);
             if (blk == 16) B2S_ICP_GO(3, 16);
@@ -645,25 +962,25 @@ static int icp_points_per_thread(int n_src)
 }
 
 // Fused-ingestion form: raw ranges + beam table (always the default search, PRUNE = 2).
-template <int R, int NN_BLK>
-static int launch_icp_ranges_rb(const float *tar_r, const float *src_r, const double *beam_cs, double clamp, int pairs,
+template <int R, int NN_BLK, int PRUNE>
+static int launch_icp_ranges_rbp(const float *tar_r, const float *src_r, const double *beam_cs, double clamp, int pairs,
                                 int n, int max_iter, double tol, double *T_out, int32_t *iters_out, void *stream)
 {
     int threads = ((((n + R - 1) / R) + 31) / 32) * 32;
     if (threads < 64) threads = 64;
     B2S_REQUIRE(threads <= 1024, "b2s_icp_batch_ranges: too many beams per scan");
-    const size_t smem = 16 + SCRATCH_DOUBLES * sizeof(double) + (size_t)n * sizeof(double2) + (size_t)n * 2 * sizeof(float);
+    const size_t smem = icp_smem_bytes<PRUNE, NN_BLK, R>(n, (size_t)n * sizeof(float), threads);
     B2S_REQUIRE(smem <= 227 * 1024, "b2s_icp_batch_ranges: too many beams for shared memory");
     if (smem > 48 * 1024)
-        B2S_CUDA(cudaFuncSetAttribute(icp_batch_kernel<float, R, 2, NN_BLK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        B2S_CUDA(cudaFuncSetAttribute(icp_batch_kernel<float, R, PRUNE, NN_BLK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
     if (threads > 512) {  // (large scans only: the query is not free)
         cudaFuncAttributes fa;
-        B2S_CUDA(cudaFuncGetAttributes(&fa, icp_batch_kernel<float, R, 2, NN_BLK, true>));
+        B2S_CUDA(cudaFuncGetAttributes(&fa, icp_batch_kernel<float, R, PRUNE, NN_BLK, true>));
         B2S_REQUIRE(threads <= fa.maxThreadsPerBlock, "b2s_icp_batch_ranges: scan too large for one CTA's registers");
     }
-    const int use_bulk = ((uintptr_t)tar_r % 16 == 0) && (((size_t)n * sizeof(float)) % 16 == 0);
-    icp_batch_kernel<float, R, 2, NN_BLK, true><<<pairs, threads, smem, (cudaStream_t)stream>>>(
+    const int use_bulk = (((uintptr_t)tar_r % 16 == 0) && (((size_t)n * sizeof(float)) % 16 == 0) ? 1 : 0) | (g_icp_layout << 1);
+    icp_batch_kernel<float, R, PRUNE, NN_BLK, true><<<pairs, threads, smem, (cudaStream_t)stream>>>(
         tar_r, src_r, n, n, max_iter, tol, T_out, iters_out, use_bulk, reinterpret_cast<const double2 *>(beam_cs), clamp);
     B2S_CUDA(cudaGetLastError());
     return B2S_OK;
@@ -673,10 +990,18 @@ template <int R>
 static int launch_icp_ranges_r(const float *tar_r, const float *src_r, const double *beam_cs, double clamp, int pairs,
                                int n, int max_iter, double tol, double *T_out, int32_t *iters_out, void *stream)
 {
+    // (the fused-ingestion form has the two default searches: queued, and the collective one of icp_prune 0..3)
     const int blk = (g_icp_block == 8 || g_icp_block == 16 || g_icp_block == 32) ? g_icp_block : (n <= 600 ? 8 : 16);
-    if (blk == 8) return launch_icp_ranges_rb<R, 8>(tar_r, src_r, beam_cs, clamp, pairs, n, max_iter, tol, T_out, iters_out, stream);
-    if (blk == 16) return launch_icp_ranges_rb<R, 16>(tar_r, src_r, beam_cs, clamp, pairs, n, max_iter, tol, T_out, iters_out, stream);
-    return launch_icp_ranges_rb<R, 32>(tar_r, src_r, beam_cs, clamp, pairs, n, max_iter, tol, T_out, iters_out, stream);
+#define B2S_ICP_GO(B, P) \
+    return launch_icp_ranges_rbp<R, B, P>(tar_r, src_r, beam_cs, clamp, pairs, n, max_iter, tol, T_out, iters_out, stream)
+    if (g_icp_prune == 4) {
+        if (blk == 8) B2S_ICP_GO(8, 4);
+        B2S_ICP_GO(16, 4);
+    }
+    if (blk == 8) B2S_ICP_GO(8, 2);
+    if (blk == 16) B2S_ICP_GO(16, 2);
+    B2S_ICP_GO(32, 2);
+#undef B2S_ICP_GO
 }
 
 static int launch_icp_ranges(const float *tar_r, const float *src_r, const double *beam_cs, double clamp, int pairs, int n,

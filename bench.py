@@ -587,7 +587,7 @@ def bench_icp(args, rank, world, torch, devapi, bdist, synth):
                      "unit": "GB/s", "frac": hbm_bytes / step_s / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                      "note": "compute (FP64 issue) bound by design: each pair reads 8(N+M)+76 B once and iterates on chip, "
                              "so the HBM fraction is expected to be << 1%",
-                     "nn_search": "exact, warp-level + per-lane block pruning (identical correspondences to the N x M brute force)",
+                     "nn_search": "exact, warp-level + per-lane block pruning, surviving (point, block) pairs queued and spread over the lanes (identical correspondences to the N x M brute force)",
                      "brute_force_equivalent_pair_evals_per_s": evals / step_s,
                      "brute_force_equivalent_fp64_tflops": flops / step_s / 1e12,
                      "fp64_peak_tflops_nominal": FP64_PEAK_TFLOPS,
@@ -809,7 +809,7 @@ def main():
     ap.add_argument("--icp-scans", type=int, default=ICP_SCANS)
     ap.add_argument("--grid-variant", type=int, default=0)
     ap.add_argument("--icp-r", type=int, default=0, help="force ICP source points per thread (tuning)")
-    ap.add_argument("--icp-prune", type=int, default=-1, help="0: brute-force NN, 1: per-lane block pruning, 2: warp-level + per-lane (default), 3: warp-level only (tuning)")
+    ap.add_argument("--icp-prune", type=int, default=-1, help="0: brute-force NN, 1: per-lane block pruning, 2: warp-level + per-lane, 3: warp-level only, 4: queued (default) (tuning)")
     ap.add_argument("--merge", default="p2p", choices=["p2p", "nccl"], help="multi-GPU grid merge")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only", default="both", choices=["both", "primary"])

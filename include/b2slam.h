@@ -52,9 +52,11 @@ const char *b2s_status_string(int status);
 const char *b2s_last_error(void); /* thread-local, valid until the next call on this thread */
 int b2s_device_count(int *count);
 /* Kernel-variant switch for benchmarking.  Keys: "grid_variant" 1 = one RED per visit, 2 = warp-aggregated
- * runs, 3 = lean loop, 4 = transposed scratch plane (default); "icp_prune" 0 = brute force, 1 = per-lane
- * block pruning, 2 = warp-level + per-lane (default), 3 = warp-level only; "icp_block" 0 (automatic) / 8 /
- * 16 / 32 targets per pruning block; "icp_src_per_thread" 0 (automatic) / 2 / 3 / 4; "icp_graph" 0 / 1
+ * runs, 3 = lean loop, 4 = transposed scratch plane, 5 = 4 + test-free core phase (default); "icp_prune"
+ * 0 = brute force, 1 = per-lane block pruning, 2 = warp-level + per-lane with whole-warp block visits,
+ * 3 = warp-level only, 4 = both tests, surviving (point, block) pairs queued and spread over the lanes
+ * (default); "icp_block" 0 (automatic) / 8 / 16 / 32 targets per pruning block; "icp_layout" 0 strided /
+ * 1 balanced / 2 automatic point groups per warp; "icp_src_per_thread" 0 (automatic) / 2 / 3 / 4; "icp_graph" 0 / 1
  * (single-pair calls replay a captured CUDA graph); "h2d_chunks" 0 (automatic) .. 16 pipeline depth of the
  * host-buffer calls.  Not part of the reference surface; process-global, set it before the calls it should
  * affect (cached single-pair graphs are re-captured after a change). */

@@ -1,8 +1,14 @@
-"""Minimal ICP launcher for ncu: cfg 2 (360 beams) or cfg 4 shape (1080 beams), 3 launches."""
+"""Minimal ICP launcher for ncu: cfg 2 (360 beams) or cfg 4 shape (1080 beams), 3 launches.
+usage: icp_prof.py [360|1080] [icp_prune] [icp_block]"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-from b2slam import devapi, synth
+from b2slam import _lib, devapi, synth
+
+if len(sys.argv) > 2:
+    _lib.check(_lib.lib().b2s_tune(b"icp_prune", int(sys.argv[2])))
+if len(sys.argv) > 3:
+    _lib.check(_lib.lib().b2s_tune(b"icp_block", int(sys.argv[3])))
 
 if len(sys.argv) > 1 and sys.argv[1] == "1080":
     tar, src, _ = synth.icp_pairs(4001, 8192, 1080)

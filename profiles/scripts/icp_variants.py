@@ -13,7 +13,7 @@ def run(name, tar, src):
     T = torch.empty((P, 3, 3), dtype=torch.float64, device="cuda")
     it = torch.empty(P, dtype=torch.int32, device="cuda")
     ref = None
-    for prune, block in ((0, 0), (2, 8), (2, 16), (3, 8), (3, 16)):
+    for prune, block in ((0, 0), (2, 8), (2, 16), (4, 8), (4, 16)):
         _lib.check(tune(b"icp_prune", prune)); _lib.check(tune(b"icp_block", block))
         for r in ((0,) if prune == 0 else (0, 3)):
             _lib.check(tune(b"icp_src_per_thread", r))
@@ -32,7 +32,7 @@ def run(name, tar, src):
             same = bool(torch.equal(T, ref[0]) and torch.equal(it, ref[1]))
             print("%s prune %d block %2d src/thread %d: %8.3f ms  %10.3e pairs/s  bit-identical to brute force: %s"
                   % (name, prune, block, r, ms, P / ms * 1e3, same), flush=True)
-    tune(b"icp_prune", 2); tune(b"icp_block", 0); tune(b"icp_src_per_thread", 0)
+    tune(b"icp_prune", 4); tune(b"icp_block", 0); tune(b"icp_src_per_thread", 0)
 
 
 xy, _ = synth.room_sequence(9001, 10000, 360)

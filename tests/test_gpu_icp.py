@@ -78,7 +78,7 @@ def test_batched_search_resolves_sqrt_ties_like_the_reference(env):
     z = load_golden("icp_ties.npz")
     L = env.lib.lib()
     try:
-        for prune in (0, 1, 2, 3):
+        for prune in (0, 1, 2, 3, 4):
             assert L.b2s_tune(b"icp_prune", prune) == 0
             for n in range(int(z["icp_count"])):
                 icp = env.b2slam.ICP(max_iter=int(z["icp%d_max_iter" % n]), tolerance=float(z["icp%d_tol" % n]))
@@ -87,7 +87,7 @@ def test_batched_search_resolves_sqrt_ties_like_the_reference(env):
                 assert (it == int(z["icp%d_iters" % n])).all(), (prune, n)
                 np.testing.assert_allclose(T[1], z["icp%d_T" % n], rtol=0, atol=T_ATOL, err_msg="prune %d case %d" % (prune, n))
     finally:
-        L.b2s_tune(b"icp_prune", 2)
+        L.b2s_tune(b"icp_prune", 4)
     # the 10^4 generated single-point cases through the batched kernel with max_iter = 1: the transform of a one-point
     # source is the pure translation onto its match, so T's translation names the chosen target
     tar = np.ascontiguousarray(np.transpose(z["gen_tar"], (0, 2, 1)))            # (P, 2, 6)
@@ -343,12 +343,12 @@ def test_cfg4_shape_sample_vs_oracle(env):
     # every pruning block size gives the brute-force answer bit for bit
     tune = env.lib.lib().b2s_tune
     try:
-        for prune, block in ((0, 0), (1, 16), (1, 32), (2, 8), (2, 16), (2, 32), (3, 8), (3, 16)):
+        for prune, block in ((0, 0), (1, 16), (1, 32), (2, 8), (2, 16), (2, 32), (3, 8), (3, 16), (4, 8), (4, 16)):
             assert tune(b"icp_prune", prune) == 0 and tune(b"icp_block", block) == 0
             T3, it3 = env.icp.process_batch(tar[:256], src[:256])
             assert np.array_equal(it3, it[:256]) and np.array_equal(T3, T[:256]), (prune, block)
     finally:
-        tune(b"icp_prune", 2)
+        tune(b"icp_prune", 4)
         tune(b"icp_block", 0)
 
 
@@ -367,12 +367,12 @@ def test_non_finite_target_points_are_never_matched(env):
     tune = env.lib.lib().b2s_tune
     got = {}
     try:
-        for prune in (0, 1, 2, 3):
+        for prune in (0, 1, 2, 3, 4):
             assert tune(b"icp_prune", prune) == 0
             got[prune] = env.icp.process_batch(tar, src)
     finally:
-        tune(b"icp_prune", 2)
-    for prune in (0, 1, 2, 3):
+        tune(b"icp_prune", 4)
+    for prune in (0, 1, 2, 3, 4):
         T, it = got[prune]
         assert np.array_equal(it, want_it), prune
         np.testing.assert_allclose(T, want_T, rtol=0, atol=T_ATOL)
@@ -444,13 +444,13 @@ def test_random_icp_shapes_vs_oracle(env):
         tar = np.ascontiguousarray(tar.astype(np.float32))
         src = np.ascontiguousarray(src.astype(np.float32))
         want_T, want_it = env.corc.icp_batch(tar, src, 30, 1e-3)
-        for prune in (3, 2, 1, 0):
+        for prune in (4, 3, 2, 1, 0):
             assert env.lib.lib().b2s_tune(b"icp_prune", prune) == 0
             assert env.lib.lib().b2s_tune(b"icp_block", (0, 8, 16, 32)[trial % 4]) == 0
             try:
                 T, it = env.icp.process_batch(tar, src)
             finally:
-                env.lib.lib().b2s_tune(b"icp_prune", 2)
+                env.lib.lib().b2s_tune(b"icp_prune", 4)
                 env.lib.lib().b2s_tune(b"icp_block", 0)
             assert np.array_equal(it, want_it), "trial %d n %d m %d prune %d" % (trial, n, m, prune)
             np.testing.assert_allclose(T, want_T, rtol=0, atol=1e-9 * max(1.0, scale),
