@@ -196,6 +196,14 @@ __device__ __forceinline__ void cta_rigid_fit(const double (&ax)[R], const doubl
 // error <= 2^-22 by the PTX ISA, subnormal inputs flushed to zero) times 1 + 2^-20, plus more than the root of the
 // largest flushed input.  Like the rounded-up exact root it replaces (a range check, a branch and six instructions),
 // this only widens what the search looks at; inf stays inf and NaN stays NaN, which make every skip test false.
+// x << s with PTX semantics: shift counts above 31 give 0 (the C++ operator leaves them undefined).
+__device__ __forceinline__ unsigned shl_sat(unsigned x, unsigned s)
+{
+    unsigned r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s));
+    return r;
+}
+
 __device__ __forceinline__ float sqrt_up(float x)
 {
     float r;
@@ -276,8 +284,8 @@ static __device__ __noinline__ int warp_careful_nearest(double px, double py, co
 // every NN_BLK points (block stride NN_BLK + 1: neighbouring blocks start 4 banks apart), filled with NaN like the
 // tail of a ragged last block -- NaN never wins and never raises the near-tie flag.
 constexpr int QK = 3;                     // queued items (= result slots) per source point
-constexpr int QCAND = 12;                 // candidate blocks of a group of 32 points beyond which it goes collective
-constexpr unsigned NAN_HI = 0x7ff80000u;  // high word of the padding NaN
+constexpr int QCAND = 16;                 // candidate blocks of a group of 32 points beyond which it goes collective
+constexpr int QBLOCKS = 254;              // most blocks per target scan (block number + 1 fits a byte)
 
 // Collective search of one group of 32 points on the padded target layout: the PRUNE == 2 algorithm (warp-level test,
 // per-lane test, whole-warp visits).  Returns the winner's index, bit 31 = near-tie flag.
@@ -372,11 +380,9 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? B2S_ICP_REGS_BLK8 : B2S_ICP_
     };
     constexpr bool QUEUED = PRUNE == 4;
     constexpr int PAD_BLK = QUEUED ? NN_BLK : 0;      // one unused slot after every PAD_BLK targets (queued search)
-    // Per warp: QCAP queue entries (4 bytes) directly followed by QCAP result slots (8 bytes).  A group that turns out
-    // to need the collective search may have queued up to QCAND x 32 entries before it is rolled back; they spill into
-    // the result slots, which nothing reads before phase B has rewritten them.
+    // Per warp: QCAP queue entries (4 bytes) followed by QCAP result slots (8 bytes).
     constexpr int QCAP = R * QK * 32;
-    static_assert(!QUEUED || QCAND * 32 <= QK * 32 + 2 * QCAP, "queue overrun must stay inside the warp's result slots");
+    static_assert(QK == 3, "phase C merges exactly three result slots");
     const int nblk = (m + NN_BLK - 1) / NN_BLK;
     auto TI = [](int j) { return PAD_BLK ? j + j / (PAD_BLK ? PAD_BLK : 1) : j; };  // index into tar[]
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -582,10 +588,10 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? B2S_ICP_REGS_BLK8 : B2S_ICP_
                 const float wxf = __double2float_rn(wx), wyf = __double2float_rn(wy);
                 const float gE = __fmul_ru(__fadd_ru(gmax, __fmul_ru(__fadd_ru(fabsf(wxf), fabsf(wyf)), 2.3841858e-7f)),
                                            1.000002f);
-                const unsigned start = total;
-                // item: point slot (12 bits) | block (10 bits) << 12 | result slot r * QK + k (5 bits) << 22
+                // item: point slot (12 bits) | block (10 bits) << 12 | result slot r * QK + k (4 bits) << 22
                 const unsigned item0 = (unsigned)(tid + r * blockDim.x) | ((unsigned)(r * QK) << 22);
-                unsigned item = item0;
+                unsigned mine = 0;  // byte k: 1 + the k-th block this point needs (ascending)
+                unsigned sh = 0;    // 8 x the number of blocks it needs (shl_sat drops what does not fit)
                 int ncand = 0;
                 for (int base = 0; base < nblk; base += 32) {
                     bool keep = false;
@@ -597,7 +603,7 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? B2S_ICP_REGS_BLK8 : B2S_ICP_
                     }
                     unsigned todo = __ballot_sync(0xffffffffu, keep);
                     ncand += __popc(todo);
-                    if (ncand > QCAND) break;  // (the queue has room for QCAND candidate blocks x 32 points per group)
+                    if (ncand > QCAND) break;  // a bound this loose: the collective search wastes less
                     while (todo) {  // two candidate blocks per pass (independent loads and tests)
                         const int b0 = base + __ffs(todo) - 1;
                         todo &= todo - 1;
@@ -609,20 +615,28 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? B2S_ICP_REGS_BLK8 : B2S_ICP_
                         const float reach0 = __fadd_ru(c0.z, suE), reach1 = __fadd_ru(c1.z, suE);
                         const bool need0 = real && !(fmaf(y0, y0, x0 * x0) > __fmul_ru(reach0, reach0));
                         const bool need1 = real && two && !(fmaf(y1, y1, x1 * x1) > __fmul_ru(reach1, reach1));
-                        const unsigned m0 = __ballot_sync(0xffffffffu, need0), m1 = __ballot_sync(0xffffffffu, need1);
-                        if (need0) q[total + __popc(m0 & lt)] = item + ((unsigned)b0 << 12);
-                        item += need0 ? (1u << 22) : 0u;
-                        total += __popc(m0);
-                        if (need1) q[total + __popc(m1 & lt)] = item + ((unsigned)b1 << 12);
-                        item += need1 ? (1u << 22) : 0u;
-                        total += __popc(m1);
+                        if (need0) {
+                            mine |= shl_sat((unsigned)b0 + 1u, sh);
+                            sh += 8;
+                        }
+                        if (need1) {
+                            mine |= shl_sat((unsigned)b1 + 1u, sh);
+                            sh += 8;
+                        }
                     }
                 }
-                const int c = (int)((item - item0) >> 22);
+                const int c = (int)(sh >> 3);
                 // too many candidate blocks, or a point that needs more blocks than it has result slots
                 if (ncand > QCAND || __any_sync(0xffffffffu, c > QK)) {
-                    total = start;
                     collective |= 1u << r;
+                } else {
+                    static_assert(QK <= 3, "the two ballots below count up to 3 items per point");
+                    const unsigned c0 = __ballot_sync(0xffffffffu, (c & 1) != 0), c1 = __ballot_sync(0xffffffffu, (c & 2) != 0);
+                    const unsigned at = total + __popc(c0 & lt) + 2 * __popc(c1 & lt);
+#pragma unroll
+                    for (int k = 0; k < QK; ++k)
+                        if (k < c) q[at + k] = item0 + ((((mine >> (8 * k)) & 255u) - 1u) << 12) + ((unsigned)k << 22);
+                    total += __popc(c0) + 2 * __popc(c1);
                 }
                 cnt[r] = c;
             }
@@ -664,7 +678,8 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? B2S_ICP_REGS_BLK8 : B2S_ICP_
                 if (valid) res[(e >> 22) * 32 + (e & 31u)] = make_uint2(lo[0], b | (near ? 0x80000000u : 0u));
             }
             __syncwarp();
-            // ---- phase C: every point merges its own results, blocks ascending
+            // ---- phase C: every point merges its own (up to QK) results; branch-free, the two smallest masked keys
+            // decide the near-tie flag exactly as inside a block
             unsigned flagged = 0;  // bit r: point r of this lane is a near tie
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -673,24 +688,22 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? B2S_ICP_REGS_BLK8 : B2S_ICP_
                     const unsigned w = collective_nearest_padded<NN_BLK>(sx[r], sy[r], r < count, arg[r], tar, bnd, nblk, lane);
                     arg[r] = (int)(w & 0x7fffffffu);
                     near = (w >> 31) != 0;
-                } else if (__all_sync(0xffffffffu, cnt[r] <= 1)) {  // the usual case: one block per point
-                    const uint2 v = res[(r * QK) * 32 + lane];
-                    const bool any = cnt[r] != 0;
-                    arg[r] = any ? (int)((v.y & 0x3ffu) * NN_BLK + (v.x & KMASK)) : 0;
-                    near = any && ((v.y >> 31) != 0 || v.x >= 0x7ff00000u);  // (nothing finite in the block: let the careful search decide)
                 } else {
-                    unsigned bh = 0x7ff00000u;
-                    int bj = 0;
-                    for (int k = 0; k < cnt[r]; ++k) {
-                        const uint2 v = res[(r * QK + k) * 32 + lane];
-                        const unsigned fh = v.x & ~KMASK;
-                        near |= (v.y >> 31) != 0 || (fh - bh + NN_BLK) <= 2u * NN_BLK;
-                        if (fh < bh) {
-                            bh = fh;
-                            bj = (int)((v.y & 0x3ffu) * NN_BLK + (v.x & KMASK));
-                        }
+                    const int c = cnt[r];
+                    uint2 v[QK];
+                    unsigned f[QK];
+#pragma unroll
+                    for (int k = 0; k < QK; ++k) {
+                        v[k] = res[(r * QK + k) * 32 + lane];
+                        f[k] = k < c ? (v[k].x & ~KMASK) : 0xffffffffu;
+                        near |= k < c && (v[k].y >> 31) != 0;
                     }
-                    arg[r] = bj;
+                    const unsigned best = min(f[0], min(f[1], f[2]));
+                    const unsigned second = max(min(f[0], f[1]), min(max(f[0], f[1]), f[2]));  // median of three
+                    const uint2 win = f[0] == best ? v[0] : (f[1] == best ? v[1] : v[2]);
+                    arg[r] = c ? (int)((win.y & 0x3ffu) * NN_BLK + (win.x & KMASK)) : 0;
+                    // two blocks' minima less than two mask units apart, or nothing finite at all: the careful search decides
+                    near |= c && (second - best <= (unsigned)NN_BLK || best >= 0x7ff00000u);
                 }
                 flagged |= (near && r < count) ? (1u << r) : 0u;
             }
@@ -915,16 +928,16 @@ static int launch_icp_r(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_s
 #define B2S_ICP_GO(P, B) \
     return launch_icp_rp<TIn, R, P, B>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream)
     if (g_icp_prune && fits) {
-        if (g_icp_prune == 4) {
-            if (blk == 8) B2S_ICP_GO(4, 8);
-            B2S_ICP_GO(4, 16);
+        if (g_icp_prune == 4) {  // (block numbers travel in one byte; beyond that the collective search takes over)
+            if (blk == 8 && (n_tar + 7) / 8 <= QBLOCKS) B2S_ICP_GO(4, 8);
+            if ((n_tar + 15) / 16 <= QBLOCKS) B2S_ICP_GO(4, 16);
         }
         if (g_icp_prune == 3) {
             if (blk == 8) B2S_ICP_GO(3, 8);
             if (blk == 16) B2S_ICP_GO(3, 16);
             B2S_ICP_GO(3, 32);
         }
-        if (g_icp_prune == 2) {
+        if (g_icp_prune == 2 || g_icp_prune == 4) {
             if (blk == 8) B2S_ICP_GO(2, 8);
             if (blk == 16) B2S_ICP_GO(2, 16);
             B2S_ICP_GO(2, 32);
@@ -995,8 +1008,8 @@ static int launch_icp_ranges_r(const float *tar_r, const float *src_r, const dou
 #define B2S_ICP_GO(B, P) \
     return launch_icp_ranges_rbp<R, B, P>(tar_r, src_r, beam_cs, clamp, pairs, n, max_iter, tol, T_out, iters_out, stream)
     if (g_icp_prune == 4) {
-        if (blk == 8) B2S_ICP_GO(8, 4);
-        B2S_ICP_GO(16, 4);
+        if (blk == 8 && (n + 7) / 8 <= QBLOCKS) B2S_ICP_GO(8, 4);
+        if ((n + 15) / 16 <= QBLOCKS) B2S_ICP_GO(16, 4);
     }
     if (blk == 8) B2S_ICP_GO(8, 2);
     if (blk == 16) B2S_ICP_GO(16, 2);

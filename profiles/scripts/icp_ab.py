@@ -36,7 +36,7 @@ def run(name, tar, src, combos):
                  float(T.sum()), int(it.sum())), flush=True)
 
 
-combos = [(p, b, l) for p in (2, 4) for b in (8, 16) for l in (0, 1)]
+combos = [(p, b, l) for p in (2, 4) for b in (8, 16) for l in ((0, 1) if os.environ.get('B2S_AB_LAYOUTS') else (2,))]
 xy, _ = synth.room_sequence(9001, 10000, 360)
 run("cfg2/360 ", torch.from_numpy(np.ascontiguousarray(xy[:-1])).cuda(), torch.from_numpy(np.ascontiguousarray(xy[1:])).cuda(), combos)
 tar, src, _ = synth.icp_pairs(4001, 16384, 1080)
