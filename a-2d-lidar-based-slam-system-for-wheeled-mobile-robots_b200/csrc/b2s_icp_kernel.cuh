@@ -41,7 +41,7 @@ constexpr int SUM_PAD = 10;                          // doubles per warp slot (9
 // per block); rounded to 16.
 __host__ __device__ inline size_t icp_stage_bytes(size_t in_bytes, int nblk)
 {
-    const size_t b = (size_t)nblk * 16;
+    const size_t b = ((size_t)nblk + (nblk + 31) / 32) * 16;  // + one bound per 32 blocks (queued search)
     return ((in_bytes > b ? in_bytes : b) + 15) & ~(size_t)15;
 }
 
@@ -285,6 +285,7 @@ static __device__ __noinline__ int warp_careful_nearest(double px, double py, co
 // tail of a ragged last block -- NaN never wins and never raises the near-tie flag.
 constexpr int QK = 3;                     // queued items (= result slots) per source point
 constexpr int QCAND = 16;                 // candidate blocks of a group of 32 points beyond which it goes collective
+constexpr int QSUP_MIN = 64;              // block count above which the warp test gets a second level (a bound per 32 blocks)
 constexpr int QBLOCKS = 254;              // most blocks per target scan (block number + 1 fits a byte)
 
 // Collective search of one group of 32 points on the padded target layout: the PRUNE == 2 algorithm (warp-level test,
@@ -360,7 +361,7 @@ static __device__ __noinline__ unsigned collective_nearest_padded(double px, dou
 // and the points are formed here exactly as laserToNumpy does ([ICP]:216-229, [SLAM]:115-123): float64
 // (cos a * r, sin a * r) with the beam table computed by the host's NumPy, +inf -> clamp when clamp > 0.
 template <typename TIn, int R, int PRUNE, int NN_BLK, bool RANGES = false>
-__global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? B2S_ICP_REGS_BLK8 : B2S_ICP_REGS_BLK16) : 104) icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__restrict__ src_xy, int n,
+__global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 && PRUNE != 5 ? B2S_ICP_REGS_BLK8 : B2S_ICP_REGS_BLK16) : 104) icp_batch_kernel(const TIn *__restrict__ tar_xy, const TIn *__restrict__ src_xy, int n,
                                  int m, int max_iter, double tol, double *__restrict__ T_out,
                                  int32_t *__restrict__ iters_out, int use_bulk,
                                  const double2 *__restrict__ beam_cs = nullptr, double clamp = 0.0)
@@ -378,7 +379,8 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? B2S_ICP_REGS_BLK8 : B2S_ICP_
             y = (double)scan[count + i];
         }
     };
-    constexpr bool QUEUED = PRUNE == 4;
+    constexpr bool QUEUED = PRUNE >= 4;  // 5: with the second level of the warp test (a bound per 32 blocks)
+    constexpr bool QSUP = PRUNE == 5;
     constexpr int PAD_BLK = QUEUED ? NN_BLK : 0;      // one unused slot after every PAD_BLK targets (queued search)
     // Per warp: QCAP queue entries (4 bytes) followed by QCAP result slots (8 bytes).
     constexpr int QCAP = R * QK * 32;
@@ -506,6 +508,34 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? B2S_ICP_REGS_BLK8 : B2S_ICP_
             bnd[b] = make_float4(cfx, cfy, __fmul_ru(__double2float_ru(rad), 1.000002f), 0.0f);  // (1 + 2^-19) folded in
         }
         __syncthreads();
+        if (QSUP) {
+            // one more level for the warp test: a circle around every 32 consecutive blocks (centre: the float32 centre of
+            // their centres' bounding box, radius: farthest block centre + that block's radius, rounded up), so that a warp
+            // looks only at the groups of 32 blocks it can reach.  Same argument, same margins as for a block.
+            float4 *sup = bnd + nblk;
+            const int lane_ = tid & 31;
+            for (int g = tid >> 5; g < (nblk + 31) / 32; g += (int)(blockDim.x >> 5)) {  // one warp per group, one block per lane
+                const int b = min(nblk - 1, g * 32 + lane_);  // (the tail lanes repeat the last block)
+                const float4 c = bnd[b];
+                float x0 = c.x, x1 = c.x, y0 = c.y, y1 = c.y;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+                    y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+                }
+                const float cfx = 0.5f * x0 + 0.5f * x1, cfy = 0.5f * y0 + 0.5f * y1;  // (any point serves as a centre)
+                const double dx = (double)c.x - (double)cfx, dy = (double)c.y - (double)cfy;
+                const double d = sqrt(fma(dy, dy, dx * dx)) * 1.000000001 + (double)c.z;
+                // rounded up to float32; NaN / inf (a block that is never skipped, a non-finite centre) order above all
+                // finite values as unsigned bit patterns of non-negative floats, so one REDUX takes the maximum
+                float df = __fmul_ru(__double2float_ru(d), 1.000002f);
+                if (!(df >= 0.0f) || !(fabsf(cfx) < INFINITY) || !(fabsf(cfy) < INFINITY)) df = INFINITY;
+                const float reach = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(df)));
+                if (lane_ == 0)
+                    sup[g] = make_float4(reach < INFINITY ? cfx : 0.0f, reach < INFINITY ? cfy : 0.0f, reach, 0.0f);
+            }
+            __syncthreads();
+        }
     }
 
     // previous match of every source point; seeds the pruning bound (first pass: the target with the
@@ -593,7 +623,20 @@ __global__ void __maxnreg__(R <= 3 ? (NN_BLK == 8 ? B2S_ICP_REGS_BLK8 : B2S_ICP_
                 unsigned mine = 0;  // byte k: 1 + the k-th block this point needs (ascending)
                 unsigned sh = 0;    // 8 x the number of blocks it needs (shl_sat drops what does not fit)
                 int ncand = 0;
-                for (int base = 0; base < nblk; base += 32) {
+                unsigned groups = 0xffffffffu >> (32 - (nblk + 31) / 32);  // bit g: blocks 32 g .. 32 g + 31
+                if (QSUP) {  // (a template parameter: with two groups or fewer the extra level costs more than it saves)
+                    bool far = false;
+                    if (lane < (nblk + 31) / 32) {  // lane g: can the warp reach any block of group g ?
+                        const float4 cs = bnd[nblk + lane];
+                        const float cxd = wxf - cs.x, cyd = wyf - cs.y;
+                        const float reach = __fadd_ru(cs.z, gE);
+                        far = fmaf(cyd, cyd, cxd * cxd) > __fmul_ru(reach, reach);
+                    }
+                    groups &= ~__ballot_sync(0xffffffffu, far);
+                }
+                while (groups) {
+                    const int base = (__ffs(groups) - 1) * 32;
+                    groups &= groups - 1;
                     bool keep = false;
                     if (base + lane < nblk) {
                         const float4 cb = bnd[base + lane];
@@ -879,7 +922,7 @@ static size_t icp_smem_bytes(int n_tar, size_t in_bytes, int threads)
 {
     const size_t nblk = ((size_t)n_tar + NN_BLK - 1) / NN_BLK;
     size_t bytes = 16 + icp_scratch_doubles(threads / 32) * sizeof(double) + icp_stage_bytes(in_bytes, (int)nblk);
-    if (PRUNE == 4) {
+    if (PRUNE >= 4) {
         bytes += nblk * (NN_BLK + 1) * sizeof(double2);                       // padded targets
         bytes += (size_t)R * threads * sizeof(double2);                       // moved source points
         bytes += (size_t)(threads / 32) * (size_t)(R * QK * 32) * (sizeof(unsigned) + sizeof(uint2));  // queues + results
@@ -929,8 +972,14 @@ static int launch_icp_r(const TIn *tar_xy, const TIn *src_xy, int pairs, int n_s
     return launch_icp_rp<TIn, R, P, B>(tar_xy, src_xy, pairs, n_src, n_tar, max_iter, tol, T_out, iters_out, stream)
     if (g_icp_prune && fits) {
         if (g_icp_prune == 4) {  // (block numbers travel in one byte; beyond that the collective search takes over)
-            if (blk == 8 && (n_tar + 7) / 8 <= QBLOCKS) B2S_ICP_GO(4, 8);
-            if ((n_tar + 15) / 16 <= QBLOCKS) B2S_ICP_GO(4, 16);
+            if (blk == 8 && (n_tar + 7) / 8 <= QBLOCKS) {
+                if ((n_tar + 7) / 8 > QSUP_MIN) B2S_ICP_GO(5, 8);
+                B2S_ICP_GO(4, 8);
+            }
+            if ((n_tar + 15) / 16 <= QBLOCKS) {
+                if ((n_tar + 15) / 16 > QSUP_MIN) B2S_ICP_GO(5, 16);
+                B2S_ICP_GO(4, 16);
+            }
         }
         if (g_icp_prune == 3) {
             if (blk == 8) B2S_ICP_GO(3, 8);
@@ -1004,12 +1053,18 @@ static int launch_icp_ranges_r(const float *tar_r, const float *src_r, const dou
                                int n, int max_iter, double tol, double *T_out, int32_t *iters_out, void *stream)
 {
     // (the fused-ingestion form has the two default searches: queued, and the collective one of icp_prune 0..3)
-    const int blk = (g_icp_block == 8 || g_icp_block == 16 || g_icp_block == 32) ? g_icp_block : (n <= 600 ? 8 : 16);
+    const int blk = (g_icp_block == 8 || g_icp_block == 16 || g_icp_block == 32) ? g_icp_block : (g_icp_prune == 4 || n <= 600 ? 8 : 16);
 #define B2S_ICP_GO(B, P) \
     return launch_icp_ranges_rbp<R, B, P>(tar_r, src_r, beam_cs, clamp, pairs, n, max_iter, tol, T_out, iters_out, stream)
     if (g_icp_prune == 4) {
-        if (blk == 8 && (n + 7) / 8 <= QBLOCKS) B2S_ICP_GO(8, 4);
-        if ((n + 15) / 16 <= QBLOCKS) B2S_ICP_GO(16, 4);
+        if (blk == 8 && (n + 7) / 8 <= QBLOCKS) {
+            if ((n + 7) / 8 > QSUP_MIN) B2S_ICP_GO(8, 5);
+            B2S_ICP_GO(8, 4);
+        }
+        if ((n + 15) / 16 <= QBLOCKS) {
+            if ((n + 15) / 16 > QSUP_MIN) B2S_ICP_GO(16, 5);
+            B2S_ICP_GO(16, 4);
+        }
     }
     if (blk == 8) B2S_ICP_GO(8, 2);
     if (blk == 16) B2S_ICP_GO(16, 2);
