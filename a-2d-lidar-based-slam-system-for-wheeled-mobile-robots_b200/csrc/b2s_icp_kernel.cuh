@@ -6,7 +6,9 @@
 // with a 1-D bulk async copy + mbarrier), then runs up to max_iter iterations of
 //   nearest neighbour               (exact: the index of the N*M brute force with strict '<' in ascending j, i.e.
 //                                    the lowest index wins ties like the reference loop, found with a warp-level
-//                                    and a per-lane block-pruning test in front; PRUNE = 0 is the plain brute force)
+//                                    and a per-lane block-pruning test in front.  PRUNE = 4 / 5, the default, queues
+//                                    the (point, block) pairs that survive both tests and spreads them over the lanes;
+//                                    PRUNE = 1..3 evaluate a surviving block with the whole warp; 0 is the brute force)
 //   centroid + 2x2 cross-covariance (ONE reduction about fixed shifts; the reference centres, then multiplies)
 //   closed-form proper rotation     ((c, s) = (W00+W11, W10-W01) / norm == U.Vt with the W9 reflection fix)
 //   src <- T.src, mean-error stop rule
@@ -15,8 +17,8 @@
 // Numerics: everything is float64, like the reference.  B200 (sm_100a) issues FP64 at half the
 // FP32 rate, and an FP32 search would need a second-best tracker plus a float64 re-check of
 // near ties to keep correspondences identical, which costs about the same issue slots; see
-// DESIGN.md "ICP numerics".  Source points live in registers (R per thread) for the whole solve;
-// targets live in shared memory as double2 and are read as warp broadcasts.
+// DESIGN.md "ICP numerics".  Source points live in registers (R per thread) for the whole solve (the queued search
+// keeps a copy of the moved points in shared memory); targets live in shared memory as double2.
 //
 // This header holds the kernel and its launch logic; b2s_icp_f32.cu / b2s_icp_f64.cu instantiate it per input
 // type (two translation units so the instances compile in parallel).
@@ -269,7 +271,7 @@ static __device__ __noinline__ int warp_careful_nearest(double px, double py, co
         }                                                   \
     } while (0)
 
-// ---------------------------------------------------------------- the queued search (PRUNE == 4)
+// ---------------------------------------------------------------- the queued search (PRUNE == 4, 5)
 //
 // The collective search (PRUNE 1..3) evaluates a block with the whole warp as soon as ONE of its 32 source points needs
 // it: 32 consecutive points need the union of ~5 blocks, each point only 1-2 of them, so two thirds of the distance
