@@ -381,6 +381,49 @@ def test_non_finite_target_points_are_never_matched(env):
 
 # ----------------------------------------------------------------------------- adjacent steps
 
+def test_queued_search_overflow_paths_equal_brute_force(env):
+    """The queued search (icp_prune 4) hands a group of 32 points to the collective search when a point needs more than
+    three blocks or the group has more than 16 candidate blocks, takes a second level of bounds above 64 blocks, and falls
+    back to 16-target blocks above 254 blocks.  Shapes that force each of those, float32 and float64 clouds, ragged last
+    blocks: T and the iteration counts equal the brute force bit for bit, and the oracle within tolerance."""
+    rng = np.random.Generator(np.random.PCG64(4242))
+    cases = []
+    # (a) a tight cluster: every block is within reach of every point -> every group overflows its queue
+    tar = rng.normal(0, 0.02, (3, 2, 333)); src = tar[:, :, rng.integers(0, 333, 301)] + rng.normal(0, 0.005, (3, 2, 301))
+    cases.append(("cluster", tar, src))
+    # (b) a coarse first bound: the source is the target rotated by 0.5 rad, so the first iterations need many blocks
+    ang = np.linspace(-np.pi, np.pi, 700); r = 5 + np.sin(3 * ang)
+    tar = np.stack([r * np.cos(ang), r * np.sin(ang)])[None].repeat(2, 0) + rng.normal(0, 0.01, (2, 2, 700))
+    c, s_ = np.cos(0.5), np.sin(0.5)
+    src = np.stack([c * tar[:, 0] - s_ * tar[:, 1], s_ * tar[:, 0] + c * tar[:, 1]], axis=1)[:, :, ::-1][:, :, :650].copy()
+    cases.append(("rotated", tar, src))
+    # (c) 1501 targets: 188 blocks of 8 -> second level of the warp test, ragged last block; (d) 2301: 16-target blocks
+    for m, n in ((1501, 1490), (2301, 2304)):
+        ang = np.linspace(-np.pi, np.pi, m); r = 6 + 2 * np.sin(2 * ang + 0.3)
+        tar = np.stack([r * np.cos(ang), r * np.sin(ang)])[None] + rng.normal(0, 0.01, (1, 2, m))
+        pick = np.sort(rng.integers(0, m, n))
+        c, s_ = np.cos(0.03), np.sin(0.03)
+        src = np.stack([c * tar[:, 0, pick] - s_ * tar[:, 1, pick] + 0.05, s_ * tar[:, 0, pick] + c * tar[:, 1, pick] - 0.04], axis=1)
+        cases.append(("large%d" % m, tar, src + rng.normal(0, 0.01, src.shape)))
+    tune = env.lib.lib().b2s_tune
+    for name, tar, src in cases:
+        for dtype in (np.float32, np.float64):
+            t, s = np.ascontiguousarray(tar.astype(dtype)), np.ascontiguousarray(src.astype(dtype))
+            got = {}
+            try:
+                for prune in ((0, 4) if name.startswith("large") or dtype is np.float32 else (2, 4)):
+                    assert tune(b"icp_prune", prune) == 0
+                    got[prune] = env.icp.process_batch(t, s)
+            finally:
+                tune(b"icp_prune", 4)
+            (Ta, ia), (Tb, ib) = got.values()
+            assert np.array_equal(ia, ib) and np.array_equal(Ta, Tb), (name, dtype)
+            if t.shape[2] <= 800:
+                want_T, want_it = env.corc.icp_batch(t, s, 30, 1e-3)
+                assert np.array_equal(ib, want_it), (name, dtype)
+                np.testing.assert_allclose(Tb, want_T, rtol=0, atol=T_ATOL, err_msg=name)
+
+
 def test_pose_chain_parallel_prefix_vs_sequential_loop(env):
     from b2slam import scan
     from oracle import pyref
