@@ -568,6 +568,8 @@ def bench_icp(args, rank, world, torch, devapi, bdist, synth):
     # streaming form of the sequence call: submit stream k + 1, then wait for stream k (two in flight)
     stream_steps = max(10, min(args.steps, 40))
     seq_stream_s = time_host_stream(lambda: icp.submit_sequence(h_seq), stream_steps, bdist, torch)
+    # ... and of the raw-range call: half the bytes per scan, which is what counts once several ranks share the host
+    raw_stream_s = time_host_stream(lambda: icp.submit_scans(h_rng, -math.pi, math.pi), stream_steps, bdist, torch)
 
     peak, peak_src = measured_peaks()
     import ctypes
@@ -601,6 +603,11 @@ def bench_icp(args, rank, world, torch, devapi, bdist, synth):
                 "h2d_bytes_per_step": int(h_seq.nbytes), "d2h_bytes_per_step": P * 76,
                 "api": "ICP.submit_sequence + IcpTicket.wait (b2s_icp_submit_sequence / b2s_icp_wait), two streams in flight",
                 "ms_per_step": seq_stream_s / stream_steps * 1e3},
+        "e2e_streaming_raw_scans": {"value": world * P * stream_steps / raw_stream_s, "unit": "pairs/s",
+                                    "h2d_bytes_per_step": int(h_rng.nbytes), "d2h_bytes_per_step": P * 76,
+                                    "api": "ICP.submit_scans + IcpTicket.wait (b2s_icp_submit_scans / b2s_icp_wait), two "
+                                           "streams in flight, raw ranges in (laserToNumpy inside the kernel)",
+                                    "ms_per_step": raw_stream_s / stream_steps * 1e3},
         "e2e_blocking_call": {"value": world * P * e2e_steps / e2e_s, "unit": "pairs/s",
                               "h2d_bytes_per_step": int(h_seq.nbytes), "d2h_bytes_per_step": P * 76,
                               "api": "ICP.process_sequence (b2s_icp_process_sequence)", "ms_per_step": e2e_s / e2e_steps * 1e3},
@@ -878,7 +885,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": prim["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": prim["dtype"],
             "data": "synthetic", "config": prim["config"], "roofline": prim["roofline"], "e2e": prim["e2e"],
-            **{k: prim[k] for k in ("e2e_blocking_call", "e2e_fused_ingestion", "e2e_pair_form", "merge_bit_identical",
+            **{k: prim[k] for k in ("e2e_blocking_call", "e2e_fused_ingestion", "e2e_pair_form", "e2e_streaming_raw_scans", "merge_bit_identical",
                                     "merge_check") if k in prim},
             "gpu_launches": sum(r["gpu_launches"] for r in results.values()), "clocks": prim["clocks"],
             "cpu_baseline": cpu.get(order[0]),
