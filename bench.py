@@ -19,8 +19,10 @@ the streaming form of the raw-scan call (dist.ShardedMappingP2P.submit_scans + T
 upload of step k+1 overlaps the read-back of step k; ranges + poses, 4 B per beam); beside it `e2e_blocking_call`
 (Mapping.update_batch on world-frame endpoints, one call at a time; N > 1: ShardedMappingP2P.update_batch) and
 `e2e_fused_ingestion` (the blocking raw-scan call Mapping.update_scans / ShardedMappingP2P.update_scans).  For the ICP
-`e2e` is ICP.process_sequence (cfg 2 is a scan stream), with `e2e_fused_ingestion` (ICP.process_scans, raw ranges)
-and `e2e_pair_form` (ICP.process_batch on explicit pairs, twice the bytes).
+`e2e` is the streaming raw-range call too (ICP.submit_scans + IcpTicket.wait: cfg 2 is a scan stream), with
+`e2e_streaming_sequence` (the same on float32 points, twice the bytes: PCIe-bound), `e2e_blocking_call`
+(ICP.process_sequence), `e2e_fused_ingestion` (ICP.process_scans, blocking) and `e2e_pair_form` (ICP.process_batch on
+explicit pairs, four times the bytes).
 
 With N > 1 ranks the line also carries `merge_bit_identical`: after the timed region a reduced batch per rank goes
 through the same peer-memory merge, every rank ray-casts ALL ranks' scans in one pass by itself, and the merged map
@@ -599,15 +601,16 @@ def bench_icp(args, rank, world, torch, devapi, bdist, synth):
                                   "equivalent rate is not a utilisation; fp64_pipe_executed is: the share of the FP64 pipe and "
                                   "the executed warp instructions of this kernel from the committed ncu capture "
                                   "(profiles/r2/ncu_stamps.json, null when the kernel source changed since)"},
-        "e2e": {"value": world * P * stream_steps / seq_stream_s, "unit": "pairs/s",
-                "h2d_bytes_per_step": int(h_seq.nbytes), "d2h_bytes_per_step": P * 76,
-                "api": "ICP.submit_sequence + IcpTicket.wait (b2s_icp_submit_sequence / b2s_icp_wait), two streams in flight",
-                "ms_per_step": seq_stream_s / stream_steps * 1e3},
-        "e2e_streaming_raw_scans": {"value": world * P * stream_steps / raw_stream_s, "unit": "pairs/s",
-                                    "h2d_bytes_per_step": int(h_rng.nbytes), "d2h_bytes_per_step": P * 76,
-                                    "api": "ICP.submit_scans + IcpTicket.wait (b2s_icp_submit_scans / b2s_icp_wait), two "
-                                           "streams in flight, raw ranges in (laserToNumpy inside the kernel)",
-                                    "ms_per_step": raw_stream_s / stream_steps * 1e3},
+        "e2e": {"value": world * P * stream_steps / raw_stream_s, "unit": "pairs/s",
+                "h2d_bytes_per_step": int(h_rng.nbytes), "d2h_bytes_per_step": P * 76,
+                "api": "ICP.submit_scans + IcpTicket.wait (b2s_icp_submit_scans / b2s_icp_wait), two streams in flight: raw "
+                       "ranges in (what the sensor delivers; laserToNumpy inside the kernel), T and iteration counts out",
+                "ms_per_step": raw_stream_s / stream_steps * 1e3},
+        "e2e_streaming_sequence": {"value": world * P * stream_steps / seq_stream_s, "unit": "pairs/s",
+                                   "h2d_bytes_per_step": int(h_seq.nbytes), "d2h_bytes_per_step": P * 76,
+                                   "api": "ICP.submit_sequence + IcpTicket.wait (b2s_icp_submit_sequence / b2s_icp_wait), "
+                                          "two streams in flight, float32 points in (PCIe-bound: 28.8 MB per stream)",
+                                   "ms_per_step": seq_stream_s / stream_steps * 1e3},
         "e2e_blocking_call": {"value": world * P * e2e_steps / e2e_s, "unit": "pairs/s",
                               "h2d_bytes_per_step": int(h_seq.nbytes), "d2h_bytes_per_step": P * 76,
                               "api": "ICP.process_sequence (b2s_icp_process_sequence)", "ms_per_step": e2e_s / e2e_steps * 1e3},
@@ -885,7 +888,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": prim["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": prim["dtype"],
             "data": "synthetic", "config": prim["config"], "roofline": prim["roofline"], "e2e": prim["e2e"],
-            **{k: prim[k] for k in ("e2e_blocking_call", "e2e_fused_ingestion", "e2e_pair_form", "e2e_streaming_raw_scans", "merge_bit_identical",
+            **{k: prim[k] for k in ("e2e_blocking_call", "e2e_fused_ingestion", "e2e_pair_form", "e2e_streaming_sequence", "merge_bit_identical",
                                     "merge_check") if k in prim},
             "gpu_launches": sum(r["gpu_launches"] for r in results.values()), "clocks": prim["clocks"],
             "cpu_baseline": cpu.get(order[0]),
