@@ -59,6 +59,13 @@ def test_argument_validation_needs_no_device():
     assert L.b2s_icp_batch_f32(None, None, 1, 0, 8, 30, 1e-3, None, None, None) == _lib.ERR_INVALID_ARG
     assert L.b2s_tune(b"grid_variant", 7) == _lib.ERR_INVALID_ARG
     assert L.b2s_tune(b"nope", 1) == _lib.ERR_INVALID_ARG
+    # the ICP search switches: every documented value is accepted, the next one is not; the defaults are restored
+    for key, good, bad, default in ((b"icp_prune", (0, 1, 2, 3, 4), 5, 4), (b"icp_block", (0, 8, 16, 32), 12, 0),
+                                    (b"icp_layout", (0, 1, 2), 3, 2), (b"icp_src_per_thread", (0, 2, 3, 4), 1, 0)):
+        for v in good:
+            assert L.b2s_tune(key, v) == 0, (key, v)
+        assert L.b2s_tune(key, bad) == _lib.ERR_INVALID_ARG, key
+        assert L.b2s_tune(key, default) == 0
 
 
 @pytest.mark.skipif(_lib.device_count() > 0, reason="only meaningful without a GPU")
